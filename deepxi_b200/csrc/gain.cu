@@ -1,0 +1,104 @@
+// Element-wise map / gain kernels (HBM-streaming).
+#include "gain_math.cuh"
+
+namespace dxi {
+
+// x_bar [n_rows, NB] -> xi_hat / gain / ibm.  One thread per element, 4 elements per thread in
+// flight (grid-stride by whole-grid steps keeps every warp access a contiguous 128 B).
+template <int UNROLL>
+__global__ void __launch_bounds__(256) map_gain_kernel(const float* __restrict__ xbar, const float* __restrict__ mu,
+                                                       const float* __restrict__ sigma, int64_t n, int n_bins,
+                                                       int gtype, float* __restrict__ xi_out,
+                                                       float* __restrict__ g_out, uint8_t* __restrict__ ibm_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * UNROLL) {
+    float xb[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      int64_t i = base + u * stride;
+      xb[u] = i < n ? __ldcs(xbar + i) : 0.5f;
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      int64_t i = base + u * stride;
+      if (i >= n) continue;
+      int k = (int)(i % n_bins);
+      float xi = xi_from_xbar(xb[u], __ldg(mu + k), __ldg(sigma + k));
+      if (xi_out) __stcs(xi_out + i, xi);
+      if (g_out) __stcs(g_out + i, gfunc_eval(gtype, xi, __fadd_rn(xi, 1.0f)));   // gamma_hat = xi_hat + 1 (inp_tgt.py:212)
+      if (ibm_out) ibm_out[i] = xi > 1.0f ? 1 : 0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) gfunc_kernel(const float* __restrict__ xi, const float* __restrict__ gamma,
+                                                    int64_t n, int gtype, float* __restrict__ G) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float x = __ldcs(xi + i);
+    float g = gamma ? __ldcs(gamma + i) : 0.0f;
+    __stcs(G + i, gfunc_eval(gtype, x, g));
+  }
+}
+
+__global__ void __launch_bounds__(256) cdf_map_kernel(const float* __restrict__ xi, const float* __restrict__ mu,
+                                                      const float* __restrict__ sigma, int64_t n, int n_bins,
+                                                      float* __restrict__ xbar) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int k = (int)(i % n_bins);
+    __stcs(xbar + i, xbar_from_xi(__ldcs(xi + i), __ldg(mu + k), __ldg(sigma + k)));
+  }
+}
+
+static inline int grid_for(int64_t n, int per_thread) {
+  int64_t blocks = (n + 256LL * per_thread - 1) / (256LL * per_thread);
+  const int64_t cap = 148LL * 8 * 4;   // multiple of the SM count x resident CTAs
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+static inline bool valid_gtype(int g) { return g >= DXI_G_MMSE_LSA && g <= DXI_G_DEEPMMSE; }
+
+}  // namespace dxi
+
+using namespace dxi;
+
+extern "C" DXI_API int dxi_map_gain(const float* xbar, const float* mu, const float* sigma, int64_t n_rows, int n_bins,
+                            int gtype, float* xi_hat, float* gain, uint8_t* ibm, void* stream) {
+  if (int rc = check_device()) return rc;
+  DXI_REQUIRE(xbar && mu && sigma, "dxi_map_gain: null input");
+  DXI_REQUIRE(n_rows >= 0 && n_bins > 0, "dxi_map_gain: bad shape");
+  DXI_REQUIRE(!gain || valid_gtype(gtype), "Invalid gain function type.");
+  DXI_REQUIRE(xi_hat || gain || ibm, "dxi_map_gain: no output requested");
+  int64_t n = n_rows * n_bins;
+  if (n == 0) return DXI_OK;
+  map_gain_kernel<4><<<grid_for(n, 4), 256, 0, as_stream(stream)>>>(xbar, mu, sigma, n, n_bins, gtype, xi_hat, gain, ibm);
+  DXI_LAUNCHED("map_gain_kernel");
+  return DXI_OK;
+}
+
+extern "C" DXI_API int dxi_gfunc(const float* xi, const float* gamma, int64_t n, int gtype, float* G, void* stream) {
+  if (int rc = check_device()) return rc;
+  DXI_REQUIRE(valid_gtype(gtype), "Invalid gain function type.");
+  DXI_REQUIRE(xi && G && n >= 0, "dxi_gfunc: bad argument");
+  bool needs_gamma = gtype == DXI_G_MMSE_LSA || gtype == DXI_G_MMSE_STSA || gtype == DXI_G_DEEPMMSE;
+  DXI_REQUIRE(gamma || !needs_gamma, "dxi_gfunc: this gain function needs gamma");
+  if (n == 0) return DXI_OK;
+  gfunc_kernel<<<grid_for(n, 1), 256, 0, as_stream(stream)>>>(xi, gamma, n, gtype, G);
+  DXI_LAUNCHED("gfunc_kernel");
+  return DXI_OK;
+}
+
+extern "C" DXI_API int dxi_cdf_map(const float* xi, const float* mu, const float* sigma, int64_t n_rows, int n_bins,
+                           float* xbar, void* stream) {
+  if (int rc = check_device()) return rc;
+  DXI_REQUIRE(xi && mu && sigma && xbar, "dxi_cdf_map: null argument");
+  DXI_REQUIRE(n_rows >= 0 && n_bins > 0, "dxi_cdf_map: bad shape");
+  int64_t n = n_rows * n_bins;
+  if (n == 0) return DXI_OK;
+  cdf_map_kernel<<<grid_for(n, 1), 256, 0, as_stream(stream)>>>(xi, mu, sigma, n, n_bins, xbar);
+  DXI_LAUNCHED("cdf_map_kernel");
+  return DXI_OK;
+}

@@ -1,0 +1,118 @@
+// Device math for the inverse CDF map and the gain functions.
+//
+// Follows the float32 operation order of the reference so that results agree with its TF/numpy
+// chain to a few ulp:  deepxi/map.py:373-390 (NormalCDF.inverse), :62-85 (db / db_inverse),
+// deepxi/gain.py:13-166 (mmse_stsa, mmse_lsa, wf, srwf, cwf, irm, ibm, deepmmse).
+#pragma once
+#include "common.cuh"
+
+namespace dxi {
+
+__device__ __forceinline__ float wf_gain(float xi) { return __fdiv_rn(xi, __fadd_rn(xi, 1.0f)); }
+
+// E1(x), x > 0, float32.  Power series for x <= 2, even-form continued fraction above.
+// (The reference calls scipy.special.exp1, gain.py:67; abs error here <= 2e-6 at x=1e-12 where
+// E1 ~ 27 is itself only representable to 1.9e-6, <= 2e-7 for x >= 1e-3.)
+__device__ __forceinline__ float expint_e1(float x) {
+  if (x <= 2.0f) {
+    // sum_{k=1..16} (-1)^{k+1} x^k / (k k!)
+    float p = -2.9868938e-15f;                 // k=16
+    p = fmaf(p, x, 5.0981123e-14f);            // k=15
+    p = fmaf(p, x, -8.1933948e-13f);           // k=14
+    p = fmaf(p, x, 1.2353000e-11f);            // k=13
+    p = fmaf(p, x, -1.7397141e-10f);           // k=12
+    p = fmaf(p, x, 2.2774621e-9f);             // k=11
+    p = fmaf(p, x, -2.7557319e-8f);            // k=10
+    p = fmaf(p, x, 3.0619244e-7f);             // k=9
+    p = fmaf(p, x, -3.1001984e-6f);            // k=8
+    p = fmaf(p, x, 2.8344671e-5f);             // k=7
+    p = fmaf(p, x, -2.3148148e-4f);            // k=6
+    p = fmaf(p, x, 1.6666667e-3f);             // k=5
+    p = fmaf(p, x, -1.0416667e-2f);            // k=4
+    p = fmaf(p, x, 5.5555556e-2f);             // k=3
+    p = fmaf(p, x, -0.25f);                    // k=2
+    p = fmaf(p, x, 1.0f);                      // k=1
+    return fmaf(p, x, -0.57721566490153286f - logf(x));
+  }
+  // E1 = e^{-x} / (x+1 - 1/(x+3 - 4/(x+5 - 9/(x+7 - ...)))), 10 levels
+  float d = x + 21.0f;
+#pragma unroll
+  for (int k = 10; k >= 1; --k) d = (x + (float)(2 * k - 1)) - __fdividef((float)(k * k), d);
+  return __fdividef(expf(-x), d);
+}
+
+// mmse_lsa (gain.py:47-69)
+__device__ __forceinline__ float gain_mmse_lsa(float xi, float gamma) {
+  xi = fmaxf(xi, 1e-12f);
+  gamma = fmaxf(gamma, 1e-12f);
+  float v1 = __fdiv_rn(xi, __fadd_rn(1.0f, xi));
+  float nu = __fmul_rn(v1, gamma);
+  float v2 = expint_e1(nu);
+  return __fmul_rn(v1, expf(__fmul_rn(0.5f, v2)));
+}
+
+// mmse_stsa (gain.py:13-45): the float32 formula with unscaled Bessel functions; where it
+// overflows to Inf/NaN (nu >~ 173) the reference substitutes the Wiener gain (gain.py:42-44).
+__device__ __forceinline__ float gain_mmse_stsa(float xi, float gamma) {
+  xi = fmaxf(xi, 1e-12f);
+  gamma = fmaxf(gamma, 1e-12f);
+  float nu = __fmul_rn(xi, __fdiv_rn(gamma, __fadd_rn(1.0f, xi)));
+  float a = __fmul_rn(__fdiv_rn(1.7724539f, 2.0f), __fdiv_rn(sqrtf(nu), gamma));
+  float b = __fmul_rn(a, expf(__fdiv_rn(-nu, 2.0f)));
+  float h = __fdiv_rn(nu, 2.0f);
+  float c = __fadd_rn(__fmul_rn(__fadd_rn(1.0f, nu), cyl_bessel_i0f(h)), __fmul_rn(nu, cyl_bessel_i1f(h)));
+  float G = __fmul_rn(b, c);
+  if (isnan(G) || isinf(G)) G = wf_gain(xi);
+  return G;
+}
+
+// deepmmse (gain.py:154-166)
+__device__ __forceinline__ float gain_deepmmse(float xi, float gamma) {
+  float op = __fadd_rn(1.0f, xi);
+  return __fadd_rn(__fdiv_rn(1.0f, op), __fdiv_rn(xi, __fmul_rn(gamma, op)));
+}
+
+// gfunc dispatch (gain.py:168-191).  gtype is warp-uniform.
+__device__ __forceinline__ float gfunc_eval(int gtype, float xi, float gamma) {
+  switch (gtype) {
+    case DXI_G_MMSE_LSA:  return gain_mmse_lsa(xi, gamma);
+    case DXI_G_MMSE_STSA: return gain_mmse_stsa(xi, gamma);
+    case DXI_G_WF:        return wf_gain(xi);
+    case DXI_G_SRWF:
+    case DXI_G_IRM:       return sqrtf(wf_gain(xi));
+    case DXI_G_CWF:       return wf_gain(sqrtf(xi));
+    case DXI_G_IBM:       return xi > 1.0f ? 1.0f : 0.0f;
+    case DXI_G_DEEPMMSE:  return gain_deepmmse(xi, gamma);
+  }
+  return 0.0f;
+}
+
+// NormalCDF.inverse for 'DBNormalCDF' (map.py:373-390): xi = 10^((sigma*sqrt(2)*erfinv(2 xbar - 1) + mu)/10).
+// Within 1e-3 dB of the 0 dB threshold the chain is re-evaluated with a double-precision erfinv and
+// the reference's float32 roundings, so that (xi > 1) -- the IBM -- is decided exactly as the
+// float32 chain of the reference decides it.
+__device__ __forceinline__ float xi_from_xbar(float xbar, float mu, float sigma) {
+  float v1 = __fmul_rn(sigma, 1.41421354f);            // sigma * f32(sqrt(2))
+  float v2 = __fmul_rn(2.0f, xbar);
+  float arg = __fsub_rn(v2, 1.0f);
+  float v3 = erfinvf(arg);
+  float x = __fadd_rn(__fmul_rn(v1, v3), mu);
+  if (fabsf(x) < 1e-3f) {
+    v3 = (float)erfinv((double)arg);
+    x = __fadd_rn(__fmul_rn(v1, v3), mu);
+    return (float)pow(10.0, (double)__fdiv_rn(x, 10.0f));
+  }
+  return exp10f(__fdiv_rn(x, 10.0f));
+}
+
+// NormalCDF.map for 'DBNormalCDF' (map.py:356-371, :62-73)
+__device__ __forceinline__ float xbar_from_xi(float xi, float mu, float sigma) {
+  xi = fmaxf(xi, 1e-12f);
+  float xdb = __fmul_rn(10.0f, __fdiv_rn(logf(xi), 2.30258512f));
+  float v1 = __fsub_rn(xdb, mu);
+  float v2 = __fmul_rn(sigma, 1.41421354f);
+  float v3 = erff(__fdiv_rn(v1, v2));
+  return __fmul_rn(0.5f, __fadd_rn(1.0f, v3));
+}
+
+}  // namespace dxi

@@ -1,0 +1,48 @@
+// Network handle shared by the fp32 and tcgen05 back ends.
+#pragma once
+#include <map>
+#include <string>
+#include <vector>
+#include "common.cuh"
+
+struct dxi_net {
+  int kind = 0;
+  dxi_net_cfg cfg{};
+  int device = 0;
+  bool finalized = false;
+  std::map<std::string, std::vector<float>> host;        // checkpoint tensors by Keras name
+  std::map<std::string, std::vector<int64_t>> shapes;
+  // fp32 device copies (one arena) -- used by the fp32 back end and by the CUDA-core layers
+  float* d_arena = nullptr;
+  std::map<std::string, size_t> d_offset;                 // in floats
+  // tcgen05 back end: packed fp16 hi/lo operand images (see tcn_umma.cu)
+  void* d_umma = nullptr;
+  size_t umma_bytes = 0;
+  std::vector<size_t> umma_stage_offset;
+
+  const float* dev_tensor(int layer, const char* var) const {
+    char name[96];
+    snprintf(name, sizeof(name), "layer_with_weights-%d/%s", layer, var);
+    auto it = d_offset.find(name);
+    return it == d_offset.end() ? nullptr : d_arena + it->second;
+  }
+  const std::vector<float>* host_tensor(int layer, const char* var) const {
+    char name[96];
+    snprintf(name, sizeof(name), "layer_with_weights-%d/%s", layer, var);
+    auto it = host.find(name);
+    return it == host.end() ? nullptr : &it->second;
+  }
+};
+
+namespace dxi {
+int64_t resnet_f32_workspace_bytes(const dxi_net& net, int B, int T);
+int resnet_f32_forward(const dxi_net& net, const float* mag, int B, int T, float* xbar, void* ws, size_t ws_bytes,
+                       cudaStream_t st);
+int64_t resnet_umma_workspace_bytes(const dxi_net& net, int B, int T);
+int resnet_umma_prepare(dxi_net& net, cudaStream_t st);
+int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, float* xbar, void* ws, size_t ws_bytes,
+                        cudaStream_t st);
+int64_t mhanet_workspace_bytes(const dxi_net& net, int B, int T);
+int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xbar, void* ws, size_t ws_bytes,
+                   cudaStream_t st);
+}  // namespace dxi

@@ -1,0 +1,337 @@
+// STFT analysis and iSTFT synthesis kernels.
+//
+// Analysis  (deepxi/sig.py:43-55, :189-199; model.py:2232-2254): int16/f32 waveform -> |STFT|, angle(STFT),
+//           512-sample Hamming(periodic=False) frames, hop 256, pad_end, rfft-512 -> 257 bins.
+// Synthesis (deepxi/sig.py:57-69; inp_tgt.py:198-214; utils.py:28): (|X| G) e^{j phase} -> irfft-512 ->
+//           inverse_stft_window_fn -> overlap-add -> f32 and/or truncated int16.
+//
+// HBM layout: waveforms [B, stride] sample-fastest; spectra [B, Tmax, 257] bin-fastest, so the frames
+// of one utterance are one contiguous run and every global access below is a flat coalesced stream.
+// Each sample is read from HBM once (the 50 % frame overlap is served from shared memory) and every
+// output element is written once.
+#include <math.h>
+#include <mutex>
+#include "fft.cuh"
+#include "gain_math.cuh"
+
+namespace dxi {
+
+__device__ float d_win[N_D];          // analysis window
+__device__ float d_swin[N_D];         // synthesis window / 256 (irfft scaling folded in)
+__device__ float2 d_tw256[256];       // e^{-2 pi j m / 256}
+__device__ float2 d_tw512[NBINS];     // e^{-2 pi j k / 512}, k = 0..256
+
+static std::mutex g_tab_mutex;
+static bool g_tab_ready[64] = {};
+
+static int ensure_tables(cudaStream_t stream) {
+  int dev = 0;
+  DXI_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_tab_mutex);
+  if (dev < 64 && g_tab_ready[dev]) return DXI_OK;
+  static float win[N_D], swin[N_D];
+  static float2 tw256[256], tw512[NBINS];
+  double w[N_D];
+  for (int n = 0; n < N_D; ++n) w[n] = 0.54 - 0.46 * cos(2.0 * M_PI * n / (N_D - 1));   // sig.py:38-39
+  for (int n = 0; n < N_D; ++n) {
+    int m = n % N_S;
+    double den = w[m] * w[m] + w[m + N_S] * w[m + N_S];     // tf.signal.inverse_stft_window_fn
+    win[n] = (float)w[n];
+    // the reference multiplies the float32 irfft output by the float32 synthesis window; the 1/256
+    // of the half-size inverse transform is exact in binary and is folded in here
+    swin[n] = (float)(w[n] / den) * (1.0f / 256.0f);
+  }
+  for (int m = 0; m < 256; ++m) tw256[m] = make_float2((float)cos(2.0 * M_PI * m / 256.0), (float)-sin(2.0 * M_PI * m / 256.0));
+  for (int k = 0; k < NBINS; ++k) tw512[k] = make_float2((float)cos(2.0 * M_PI * k / 512.0), (float)-sin(2.0 * M_PI * k / 512.0));
+  DXI_CUDA(cudaMemcpyToSymbolAsync(d_win, win, sizeof(win), 0, cudaMemcpyHostToDevice, stream));
+  DXI_CUDA(cudaMemcpyToSymbolAsync(d_swin, swin, sizeof(swin), 0, cudaMemcpyHostToDevice, stream));
+  DXI_CUDA(cudaMemcpyToSymbolAsync(d_tw256, tw256, sizeof(tw256), 0, cudaMemcpyHostToDevice, stream));
+  DXI_CUDA(cudaMemcpyToSymbolAsync(d_tw512, tw512, sizeof(tw512), 0, cudaMemcpyHostToDevice, stream));
+  DXI_CUDA(cudaStreamSynchronize(stream));   // one-time: the host tables above are static scratch
+  if (dev < 64) g_tab_ready[dev] = true;
+  return DXI_OK;
+}
+
+constexpr int FR = 16;   // frames transformed per CTA pass (16 threads per frame, 256 threads)
+
+struct StftSmem {
+  float2 buf[FR * FFT_FRAME_SLOTS];   // per-frame FFT exchange, then the 256 Z values
+  float xs[(FR + 1) * N_S];           // staged samples of FR overlapping frames
+  float win[N_D];
+  float2 tw256[256];
+  float2 tw512[NBINS + 1];
+};
+
+// ----------------------------------------------------------------------------------------------
+// Analysis
+// ----------------------------------------------------------------------------------------------
+template <bool I16>
+__global__ void __launch_bounds__(256) stft_kernel(const void* __restrict__ wav_, const int32_t* __restrict__ lens,
+                                                   int B, int64_t stride, int Tmax, int groups_per_utt,
+                                                   int vec_ok, float* __restrict__ mag, float* __restrict__ phase) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  StftSmem& sm = *reinterpret_cast<StftSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < N_D; i += 256) sm.win[i] = d_win[i];
+  sm.tw256[tid] = d_tw256[tid];
+  for (int i = tid; i < NBINS; i += 256) sm.tw512[i] = d_tw512[i];
+  __syncthreads();
+
+  const int f = tid >> 4, lane16 = tid & 15;
+  const int total = B * groups_per_utt;
+  for (int g = blockIdx.x; g < total; g += gridDim.x) {
+    const int b = g / groups_per_utt, t0 = (g - b * groups_per_utt) * FR;
+    const int nf = min(FR, Tmax - t0);
+    int64_t len = lens ? (int64_t)lens[b] : stride;
+    if (len > stride) len = stride;
+    const int64_t s0 = (int64_t)t0 * N_S;
+    const int64_t out0 = ((int64_t)b * Tmax + t0) * NBINS;
+    if (s0 >= len) {   // frames at or beyond ceil(len/256): zeros (model.py:2246-2253 leaves them zero)
+      for (int i = tid; i < nf * NBINS; i += 256) { __stcs(mag + out0 + i, 0.0f); __stcs(phase + out0 + i, 0.0f); }
+      continue;
+    }
+    // ---- stage (nf+1)*256 samples, normalised (sig.py:189-199: int16 -> f32 / 32768)
+    const int n_stage = (nf + 1) * N_S;
+    if (I16) {
+      const int16_t* w = reinterpret_cast<const int16_t*>(wav_) + (int64_t)b * stride + s0;
+      for (int i = tid * 8; i < n_stage; i += 256 * 8) {
+        if (vec_ok && s0 + i + 8 <= len) {
+          int4 q = __ldcs(reinterpret_cast<const int4*>(w + i));
+          const int16_t* h = reinterpret_cast<const int16_t*>(&q);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sm.xs[i + j] = (float)h[j] * (1.0f / 32768.0f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sm.xs[i + j] = (s0 + i + j < len) ? (float)w[i + j] * (1.0f / 32768.0f) : 0.0f;
+        }
+      }
+    } else {
+      const float* w = reinterpret_cast<const float*>(wav_) + (int64_t)b * stride + s0;
+      for (int i = tid * 4; i < n_stage; i += 256 * 4) {
+        if (vec_ok && s0 + i + 4 <= len) {
+          float4 q = __ldcs(reinterpret_cast<const float4*>(w + i));
+          sm.xs[i] = q.x; sm.xs[i + 1] = q.y; sm.xs[i + 2] = q.z; sm.xs[i + 3] = q.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sm.xs[i + j] = (s0 + i + j < len) ? w[i + j] : 0.0f;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- window + 256-point complex FFT of z[m] = x[2m] + j x[2m+1]
+    float2* fb = sm.buf + f * FFT_FRAME_SLOTS;
+    float2 v[16];
+    if (f < nf) {
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) {
+        const int n = 32 * n1 + 2 * lane16;
+        float2 x = *reinterpret_cast<const float2*>(&sm.xs[f * N_S + n]);
+        float2 w = *reinterpret_cast<const float2*>(&sm.win[n]);
+        v[n1] = make_float2(x.x * w.x, x.y * w.y);
+      }
+      fft256_pass1<-1>(v, fb, sm.tw256, lane16);
+    }
+    __syncwarp();
+    if (f < nf) fft256_pass2<-1>(v, fb, lane16);
+    __syncwarp();
+    if (f < nf) {
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) fb[lane16 + 16 * k2] = v[fft16_pos(k2)];
+    }
+    __syncthreads();
+    // ---- split step, magnitude and phase; flat coalesced stores over (frame, bin)
+    for (int i = tid; i < nf * NBINS; i += 256) {
+      const int fi = i / NBINS, k = i - fi * NBINS;
+      const float2* z = sm.buf + fi * FFT_FRAME_SLOTS;
+      float2 X = rfft_split(z[k & 255], z[(256 - k) & 255], sm.tw512[k]);
+      if (k == 0 || k == 256) X.y = 0.0f;
+      __stcs(mag + out0 + i, sqrtf(fmaf(X.x, X.x, X.y * X.y)));
+      __stcs(phase + out0 + i, atan2_poly(X.y, X.x));
+    }
+    __syncthreads();
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Synthesis
+// ----------------------------------------------------------------------------------------------
+constexpr int HOPS_PER_STRIP = 64;   // a strip recomputes one leading frame: 1/64 redundant work
+
+struct IstftSmem {
+  float2 buf[FR * FFT_FRAME_SLOTS];   // per frame: 257 spectrum values, then the FFT exchange
+  float fr[FR * N_D];                 // windowed time-domain frames
+  float carry[N_S];                   // second half of the last frame of the previous pass
+  float swin[N_D];
+  float2 tw256[256];
+  float2 tw512[NBINS + 1];
+};
+
+// MODE 0: gain tensor (nullable); MODE 1: fused inverse map + gain from xbar (inp_tgt.py:198-214)
+template <int MODE>
+__global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ mag, const float* __restrict__ gain_or_xbar,
+                                                    const float* __restrict__ phase, const float* __restrict__ mu,
+                                                    const float* __restrict__ sigma, int gtype,
+                                                    const int32_t* __restrict__ n_frames, int B, int Tmax,
+                                                    int strips_per_utt, float* __restrict__ wav_f32,
+                                                    int16_t* __restrict__ wav_i16, int64_t out_stride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  IstftSmem& sm = *reinterpret_cast<IstftSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < N_D; i += 256) sm.swin[i] = d_swin[i];
+  sm.tw256[tid] = d_tw256[tid];
+  for (int i = tid; i < NBINS; i += 256) sm.tw512[i] = d_tw512[i];
+  __syncthreads();
+
+  const int f = tid >> 4, lane16 = tid & 15;
+  const int total = B * strips_per_utt;
+  for (int s = blockIdx.x; s < total; s += gridDim.x) {
+    const int b = s / strips_per_utt;
+    const int hs = (s - b * strips_per_utt) * HOPS_PER_STRIP;      // first hop of the strip
+    const int he = min(hs + HOPS_PER_STRIP, Tmax + 1);              // hops hs..he-1; hop h = tail(h-1) + head(h)
+    int T = n_frames ? min(n_frames[b], Tmax) : Tmax;
+    const int64_t in0 = (int64_t)b * Tmax * NBINS;
+    float* of = wav_f32 ? wav_f32 + (int64_t)b * out_stride : nullptr;
+    int16_t* oi = wav_i16 ? wav_i16 + (int64_t)b * out_stride : nullptr;
+    // frames hs-1 .. he-1 in passes of FR; the first frame of the strip only provides its tail
+    for (int f0 = hs - 1; f0 < he; f0 += FR) {
+      const int nf = min(FR, he - f0);
+      // ---- spectrum of every frame: Y = (|X| G) e^{j phase}
+      for (int i = tid; i < nf * NBINS; i += 256) {
+        const int fi = i / NBINS, k = i - fi * NBINS;
+        const int t = f0 + fi;
+        float2 Y = make_float2(0.0f, 0.0f);
+        if (t >= 0 && t < T) {
+          const int64_t gi = in0 + (int64_t)t * NBINS + k;
+          float m = __ldcs(mag + gi);
+          float p = __ldcs(phase + gi);
+          if (MODE == 0) {
+            if (gain_or_xbar) m *= __ldcs(gain_or_xbar + gi);
+          } else {
+            float xi = xi_from_xbar(__ldcs(gain_or_xbar + gi), __ldg(mu + k), __ldg(sigma + k));
+            m = __fmul_rn(m, gfunc_eval(gtype, xi, __fadd_rn(xi, 1.0f)));
+          }
+          float sn, cs;
+          sincosf(p, &sn, &cs);
+          Y = make_float2(m * cs, (k == 0 || k == 256) ? 0.0f : m * sn);   // c2r ignores Im of DC / Nyquist
+        }
+        sm.buf[fi * FFT_FRAME_SLOTS + k] = Y;
+      }
+      __syncthreads();
+      // ---- merge step + 256-point inverse FFT
+      float2* fb = sm.buf + f * FFT_FRAME_SLOTS;
+      float2 v[16];
+      if (f < nf) {
+#pragma unroll
+        for (int n1 = 0; n1 < 16; ++n1) {
+          const int k = 16 * n1 + lane16;
+          v[n1] = irfft_merge(fb[k], fb[256 - k], sm.tw512[k]);
+        }
+      }
+      __syncwarp();
+      if (f < nf) fft256_pass1<1>(v, fb, sm.tw256, lane16);
+      __syncwarp();
+      if (f < nf) {
+        fft256_pass2<1>(v, fb, lane16);
+        // z[m] = x[2m] + j x[2m+1], m = lane16 + 16 k2; synthesis window (x 1/256 folded in)
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) {
+          const int n = 2 * (lane16 + 16 * k2);
+          float2 z = v[fft16_pos(k2)];
+          float2 w = *reinterpret_cast<const float2*>(&sm.swin[n]);
+          *reinterpret_cast<float2*>(&sm.fr[f * N_D + n]) = make_float2(z.x * w.x, z.y * w.y);
+        }
+      }
+      __syncthreads();
+      // ---- overlap-add: hop t = head(frame t) + tail(frame t-1); coalesced stores
+      const int first = (f0 == hs - 1) ? 1 : 0;
+      for (int i = tid + first * N_S; i < nf * N_S; i += 256) {
+        const int fi = i >> 8, n = i & 255;
+        const int t = f0 + fi;
+        float y = sm.fr[fi * N_D + n] + (fi > 0 ? sm.fr[(fi - 1) * N_D + N_S + n] : sm.carry[n]);
+        const int64_t o = (int64_t)t * N_S + n;
+        if (of) __stcs(of + o, y);
+        if (oi) oi[o] = (int16_t)__float2int_rz(y * 32768.0f);   // utils.py:28 truncation
+      }
+      __syncthreads();
+      sm.carry[tid] = sm.fr[(nf - 1) * N_D + N_S + tid];
+      __syncthreads();
+    }
+  }
+}
+
+static int istft_launch(int mode, const float* mag, const float* g_or_xbar, const float* phase, const float* mu,
+                        const float* sigma, int gtype, const int32_t* n_frames, int B, int Tmax, float* wav_f32,
+                        int16_t* wav_i16, int64_t out_stride, cudaStream_t st) {
+  if (int rc = ensure_tables(st)) return rc;
+  const int strips = (Tmax + 1 + HOPS_PER_STRIP - 1) / HOPS_PER_STRIP;
+  const int64_t total = (int64_t)B * strips;
+  const int grid = (int)(total < 148 * 3 ? total : 148 * 3);
+  const size_t smem = sizeof(IstftSmem);
+  if (mode == 0) {
+    DXI_CUDA(cudaFuncSetAttribute(istft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    istft_kernel<0><<<grid, 256, smem, st>>>(mag, g_or_xbar, phase, mu, sigma, gtype, n_frames, B, Tmax, strips,
+                                             wav_f32, wav_i16, out_stride);
+  } else {
+    DXI_CUDA(cudaFuncSetAttribute(istft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    istft_kernel<1><<<grid, 256, smem, st>>>(mag, g_or_xbar, phase, mu, sigma, gtype, n_frames, B, Tmax, strips,
+                                             wav_f32, wav_i16, out_stride);
+  }
+  DXI_LAUNCHED("istft_kernel");
+  return DXI_OK;
+}
+
+}  // namespace dxi
+
+using namespace dxi;
+
+extern "C" DXI_API int dxi_stft(const void* wav, int wav_is_i16, const int32_t* lens, int B, int64_t wav_stride, int Tmax,
+                        float* mag, float* phase, void* stream) {
+  if (int rc = check_device()) return rc;
+  DXI_REQUIRE(wav && mag && phase, "dxi_stft: null argument");
+  DXI_REQUIRE(B >= 0 && Tmax >= 0 && wav_stride >= 0, "dxi_stft: bad shape");
+  if (B == 0 || Tmax == 0) return DXI_OK;
+  cudaStream_t st = as_stream(stream);
+  if (int rc = ensure_tables(st)) return rc;
+  const int groups = (Tmax + FR - 1) / FR;
+  const int64_t total = (int64_t)B * groups;
+  DXI_REQUIRE(total < (1LL << 31), "dxi_stft: batch too large");
+  const int grid = (int)(total < 148 * 3 ? total : 148 * 3);
+  const size_t smem = sizeof(StftSmem);
+  const int elem = wav_is_i16 ? 2 : 4;
+  const int vec_ok = ((reinterpret_cast<uintptr_t>(wav) % 16) == 0 && ((wav_stride * elem) % 16) == 0) ? 1 : 0;
+  if (wav_is_i16) {
+    DXI_CUDA(cudaFuncSetAttribute(stft_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stft_kernel<true><<<grid, 256, smem, st>>>(wav, lens, B, wav_stride, Tmax, groups, vec_ok, mag, phase);
+  } else {
+    DXI_CUDA(cudaFuncSetAttribute(stft_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stft_kernel<false><<<grid, 256, smem, st>>>(wav, lens, B, wav_stride, Tmax, groups, vec_ok, mag, phase);
+  }
+  DXI_LAUNCHED("stft_kernel");
+  return DXI_OK;
+}
+
+extern "C" DXI_API int dxi_istft(const float* mag, const float* gain, const float* phase, const int32_t* n_frames, int B,
+                         int Tmax, float* wav_f32, int16_t* wav_i16, int64_t out_stride, void* stream) {
+  if (int rc = check_device()) return rc;
+  DXI_REQUIRE(mag && phase, "dxi_istft: null argument");
+  DXI_REQUIRE(wav_f32 || wav_i16, "dxi_istft: no output requested");
+  DXI_REQUIRE(B >= 0 && Tmax >= 0, "dxi_istft: bad shape");
+  DXI_REQUIRE(out_stride >= (int64_t)(Tmax + 1) * N_S, "dxi_istft: out_stride < (Tmax+1)*256");
+  if (B == 0 || Tmax == 0) return DXI_OK;
+  return istft_launch(0, mag, gain, phase, nullptr, nullptr, 0, n_frames, B, Tmax, wav_f32, wav_i16, out_stride,
+                      as_stream(stream));
+}
+
+extern "C" DXI_API int dxi_enhance(const float* mag, const float* phase, const float* xbar, const float* mu,
+                           const float* sigma, int gtype, const int32_t* n_frames, int B, int Tmax, float* wav_f32,
+                           int16_t* wav_i16, int64_t out_stride, void* stream) {
+  if (int rc = check_device()) return rc;
+  DXI_REQUIRE(mag && phase && xbar && mu && sigma, "dxi_enhance: null argument");
+  DXI_REQUIRE(gtype >= DXI_G_MMSE_LSA && gtype <= DXI_G_DEEPMMSE, "Invalid gain function type.");
+  DXI_REQUIRE(wav_f32 || wav_i16, "dxi_enhance: no output requested");
+  DXI_REQUIRE(B >= 0 && Tmax >= 0, "dxi_enhance: bad shape");
+  DXI_REQUIRE(out_stride >= (int64_t)(Tmax + 1) * N_S, "dxi_enhance: out_stride < (Tmax+1)*256");
+  if (B == 0 || Tmax == 0) return DXI_OK;
+  return istft_launch(1, mag, xbar, phase, mu, sigma, gtype, n_frames, B, Tmax, wav_f32, wav_i16, out_stride,
+                      as_stream(stream));
+}

@@ -1,0 +1,117 @@
+// Self test of the tcgen05 building blocks in umma.cuh: one CTA computes D[128,N] = A[128,K] B[N,K]^T
+// (fp16 operands, fp32 accumulate) and writes D to global memory; tests/test_umma_selftest.py compares
+// with numpy.  `variant` selects the encodings under test:
+//   bit0  A operand: 0 = tensor memory (the production path), 1 = shared memory (128B swizzle)
+//   bit1  B operand layout: 0 = 128-byte swizzle (production), 1 = no swizzle (8x16B core matrices)
+//   bit2  A-in-TMEM half order: 0 = even k in the low half (production), 1 = swapped
+#include "umma.cuh"
+
+namespace dxi {
+using namespace umma;
+
+__global__ void __launch_bounds__(128) umma_selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ Bm,
+                                                            int N, int K, int variant, float* __restrict__ D) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool a_smem = variant & 1, b_noswz = variant & 2, a_swap = variant & 4;
+  unsigned char* sB = smem;                               // K/64 chunks of [N x 128 B]  (or no-swizzle image)
+  unsigned char* sA = smem + (size_t)N * K * 2;           // K/64 chunks of [128 x 128 B]
+
+  if (warp == 0) tmem_alloc(&tmem_base_slot, 512);
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  // ---- B image
+  for (int i = tid; i < N * (K / 8); i += 128) {          // one 16-byte unit (8 halves) per step
+    const int n = i / (K / 8), u = i - n * (K / 8);       // unit u covers k = 8u .. 8u+7
+    uint4 val = *reinterpret_cast<const uint4*>(Bm + (size_t)n * K + 8 * u);
+    size_t off;
+    if (!b_noswz) {
+      const int c = u >> 3, uu = u & 7;
+      off = (size_t)c * N * 128 + (size_t)(n >> 3) * 1024 + (n & 7) * 128 + ((uu ^ (n & 7)) * 16);
+    } else {
+      off = (size_t)(n >> 3) * (K / 8) * 128 + (size_t)u * 128 + (n & 7) * 16;
+    }
+    *reinterpret_cast<uint4*>(sB + off) = val;
+  }
+  if (a_smem) {
+    for (int i = tid; i < 128 * (K / 8); i += 128) {
+      const int m = i / (K / 8), u = i - m * (K / 8);
+      uint4 val = *reinterpret_cast<const uint4*>(A + (size_t)m * K + 8 * u);
+      const int c = u >> 3, uu = u & 7;
+      size_t off = (size_t)c * 128 * 128 + (size_t)(m >> 3) * 1024 + (m & 7) * 128 + ((uu ^ (m & 7)) * 16);
+      *reinterpret_cast<uint4*>(sA + off) = val;
+    }
+  }
+  fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_slot;
+  const uint32_t lane_base = (uint32_t)(warp * 32);
+  const uint32_t a_col = 256;
+  if (!a_smem) {
+    // thread tid owns row tid: pack its K halves into K/2 columns starting at a_col
+    for (int c0 = 0; c0 < K / 2; c0 += 16) {
+      uint32_t r[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const __half lo = A[(size_t)tid * K + 2 * (c0 + j)], hi = A[(size_t)tid * K + 2 * (c0 + j) + 1];
+        const uint32_t l = __half_as_ushort(lo), h = __half_as_ushort(hi);
+        r[j] = a_swap ? (h | (l << 16)) : (l | (h << 16));
+      }
+      tmem_st16(tmem_addr(tbase, lane_base, a_col + c0), r);
+    }
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_f16(128, N);
+    for (int k16 = 0; k16 < K / 16; ++k16) {
+      const int c = k16 >> 2, kk = k16 & 3;
+      uint64_t bdesc;
+      if (!b_noswz) bdesc = make_smem_desc_sw128(smem_u32(sB + (size_t)c * N * 128) + kk * 32);
+      else          bdesc = make_smem_desc_noswz(smem_u32(sB) + k16 * 256, 128, (K / 8) * 128);
+      if (!a_smem) {
+        mma_ts(tbase, tmem_addr(tbase, 0, a_col + 8 * k16), bdesc, idesc, k16 > 0);
+      } else {
+        uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + (size_t)c * 128 * 128) + kk * 32);
+        mma_ss(tbase, adesc, bdesc, idesc, k16 > 0);
+      }
+    }
+    mma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int n0 = 0; n0 < N; n0 += 32) {
+    float v[32];
+    tmem_ld32(tmem_addr(tbase, lane_base, n0), v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) D[(size_t)tid * N + n0 + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+}  // namespace dxi
+
+using namespace dxi;
+
+extern "C" DXI_API int dxi_selftest_umma(const void* a_f16, const void* b_f16, int N, int K, int variant, float* d_out,
+                                 void* stream) {
+  if (int rc = check_device()) return rc;
+  DXI_REQUIRE(a_f16 && b_f16 && d_out, "dxi_selftest_umma: null argument");
+  DXI_REQUIRE(N >= 32 && N <= 256 && N % 32 == 0, "dxi_selftest_umma: N must be a multiple of 32 in [32,256]");
+  DXI_REQUIRE(K >= 64 && K <= 256 && K % 64 == 0, "dxi_selftest_umma: K must be a multiple of 64 in [64,256]");
+  const size_t smem = (size_t)N * K * 2 + 128 * (size_t)K * 2 + 2048;
+  DXI_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(reinterpret_cast<const __half*>(a_f16),
+                                                            reinterpret_cast<const __half*>(b_f16), N, K, variant, d_out);
+  DXI_LAUNCHED("umma_selftest_kernel");
+  return DXI_OK;
+}

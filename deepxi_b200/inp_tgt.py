@@ -1,0 +1,135 @@
+"""Mirror of deepxi/inp_tgt.py: inp_tgt_selector (:24-71), MagTgt.observation (:87-101) and MagXi (:141-240).
+
+Only the 'MagXi' input/target pair has committed models; the other pairs of the reference raise
+NotImplementedError, unknown names raise ValueError("Invalid inp_tgt type.") (inp_tgt.py:71).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._tensor import to_dev, ret
+from .map import map_selector
+from .sig import InputTarget
+
+_OTHER = ('MagGamma', 'MagXiGamma', 'MagGain', 'MagMag', 'MagSMM', 'MagPhaXiPha', 'STDCTXiCD', 'MagPhonme')
+
+
+def inp_tgt_selector(inp_tgt_type, N_d, N_s, K, f_s, **kwargs):
+    if inp_tgt_type == 'MagXi':
+        return MagXi(N_d, N_s, K, f_s, xi_map_type=kwargs['map_type'], xi_map_params=kwargs.get('map_params'))
+    if inp_tgt_type in _OTHER:
+        raise NotImplementedError('%s has no committed model: out of scope (SURVEY 2)' % inp_tgt_type)
+    raise ValueError('Invalid inp_tgt type.')
+
+
+class MagTgt(InputTarget):
+    """Magnitude-spectrum input and any target (inp_tgt.py:73-139)."""
+
+    def observation(self, x):
+        """Noisy-speech int16 waveform [L] (or [B, L]) -> (x_STMS, x_STPS) (inp_tgt.py:87-101).
+
+        normalise (int16 / 32768) is fused into the STFT kernel."""
+        was_np = not isinstance(x, torch.Tensor)
+        if was_np:
+            x = np.asarray(x)
+            if x.dtype != np.int16:
+                x = x.astype(np.int16)
+        elif x.dtype != torch.int16:
+            x = x.to(torch.int16)
+        x, _ = to_dev(x, torch.int16)
+        mag, pha = self._stft(x)
+        return ret(mag, was_np), ret(pha, was_np)
+
+    def observation_batch(self, x_batch, x_batch_len):
+        """DeepXi.observation_batch (model.py:2232-2254) in one launch: zero-padded device batches
+        inp [B, Tmax, 257], phase [B, Tmax, 257] and the per-utterance frame counts (host list)."""
+        x, _ = to_dev(x_batch, torch.int16)
+        lens_host = [int(l) for l in x_batch_len]
+        lens = torch.tensor(lens_host, dtype=torch.int32).to(x.device, non_blocking=True)
+        if x.dim() != 2 or x.shape[0] != len(lens_host):
+            raise ValueError('x_batch must be [B, Lmax] with one length per row')
+        Tmax = self.n_frames(max(lens_host)) if lens_host else 0
+        lib = _lib.load()
+        B, L = x.shape
+        mag = torch.empty((B, Tmax, self.n_bins), dtype=torch.float32, device=x.device)
+        pha = torch.empty_like(mag)
+        if B and Tmax:
+            _lib.check(lib.dxi_stft(_lib.ptr(x), 1, _lib.ptr(lens), B, L, Tmax, _lib.ptr(mag), _lib.ptr(pha),
+                                    _lib.stream_ptr(x.device)))
+        return mag, pha, [self.n_frames(l) for l in lens_host]
+
+
+class MagXi(MagTgt):
+    """Magnitude-spectrum input and mapped a priori SNR target (inp_tgt.py:141-240)."""
+
+    def __init__(self, N_d, N_s, K, f_s, xi_map_type, xi_map_params=None):
+        super().__init__(N_d, N_s, K, f_s)
+        self.n_feat = math.ceil(K / 2 + 1)
+        self.n_outp = self.n_feat
+        self.xi_map = map_selector(xi_map_type, xi_map_params)
+
+    def set_stats(self, mu, sigma):
+        self.xi_map.set_stats(mu, sigma)
+        return self
+
+    def xi_hat(self, xi_bar_hat):
+        """A priori SNR estimate (inp_tgt.py:216-227)."""
+        return self.xi_map.inverse(xi_bar_hat)
+
+    def gamma_hat(self, xi_bar_hat):
+        """Maximum-likelihood a posteriori SNR estimate xi_hat + 1 (inp_tgt.py:229-240)."""
+        xi = self.xi_map.inverse(xi_bar_hat)
+        return xi + np.float32(1.0) if isinstance(xi, np.ndarray) else xi + 1.0
+
+    def _map_gain(self, xi_bar_hat, gtype, want_xi=False, want_gain=False, want_ibm=False):
+        xb, was_np = to_dev(xi_bar_hat, torch.float32)
+        mu, sigma = self.xi_map._stats_dev(xb.device)
+        code = _lib.gtype_code(gtype) if want_gain else 0
+        xi = torch.empty_like(xb) if want_xi else None
+        G = torch.empty_like(xb) if want_gain else None
+        ibm = torch.empty(xb.shape, dtype=torch.uint8, device=xb.device) if want_ibm else None
+        if xb.numel():
+            _lib.check(_lib.load().dxi_map_gain(_lib.ptr(xb), _lib.ptr(mu), _lib.ptr(sigma), xb.numel() // self.n_outp,
+                                                self.n_outp, code, _lib.ptr(xi, allow_none=True),
+                                                _lib.ptr(G, allow_none=True), _lib.ptr(ibm, allow_none=True),
+                                                _lib.stream_ptr(xb.device)), value_error=True)
+        return xi, G, ibm, was_np
+
+    def gain_hat(self, xi_bar_hat, gtype):
+        """gfunc(xi_hat, xi_hat + 1, gtype): the `gain` output type named by args.py:60-64 (not implemented in
+        the reference's infer)."""
+        _, G, _, was_np = self._map_gain(xi_bar_hat, gtype, want_gain=True)
+        return ret(G, was_np)
+
+    def ibm_hat(self, xi_bar_hat):
+        """xi_hat > 1 as bool (model.py:319-322)."""
+        _, _, ibm, was_np = self._map_gain(xi_bar_hat, None, want_ibm=True)
+        return ret(ibm.bool(), was_np)
+
+    def enhanced_speech(self, x_STMS, x_STPS, xi_bar_hat, gtype, n_frames=None, int16=False):
+        """Enhanced speech (inp_tgt.py:198-214): inverse map -> gamma_hat = xi_hat + 1 -> gain -> synthesis,
+        fused in one kernel.  Accepts [T, 257] or batched [B, T, 257] (+ optional per-utterance n_frames)."""
+        code = _lib.gtype_code(gtype)
+        mag, was_np = to_dev(x_STMS, torch.float32)
+        pha, _ = to_dev(x_STPS, torch.float32)
+        xb, _ = to_dev(xi_bar_hat, torch.float32)
+        if not (mag.shape == pha.shape == xb.shape) or mag.shape[-1] != self.n_feat:
+            raise ValueError('x_STMS, x_STPS and xi_bar_hat must share the shape [..., T, %d]' % self.n_feat)
+        squeeze = mag.dim() == 2
+        if squeeze:
+            mag, pha, xb = mag[None], pha[None], xb[None]
+        B, T, _ = mag.shape
+        mu, sigma = self.xi_map._stats_dev(mag.device)
+        n_out = (T + 1) * self.N_s
+        nf = None
+        if n_frames is not None:
+            nf = torch.as_tensor(np.asarray(n_frames, np.int32)).to(mag.device, non_blocking=True)
+        y = torch.empty((B, n_out), dtype=torch.int16 if int16 else torch.float32, device=mag.device)
+        if B and T:
+            _lib.check(_lib.load().dxi_enhance(_lib.ptr(mag), _lib.ptr(pha), _lib.ptr(xb), _lib.ptr(mu), _lib.ptr(sigma),
+                                               code, _lib.ptr(nf, torch.int32, allow_none=True), B, T,
+                                               None if int16 else _lib.ptr(y), _lib.ptr(y) if int16 else None, n_out,
+                                               _lib.stream_ptr(mag.device)), value_error=True)
+        return ret(y[0] if squeeze else y, was_np)

@@ -1,0 +1,133 @@
+"""Mirror of deepxi/model.py: class DeepXi -- constructor (:44-111), infer (:224-332) and
+observation_batch (:2232-2254).  Training, testing with PESQ/STOI and the fork's experiment methods
+(infer_pho, infer_hybrid*, infer_tracking_noise*) are out of scope.
+
+Differences from the reference, all on the host side:
+  * observation -> network -> map / gain -> synthesis run batched on the GPU instead of three
+    per-utterance Python loops; files are written from one device-to-host copy per batch;
+  * `out_type='gain'` (named in args.py:60-64 but raising in the reference) returns
+    gfunc(xi_hat, xi_hat + 1, gain);
+  * `infer_batch` returns the outputs in memory (device tensors) instead of writing files.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import stats as _stats
+from . import weights as _weights
+from .inp_tgt import inp_tgt_selector
+from .network.selector import network_selector
+from .utils import save_mat, save_wav, read_mat
+
+_OUT_TYPES = ('y', 'xi_hat', 'gamma_hat', 'gain', 'ibm_hat', 'deepmmse')
+_OTHER_OUT_TYPES = ('mag_hat', 'subband_ibm_hat', 'cd_hat')
+
+
+class DeepXi:
+    def __init__(self, N_d, N_s, K, f_s, inp_tgt_type, network_type, min_snr=-10, max_snr=20, snr_inter=1,
+                 log_path=None, sample_dir=None, ver='VERSION_NAME', train_s_list=None, train_d_list=None,
+                 sample_size=None, reset_inp_tgt=False, **kwargs):
+        self.inp_tgt_type = inp_tgt_type
+        self.network_type = network_type
+        self.min_snr, self.max_snr = min_snr, max_snr
+        self.snr_levels = list(range(min_snr, max_snr + 1, snr_inter))
+        self.ver = ver
+        self.inp_tgt = inp_tgt_selector(inp_tgt_type, N_d, N_s, K, f_s, **kwargs)
+        # statistics: data/<ver>_inp_tgt.p when present (model.py:90-93), else the packaged values
+        p = os.path.join(sample_dir, ver + '_inp_tgt.p') if sample_dir else None
+        if p and os.path.exists(p) and not reset_inp_tgt:
+            st = _stats.load_inp_tgt_pickle(p)
+            if (st['N_d'], st['N_s'], st['K']) != (N_d, N_s, K):
+                raise ValueError('%s was computed for a different framing' % p)
+            mu, sigma = st['mu'], st['sigma']
+        elif 'stats' in kwargs and kwargs['stats'] is not None:
+            mu, sigma = kwargs['stats']
+        else:
+            try:
+                mu, sigma = _stats.packaged(ver)
+            except KeyError:
+                raise ValueError('no statistics for ver=%r: pass sample_dir with <ver>_inp_tgt.p, or stats=(mu, sigma); '
+                                 'computing them needs the training set (out of scope)' % ver)
+        self.inp_tgt.set_stats(mu, sigma)
+        net_kwargs = dict(kwargs)
+        for k in ('map_type', 'map_params', 'stats'):
+            net_kwargs.pop(k, None)
+        self.network = network_selector(network_type, None, self.inp_tgt.n_outp, **net_kwargs)
+        self.model = self.network
+        self._weights_epoch = None
+
+    # ------------------------------------------------------------------------------------------
+    def set_weights(self, weights):
+        self.network.load_weights(weights)
+        self._weights_epoch = 'explicit'
+
+    def load_weights(self, model_path, epoch):
+        """model.load_weights(model_path/epoch-<epoch>/variables/variables) (model.py:279-280)."""
+        self.network.load_weights(_weights.load_checkpoint(model_path, epoch))
+        self._weights_epoch = (model_path, epoch)
+
+    def observation_batch(self, x_batch, x_batch_len):
+        """model.py:2232-2254."""
+        return self.inp_tgt.observation_batch(x_batch, x_batch_len)
+
+    # ------------------------------------------------------------------------------------------
+    def infer_batch(self, test_x, test_x_len, out_type='y', gain='mmse-lsa', int16=False):
+        """One batch through the hot path; returns (output device tensor [B, ...], n_frames list).
+
+        'y' -> [B, (Tmax+1)*256] waveform (float32, or int16 with the save_wav rule); the others
+        -> [B, Tmax, 257]; slices beyond n_frames[i] are padding."""
+        if out_type in _OTHER_OUT_TYPES:
+            raise NotImplementedError('out_type %r belongs to targets without committed models' % out_type)
+        if out_type not in _OUT_TYPES:
+            raise ValueError('Invalid output type.')
+        it = self.inp_tgt
+        inp, pha, n_frames = it.observation_batch(test_x, test_x_len)
+        xbar = self.network(inp)
+        if out_type == 'y':
+            out = it.enhanced_speech(inp, pha, xbar, gain, n_frames=n_frames, int16=int16)
+        elif out_type == 'xi_hat':
+            out = it.xi_hat(xbar)
+        elif out_type == 'gamma_hat':
+            out = it.gamma_hat(xbar)
+        elif out_type == 'gain':
+            out = it.gain_hat(xbar, gain)
+        elif out_type == 'ibm_hat':
+            out = it.ibm_hat(xbar)
+        else:  # deepmmse: |X|^2 * G_deepmmse(xi_hat, xi_hat + 1)   (model.py:314-318)
+            out = inp * inp * it.gain_hat(xbar, 'deepmmse')
+        return out, n_frames
+
+    def infer(self, test_x, test_x_len, test_x_base_names, test_epoch, model_path='model', out_type='y',
+              gain='mmse-lsa', out_path='out', n_filters=40, saved_data_path=None):
+        """Deep Xi inference; the specified out_type is saved (model.py:224-332)."""
+        out_path_base = out_path
+        if not isinstance(test_epoch, list): test_epoch = [test_epoch]
+        if not isinstance(gain, list): gain = [gain]
+        for e in test_epoch:
+            if e < 1: raise ValueError('test_epoch must be greater than 0.')
+            for g in gain:
+                out_path = out_path_base + '/' + self.ver + '/' + 'e' + str(e)
+                if out_type == 'xi_hat': out_path = out_path + '/xi_hat'
+                elif out_type == 'gamma_hat': out_path = out_path + '/gamma_hat'
+                elif out_type == 'y': out_path = out_path + '/y/' + g
+                elif out_type == 'deepmmse': out_path = out_path + '/deepmmse'
+                elif out_type == 'ibm_hat': out_path = out_path + '/ibm_hat'
+                elif out_type == 'gain': out_path = out_path + '/gain/' + g
+                elif out_type in _OTHER_OUT_TYPES:
+                    raise NotImplementedError('out_type %r belongs to targets without committed models' % out_type)
+                else: raise ValueError('Invalid output type.')
+                if not os.path.exists(out_path): os.makedirs(out_path)
+                if self._weights_epoch != 'explicit' and self._weights_epoch != (model_path, e - 1):
+                    self.load_weights(model_path, e - 1)
+                out, n_frames = self.infer_batch(test_x, test_x_len, out_type, g, int16=(out_type == 'y'))
+                out = out.cpu().numpy()
+                key = {'xi_hat': 'xi_hat', 'gamma_hat': 'gamma_hat', 'gain': 'gain', 'ibm_hat': 'ibm_hat',
+                       'deepmmse': 'd_psd_hat'}.get(out_type)
+                for i, base_name in enumerate(test_x_base_names):
+                    if out_type == 'y':
+                        # polar_synthesis length (T-1)*N_s + N_d of the un-padded utterance (inp_tgt.py:198-214)
+                        n = (n_frames[i] + 1) * self.inp_tgt.N_s
+                        save_wav(out_path + '/' + base_name + '.wav', out[i, :n], self.inp_tgt.f_s)
+                    else:
+                        save_mat(out_path + '/' + base_name + '.mat', out[i, :n_frames[i]], key)

@@ -1,0 +1,90 @@
+"""Mirror of deepxi/sig.py (AnalysisSynthesis :23-69, InputTarget.normalise :189-199, n_frames :201-212).
+
+Same class / method names and argument meaning as the reference; the arithmetic runs in the fused
+CUDA kernels behind dxi_stft / dxi_istft (framing + Hamming window + 512-point real FFT + |.| / angle,
+and the inverse with synthesis window + overlap-add).  numpy in -> numpy out, torch in -> CUDA torch out.
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._tensor import to_dev, ret, device
+
+
+class AnalysisSynthesis:
+    """Analysis and synthesis stages of speech enhancement (sig.py:23-41)."""
+
+    def __init__(self, N_d, N_s, K, f_s):
+        if (N_d, N_s, K) != (512, 256, 512):
+            raise ValueError('the CUDA STFT kernels are specialised for N_d=512, N_s=256, K=512 '
+                             '(main.py:33-35 with T_d=32 ms, T_s=16 ms at 16 kHz)')
+        self.N_d, self.N_s, self.K, self.f_s = N_d, N_s, K, f_s
+        self.n_bins = K // 2 + 1
+
+    # -- analysis -----------------------------------------------------------------------------
+    def _stft(self, x, x_len=None):
+        lib = _lib.load()
+        is_i16 = x.dtype == torch.int16
+        squeeze = x.dim() == 1
+        if squeeze:
+            x = x[None]
+        if x.dim() != 2:
+            raise ValueError('Waveforms are of incorrect rank.')
+        B, L = x.shape
+        if x_len is None:
+            T = -(-L // self.N_s)
+            lens = None
+        else:
+            lens = x_len
+            T = -(-int(lens.max().item()) // self.N_s) if B else 0
+        mag = torch.empty((B, T, self.n_bins), dtype=torch.float32, device=x.device)
+        pha = torch.empty_like(mag)
+        if B and T:
+            _lib.check(lib.dxi_stft(_lib.ptr(x), int(is_i16), _lib.ptr(lens, torch.int32, allow_none=True), B, L, T,
+                                    _lib.ptr(mag), _lib.ptr(pha), _lib.stream_ptr(x.device)))
+        return (mag[0], pha[0]) if squeeze else (mag, pha)
+
+    def polar_analysis(self, x):
+        """Short-time magnitude and phase spectra of a float waveform [L] or [B, L] (sig.py:43-55)."""
+        x, was_np = to_dev(x, torch.float32)
+        mag, pha = self._stft(x)
+        return ret(mag, was_np), ret(pha, was_np)
+
+    # -- synthesis ----------------------------------------------------------------------------
+    def polar_synthesis(self, STMS, STPS):
+        """Waveform of length (T-1)*N_s + N_d from magnitude / phase spectra (sig.py:57-69)."""
+        lib = _lib.load()
+        STMS, was_np = to_dev(STMS, torch.float32)
+        STPS, _ = to_dev(STPS, torch.float32)
+        if STMS.shape != STPS.shape or STMS.shape[-1] != self.n_bins:
+            raise ValueError('STMS / STPS must both be [..., T, %d]' % self.n_bins)
+        squeeze = STMS.dim() == 2
+        if squeeze:
+            STMS, STPS = STMS[None], STPS[None]
+        B, T, _ = STMS.shape
+        n_out = (T + 1) * self.N_s
+        y = torch.empty((B, n_out), dtype=torch.float32, device=STMS.device)
+        if B and T:
+            _lib.check(lib.dxi_istft(_lib.ptr(STMS), None, _lib.ptr(STPS), None, B, T, _lib.ptr(y), None, n_out,
+                                     _lib.stream_ptr(STMS.device)))
+        return ret(y[0] if squeeze else y, was_np)
+
+    def stdct_analysis(self, x):
+        raise NotImplementedError('STDCT (deepxi/dct.py) serves only the unused STDCTXiCD target: out of scope')
+
+    def stdct_synthesis(self, STDCT):
+        raise NotImplementedError('STDCT (deepxi/dct.py) serves only the unused STDCTXiCD target: out of scope')
+
+
+class InputTarget(AnalysisSynthesis):
+    """Computes the input and target of Deep Xi (sig.py:96-108); inference-side methods only."""
+
+    def normalise(self, x):
+        """int16 waveform -> float32 in [-1, 1) (sig.py:189-199).  (observation() fuses this into the STFT.)"""
+        x, was_np = to_dev(x, torch.int16) if not (isinstance(x, torch.Tensor) and x.dtype == torch.int32) else to_dev(x, torch.int32)
+        return ret(x.to(torch.float32) / 32768.0, was_np)
+
+    def n_frames(self, N):
+        """ceil(N / N_s) (sig.py:201-212)."""
+        return int(math.ceil(float(N) / float(self.N_s)))

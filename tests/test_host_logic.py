@@ -1,0 +1,146 @@
+"""CPU tests of the host side: checkpoint index reader, weight shapes / parameter counts, statistics
+loaders, the C-ABI library (loads, exports every symbol of include/deepxi_b200.h), API error behaviour."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from deepxi_b200 import tfbundle, weights, stats, synth, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_checkpoint_index_shapes_and_param_counts(golden_dir):
+    for ver, n_params, n_entries, shards in (('resnet-1.1c_e199', 1949953, 744, 2), ('resnet-1.1n_e179', 1949953, 744, 2),
+                                             ('mhanet-1.1c_e199', 4600321, 206, 1)):
+        path = os.path.join(golden_dir, ver + '_variables.index')
+        num_shards, entries = tfbundle.read_index(path)
+        assert num_shards == shards and len(entries) + 1 == n_entries        # +1: the header entry
+        shapes = tfbundle.keras_weight_shapes(path)
+        assert sum(int(np.prod(s)) for s in shapes.values()) == n_params    # log/summary/<ver>.txt
+        synth_w = weights.synthetic_resnetv2(0) if 'resnet' in ver else weights.synthetic_mhanetv3(0)
+        assert {k: v.shape for k, v in synth_w.items()} == shapes
+
+
+def test_checkpoint_shards_missing_is_loud(golden_dir, tmp_path):
+    import shutil
+    d = tmp_path / 'epoch-199' / 'variables'
+    d.mkdir(parents=True)
+    shutil.copyfile(os.path.join(golden_dir, 'resnet-1.1c_e199_variables.index'), d / 'variables.index')
+    with pytest.raises(FileNotFoundError):
+        weights.load_checkpoint(str(tmp_path), 199)
+
+
+def test_tensor_bundle_round_trip(tmp_path):
+    """Writes a tiny bundle by hand (index table + shard) and reads it back with crc verification."""
+    import struct
+
+    def varint(v):
+        out = b''
+        while True:
+            b = v & 0x7f
+            v >>= 7
+            out += bytes([b | (0x80 if v else 0)])
+            if not v:
+                return out
+
+    arr = np.arange(12, dtype=np.float32).reshape(3, 4)
+    raw = arr.tobytes()
+    shape = b''.join(b'\x12' + varint(len(varint(d)) + 1) + b'\x08' + varint(d) for d in arr.shape)
+    entry = (b'\x08\x01' + b'\x12' + varint(len(shape)) + shape + b'\x18\x00' + b'\x20\x00' + b'\x28' + varint(len(raw))
+             + b'\x35' + struct.pack('<I', tfbundle.masked_crc32c(raw)))
+    header = b'\x08\x01'
+    key = b'layer_with_weights-0/kernel/.ATTRIBUTES/VARIABLE_VALUE'
+
+    def block(items):
+        body = b''
+        for k, v in items:                       # no prefix sharing, one restart
+            body += varint(0) + varint(len(k)) + varint(len(v)) + k + v
+        return body + struct.pack('<II', 0, 1)
+    data = block([(b'', header), (key, entry)])
+    idx = block([(b'\xff', varint(0) + varint(len(data)))])
+    blob = data + b'\x00' + b'\x00' * 4
+    ioff = len(blob)
+    blob += idx + b'\x00' + b'\x00' * 4
+    footer = varint(0) + varint(0) + varint(ioff) + varint(len(idx))
+    footer += b'\x00' * (40 - len(footer)) + struct.pack('<Q', 0xdb4775248b80fb57)
+    (tmp_path / 'variables.index').write_bytes(blob + footer)
+    (tmp_path / 'variables.data-00000-of-00001').write_bytes(raw)
+    w = tfbundle.keras_weights(str(tmp_path / 'variables'), verify_crc=True)
+    assert np.array_equal(w['layer_with_weights-0/kernel'], arr)
+    (tmp_path / 'variables.data-00000-of-00001').write_bytes(raw[:-4] + b'\x00\x00\x00\x01')
+    with pytest.raises(IOError):
+        tfbundle.keras_weights(str(tmp_path / 'variables'), verify_crc=True)
+
+
+def test_stats_loaders(golden_dir):
+    st = stats.load_inp_tgt_pickle(os.path.join(golden_dir, 'resnet-1.1c_inp_tgt.p'))
+    assert (st['N_d'], st['N_s'], st['K'], st['f_s'], st['map_type']) == (512, 256, 512, 16000, 'DBNormalCDF')
+    mu, sg = stats.packaged('resnet-1.1c')
+    assert np.array_equal(mu, st['mu']) and np.array_equal(sg, st['sigma'])
+    assert np.allclose(mu[:4], [4.620561, -1.3624355, -6.7945337, -8.149311])
+    mu_n, _ = stats.packaged('resnet-1.1n')
+    assert np.array_equal(mu, mu_n)                        # the two resnet pickles are byte-identical (F4)
+    mu_m, sg_m = stats.load_stats_mat(os.path.join(golden_dir, 'stats.mat'))
+    assert mu_m.shape == (257,) and np.allclose(mu_m[:2], [4.808382, -1.0482588])
+    assert np.array_equal(stats.packaged('stats.mat')[0], mu_m)
+    assert 0.5 < np.abs(mu_m - mu).max() < 1.0             # the stale file differs by up to 0.94 dB
+    with pytest.raises(KeyError):
+        stats.packaged('nope')
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    header = open(os.path.join(ROOT, 'include', 'deepxi_b200.h')).read()
+    declared = set(re.findall(r'\b(dxi_[a-z0-9_]+)\s*\(', header))
+    declared -= {'dxi_net'}
+    assert declared == set(_lib.SYMBOLS)
+    lib = ctypes.CDLL(built_lib)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    lib.dxi_version.restype = ctypes.c_int
+    assert lib.dxi_version() == 100                        # no compute call: just proves the library loads
+
+
+def test_library_has_no_oracle_or_cpu_fallback():
+    """The product package must not import the oracle, and must refuse to run without CUDA."""
+    import subprocess, sys
+    code = ("import sys; import deepxi_b200, deepxi_b200.model, deepxi_b200.sig, deepxi_b200.gain, deepxi_b200.map; "
+            "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'")
+    subprocess.run([sys.executable, '-c', code], check=True, cwd=ROOT)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'deepxi_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert 'import oracle' not in src and 'from oracle' not in src, f
+    import torch
+    if not torch.cuda.is_available():
+        from deepxi_b200 import gain
+        with pytest.raises(RuntimeError):
+            gain.gfunc(np.ones(4, np.float32), None, 'wf')
+
+
+def test_api_errors_match_reference_conventions():
+    from deepxi_b200 import gain, map as dmap, inp_tgt
+    from deepxi_b200.network.selector import network_selector
+    with pytest.raises(ValueError, match='Invalid gain function type.'):       # gain.py:190
+        gain.gfunc(np.ones(4, np.float32), None, 'bogus')
+    with pytest.raises(ValueError, match='Invalid map_type.'):                 # map.py:42
+        dmap.map_selector('Bogus', None)
+    with pytest.raises(ValueError, match='Invalid inp_tgt type.'):             # inp_tgt.py:71
+        inp_tgt.inp_tgt_selector('Bogus', 512, 256, 512, 16000, map_type='DBNormalCDF', map_params=None)
+    with pytest.raises(ValueError, match='Invalid network type.'):             # selector.py:131
+        network_selector('Bogus', None, 257)
+    with pytest.raises(NotImplementedError):
+        network_selector('ResLSTM', None, 257)
+    with pytest.raises(ValueError):
+        inp_tgt.inp_tgt_selector('MagXi', 400, 160, 512, 16000, map_type='DBNormalCDF', map_params=None)
+    it = inp_tgt.inp_tgt_selector('MagXi', 512, 256, 512, 16000, map_type='DBNormalCDF', map_params=None)
+    assert it.n_feat == it.n_outp == 257 and it.n_frames(64000) == 250 and it.n_frames(39088) == 153
+
+
+def test_synthetic_inputs_are_seeded():
+    a = synth.noisy_speech(2, 4000, seed=7)
+    b = synth.noisy_speech(2, 4000, seed=7)
+    assert a.dtype == np.int16 and np.array_equal(a, b) and np.abs(a).max() > 1000

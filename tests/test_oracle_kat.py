@@ -1,0 +1,178 @@
+"""Pins the oracle (CPU restatement) against the reference's own artefacts and independent implementations.
+
+KAT: set/test_noisy_speech/FB_FB10_07_voice-babble_5dB.wav + out/resnet-1.0c/e180/xi_hat/*.mat
+-> STFT -> MMSE-LSA(xi_hat, xi_hat+1) -> iSTFT -> int16 must equal out/resnet-1.0c/e180/y/mmse-lsa/*.wav
+(fixtures copied by tests/golden/make_golden.py).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+from scipy import special as spsp
+
+from oracle import sig, gain, cdfmap, tcn, attention, wavio, pipeline
+from deepxi_b200 import weights, synth
+
+
+def test_kat_stft_lsa_istft_int16(golden_dir):
+    x, fs = wavio.read_wav_int16(os.path.join(golden_dir, 'kat_noisy.wav'))
+    y_ref, _ = wavio.read_wav_int16(os.path.join(golden_dir, 'kat_y_mmse-lsa_resnet-1.0c_e180.wav'))
+    xi = np.load(os.path.join(golden_dir, 'kat_xi_hat_resnet-1.0c_e180.npy'))
+    assert fs == 16000 and len(x) == 39088 and xi.shape == (153, 257)
+    mag, pha = sig.observation(x)
+    assert mag.shape == (153, 257)                       # ceil(39088/256)
+    y = sig.polar_synthesis(mag * gain.gfunc(xi, xi + np.float32(1.0), 'mmse-lsa'), pha)
+    yi = wavio.float_to_int16(y)
+    assert len(yi) == len(y_ref) == 39424                # (T-1)*256 + 512, not trimmed to the input
+    d = np.abs(yi.astype(np.int32) - y_ref.astype(np.int32))
+    assert d.max() <= 1                                  # bit-exact up to 1 LSB of float rounding
+    assert (d != 0).sum() <= 400
+    snr = 10 * np.log10(np.sum(y_ref.astype(np.float64) ** 2) / max(np.sum(d.astype(np.float64) ** 2), 1e-30))
+    assert snr > 85.0
+
+
+def test_analysis_synthesis_identity(golden_dir):
+    x, _ = wavio.read_wav_int16(os.path.join(golden_dir, 'kat_noisy.wav'))
+    xf = sig.normalise(x)
+    mag, pha = sig.polar_analysis(xf)
+    y = sig.polar_synthesis(mag, pha)
+    assert np.abs(y[256:len(x)] - xf[256:]).max() < 5e-7   # all but the first hop (covered by one frame only)
+
+
+def test_framing_edge_cases():
+    assert sig.n_frames(1) == 1 and sig.n_frames(256) == 1 and sig.n_frames(257) == 2
+    for L in (1, 255, 256, 257, 511, 512, 513, 1000):
+        m, p = sig.polar_analysis(np.ones(L, np.float32))
+        assert m.shape == (-(-L // 256), 257)
+    m, p = sig.polar_analysis(np.zeros(600, np.float32))
+    assert not m.any() and not p.any()                   # zero frames: |X| = 0, angle = 0
+    w = sig.hamming(512)
+    assert abs(w[0] - 0.08) < 1e-7 and abs(w[511] - 0.08) < 1e-7   # periodic=False
+
+
+def test_gains_against_independent_formulas():
+    rng = np.random.default_rng(0)
+    xi = (10.0 ** rng.uniform(-6, 4, 20000)).astype(np.float32)
+    gam = (xi + 1).astype(np.float32)
+    x64, g64 = xi.astype(np.float64), gam.astype(np.float64)
+    nu = x64 / (1 + x64) * g64
+    assert np.allclose(gain.mmse_lsa(xi, gam), x64 / (1 + x64) * np.exp(0.5 * spsp.exp1(nu)), rtol=2e-6)
+    st = gain.mmse_stsa(xi, gam)
+    exact = gain.mmse_stsa_exact(xi, gam)
+    below = nu < 170.0
+    assert np.allclose(st[below], exact[below], rtol=3e-6)
+    assert np.allclose(st[nu > 180.0], (x64 / (1 + x64))[nu > 180.0], rtol=1e-6)      # Inf/NaN -> Wiener (gain.py:42-44)
+    assert np.allclose(gain.srwf(xi), np.sqrt(x64 / (1 + x64)), rtol=1e-6)
+    assert np.allclose(gain.cwf(xi), np.sqrt(x64) / (1 + np.sqrt(x64)), rtol=1e-6)
+    assert np.array_equal(gain.irm(xi), gain.srwf(xi))
+    assert np.array_equal(gain.ibm(np.array([0.5, 1.0, 1.0000001, 7.0], np.float32)), [0, 0, 1, 1])
+    assert np.allclose(gain.deepmmse(xi, gam), 1 / (1 + x64) + x64 / (g64 * (1 + x64)), rtol=1e-6)
+    with pytest.raises(ValueError):
+        gain.gfunc(xi, gam, 'nope')
+
+
+def test_cdf_map_round_trip_and_saturation(xi_stats):
+    mu, sg = xi_stats['resnet-1.1c/mu'], xi_stats['resnet-1.1c/sigma']
+    assert abs(mu[0] - 4.620561) < 1e-6 and abs(sg[0] - 26.629541) < 1e-5     # SURVEY C2 anchors
+    rng = np.random.default_rng(1)
+    xb = rng.uniform(1e-4, 1 - 1e-4, (64, 257)).astype(np.float32)
+    xi = cdfmap.normal_cdf_inverse(xb, mu, sg)
+    assert np.abs(cdfmap.normal_cdf_map(xi, mu, sg) - xb).max() < 2e-6
+    # norm.ppf as an independent erfinv
+    from scipy.stats import norm
+    assert np.allclose(10 * np.log10(xi.astype(np.float64)), norm.ppf(xb.astype(np.float64)) * sg + mu, atol=2e-4)
+    assert cdfmap.normal_cdf_inverse(np.float32(2.0 ** -26), mu[:1], sg[:1])[0] == 0.0          # 2x-1 rounds to -1
+    assert np.isinf(cdfmap.normal_cdf_inverse(np.float32(1.0), mu[:1], sg[:1])[0])
+
+
+def _torch_resnet_reference(inp, w, padding):
+    """Independent implementation with torch.nn.functional conv1d / layer_norm."""
+    import torch.nn.functional as F
+    g = lambda li, v: torch.from_numpy(w['layer_with_weights-%d/%s' % (li, v)])
+    conv = lambda x, li, d=1: F.conv1d(
+        F.pad(x, ((g(li, 'kernel').shape[0] - 1) * d, 0) if padding == 'causal' else
+              ((g(li, 'kernel').shape[0] - 1) * d // 2,) * 2),
+        g(li, 'kernel').permute(2, 1, 0).contiguous(), g(li, 'bias'), dilation=d)
+    x = torch.from_numpy(inp).permute(0, 2, 1)
+    h = conv(x, 0)
+    h = F.relu(F.layer_norm(h.permute(0, 2, 1), (256,), g(1, 'gamma'), None, 1e-6)).permute(0, 2, 1)
+    li = 2
+    for d in tcn.dilation_rates():
+        y = h
+        for dd in (1, d, 1):
+            c = y.shape[1]
+            y = F.layer_norm(F.relu(y).permute(0, 2, 1), (c,), None, None, 1e-6).permute(0, 2, 1)
+            y = conv(y, li, dd)
+            li += 1
+        h = h + y
+    return torch.sigmoid(conv(h, li)).permute(0, 2, 1).numpy()
+
+
+@pytest.mark.parametrize('padding', ['causal', 'same'])
+def test_resnetv2_oracle_vs_torch_functional(padding):
+    w = weights.synthetic_resnetv2(0)
+    inp, _, _ = sig.observation_batch(synth.noisy_speech(2, 12000, seed=3), [12000, 9000])
+    a = tcn.resnetv2_forward(inp, w, padding=padding)
+    b = _torch_resnet_reference(inp, w, padding)
+    assert a.shape == (2, 47, 257)
+    assert np.abs(a - b).max() < 2e-5
+
+
+def test_resnetv2_causality_and_padding_dependence():
+    w = weights.synthetic_resnetv2(0)
+    inp, _, _ = sig.observation_batch(synth.noisy_speech(1, 40000, seed=4), [40000])
+    full = tcn.resnetv2_forward(inp, w, padding='causal')
+    cut = tcn.resnetv2_forward(inp[:, :100], w, padding='causal')
+    assert np.abs(full[:, :100] - cut).max() < 1e-6        # causal: the past never sees the future
+    full_s = tcn.resnetv2_forward(inp, w, padding='same')
+    cut_s = tcn.resnetv2_forward(inp[:, :100], w, padding='same')
+    assert np.abs(full_s[:, :100] - cut_s).max() > 1e-4    # non-causal: depends on what follows
+
+
+def test_mhanetv3_oracle_vs_torch_sdpa():
+    import torch.nn.functional as F
+    w = weights.synthetic_mhanetv3(0)
+    inp, _, _ = sig.observation_batch(synth.noisy_speech(2, 9000, seed=5), [9000, 6000])
+    a = attention.mhanetv3_forward(inp, w, mask_mode='none')
+    g = lambda li, v: torch.from_numpy(w['layer_with_weights-%d/%s' % (li, v)])
+    x = torch.from_numpy(inp)
+    T = x.shape[1]
+    x = F.relu(F.layer_norm(x @ g(0, 'kernel')[0], (256,), g(1, 'gamma'), g(1, 'beta'), 1e-6)) + g(2, 'embeddings')[:T]
+    li = 3
+    for _ in range(5):
+        q = torch.einsum('bni,hio->bhno', x, g(li, 'query_kernel'))
+        k = torch.einsum('bni,hio->bhno', x, g(li, 'key_kernel'))
+        v = torch.einsum('bni,hio->bhno', x, g(li, 'value_kernel'))
+        att = F.scaled_dot_product_attention(q, k, v)          # scale 1/sqrt(32), no mask
+        mha = torch.einsum('bhni,hio->bno', att, g(li, 'projection_kernel'))
+        a1 = F.layer_norm(x + mha, (256,), g(li + 1, 'gamma'), g(li + 1, 'beta'), 1e-6)
+        f = F.relu(a1 @ g(li + 2, 'kernel')[0] + g(li + 2, 'bias')) @ g(li + 3, 'kernel')[0] + g(li + 3, 'bias')
+        x = F.layer_norm(a1 + f, (256,), g(li + 4, 'gamma'), g(li + 4, 'beta'), 1e-6)
+        li += 5
+    b = torch.sigmoid(x @ g(li, 'kernel')[0] + g(li, 'bias')).numpy()
+    assert np.abs(a - b).max() < 2e-5
+    # causal+pad: valid rows must not depend on later frames
+    c_full = attention.mhanetv3_forward(inp[:1], w, mask_mode='causal+pad')
+    c_cut = attention.mhanetv3_forward(inp[:1, :20], w, mask_mode='causal+pad')
+    assert np.abs(c_full[:, :20] - c_cut).max() < 1e-5
+
+
+def test_pipeline_out_types(xi_stats):
+    mu, sg = xi_stats['resnet-1.1c/mu'], xi_stats['resnet-1.1c/sigma']
+    w = weights.synthetic_resnetv2(0, n_blocks=2)
+    x = synth.noisy_speech(2, 5000, seed=6)
+    import oracle.tcn as otcn
+    fwd = otcn.resnetv2_forward
+    otcn_forward = lambda inp, ww, padding='causal': fwd(inp, ww, n_blocks=2, padding=padding)
+    pipeline.tcn.resnetv2_forward, keep = otcn_forward, pipeline.tcn.resnetv2_forward
+    try:
+        ys = pipeline.infer(x, [5000, 3000], w, mu, sg, out_type='y')
+        assert [len(y) for y in ys] == [(20 + 1) * 256, (12 + 1) * 256]
+        xi = pipeline.infer(x, [5000, 3000], w, mu, sg, out_type='xi_hat')
+        ib = pipeline.infer(x, [5000, 3000], w, mu, sg, out_type='ibm_hat')
+        assert np.array_equal(ib[0], xi[0] > 1.0)
+        with pytest.raises(ValueError):
+            pipeline.infer(x, [5000, 3000], w, mu, sg, out_type='bogus')
+    finally:
+        pipeline.tcn.resnetv2_forward = keep
