@@ -23,7 +23,7 @@ MASK_MODES = {'none': 0, 'causal+pad': 1}
 SYMBOLS = ['dxi_last_error', 'dxi_version', 'dxi_device_check', 'dxi_stft', 'dxi_istft', 'dxi_map_gain', 'dxi_gfunc',
            'dxi_cdf_map', 'dxi_enhance', 'dxi_net_create', 'dxi_net_load', 'dxi_net_finalize',
            'dxi_net_workspace_bytes', 'dxi_net_forward', 'dxi_net_destroy', 'dxi_launch_count',
-           'dxi_launch_count_reset', 'dxi_selftest_umma']
+           'dxi_launch_count_reset', 'dxi_selftest_umma', 'dxi_profile_enable', 'dxi_profile_read']
 
 
 class DxiError(RuntimeError):
@@ -68,6 +68,10 @@ def load():
     lib.dxi_launch_count.argtypes = []
     lib.dxi_launch_count_reset.restype = None
     lib.dxi_selftest_umma.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    lib.dxi_profile_enable.argtypes = [i32]
+    lib.dxi_profile_enable.restype = None
+    lib.dxi_profile_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
+    lib.dxi_profile_read.restype = i32
     for name in ('dxi_stft', 'dxi_istft', 'dxi_map_gain', 'dxi_gfunc', 'dxi_cdf_map', 'dxi_enhance', 'dxi_net_create',
                  'dxi_net_load', 'dxi_net_finalize', 'dxi_net_forward', 'dxi_net_destroy', 'dxi_selftest_umma'):
         getattr(lib, name).restype = i32
@@ -109,6 +113,17 @@ def gtype_code(gtype):
     if gtype not in GTYPES:
         raise ValueError('Invalid gain function type.')
     return GTYPES[gtype]
+
+
+def profile_enable(on=True):
+    load().dxi_profile_enable(int(bool(on)))
+
+
+def profile_read(key):
+    """(total milliseconds, launches) accumulated for a named kernel group since the last read."""
+    ms, n = ctypes.c_double(0.0), ctypes.c_int64(0)
+    check(load().dxi_profile_read(key.encode(), ctypes.byref(ms), ctypes.byref(n)))
+    return ms.value, n.value
 
 
 def launch_count():

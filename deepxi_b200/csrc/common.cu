@@ -1,6 +1,9 @@
 // Error reporting, device check and launch accounting for libdeepxi_b200.so.
 #include "common.cuh"
 #include <stdarg.h>
+#include <map>
+#include <string>
+#include <vector>
 
 namespace dxi {
 
@@ -34,9 +37,53 @@ int check_device() {
   return cached_rc;
 }
 
+// ---- per-kernel timing ------------------------------------------------------------------------------
+struct Span { cudaEvent_t a, b; int launches; };
+static thread_local bool g_prof_on = false;
+static thread_local std::map<std::string, std::vector<Span>>* g_spans = nullptr;
+
+ProfScope::ProfScope(const char* key, cudaStream_t st, int launches) : span_(nullptr), st_(st) {
+  if (!g_prof_on) return;
+  if (!g_spans) g_spans = new std::map<std::string, std::vector<Span>>();
+  Span sp{};
+  sp.launches = launches;
+  if (cudaEventCreate(&sp.a) != cudaSuccess || cudaEventCreate(&sp.b) != cudaSuccess) return;
+  cudaEventRecord(sp.a, st);
+  auto& v = (*g_spans)[key];
+  v.push_back(sp);
+  span_ = reinterpret_cast<void*>(static_cast<uintptr_t>(v.size()));   // index + 1
+  key_ = key;
+}
+ProfScope::~ProfScope() {
+  if (!span_) return;
+  auto& v = (*g_spans)[key_];
+  cudaEventRecord(v[reinterpret_cast<uintptr_t>(span_) - 1].b, st_);
+}
+
 }  // namespace dxi
 
 extern "C" {
+void dxi_profile_enable(int on) { dxi::g_prof_on = on != 0; }
+int dxi_profile_read(const char* key, double* total_ms, int64_t* launches) {
+  double ms = 0.0;
+  int64_t n = 0;
+  if (dxi::g_spans) {
+    auto it = dxi::g_spans->find(key);
+    if (it != dxi::g_spans->end()) {
+      for (auto& sp : it->second) {
+        float t = 0.0f;
+        cudaEventSynchronize(sp.b);
+        if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) { ms += t; n += sp.launches; }
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+      }
+      dxi::g_spans->erase(it);
+    }
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = n;
+  return DXI_OK;
+}
 const char* dxi_last_error(void) { return dxi::g_err; }
 int dxi_version(void) { return 100; }
 int dxi_device_check(void) { return dxi::check_device(); }

@@ -44,4 +44,14 @@ inline int cuda_fail(cudaError_t e, const char* what) {
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Optional per-kernel timing (dxi_profile_enable): CUDA events recorded on the launching stream around a
+// named group of launches; dxi_profile_read sums the elapsed times.  Off by default (no events recorded).
+struct ProfScope {
+  ProfScope(const char* key, cudaStream_t st, int launches);
+  ~ProfScope();
+  void* span_;
+  cudaStream_t st_;
+  const char* key_ = nullptr;
+};
+
 }  // namespace dxi

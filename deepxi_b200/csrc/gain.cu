@@ -74,6 +74,7 @@ extern "C" DXI_API int dxi_map_gain(const float* xbar, const float* mu, const fl
   DXI_REQUIRE(xi_hat || gain || ibm, "dxi_map_gain: no output requested");
   int64_t n = n_rows * n_bins;
   if (n == 0) return DXI_OK;
+  ProfScope prof("map_gain", as_stream(stream), 1);
   map_gain_kernel<4><<<grid_for(n, 4), 256, 0, as_stream(stream)>>>(xbar, mu, sigma, n, n_bins, gtype, xi_hat, gain, ibm);
   DXI_LAUNCHED("map_gain_kernel");
   return DXI_OK;
@@ -86,6 +87,7 @@ extern "C" DXI_API int dxi_gfunc(const float* xi, const float* gamma, int64_t n,
   bool needs_gamma = gtype == DXI_G_MMSE_LSA || gtype == DXI_G_MMSE_STSA || gtype == DXI_G_DEEPMMSE;
   DXI_REQUIRE(gamma || !needs_gamma, "dxi_gfunc: this gain function needs gamma");
   if (n == 0) return DXI_OK;
+  ProfScope prof("gfunc", as_stream(stream), 1);
   gfunc_kernel<<<grid_for(n, 1), 256, 0, as_stream(stream)>>>(xi, gamma, n, gtype, G);
   DXI_LAUNCHED("gfunc_kernel");
   return DXI_OK;
@@ -98,6 +100,7 @@ extern "C" DXI_API int dxi_cdf_map(const float* xi, const float* mu, const float
   DXI_REQUIRE(n_rows >= 0 && n_bins > 0, "dxi_cdf_map: bad shape");
   int64_t n = n_rows * n_bins;
   if (n == 0) return DXI_OK;
+  ProfScope prof("cdf_map", as_stream(stream), 1);
   cdf_map_kernel<<<grid_for(n, 1), 256, 0, as_stream(stream)>>>(xi, mu, sigma, n, n_bins, xbar);
   DXI_LAUNCHED("cdf_map_kernel");
   return DXI_OK;

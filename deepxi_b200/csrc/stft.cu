@@ -267,6 +267,7 @@ static int istft_launch(int mode, const float* mag, const float* g_or_xbar, cons
   const int64_t total = (int64_t)B * strips;
   const int grid = (int)(total < 148 * 3 ? total : 148 * 3);
   const size_t smem = sizeof(IstftSmem);
+  ProfScope prof(mode == 0 ? "istft" : "enhance", st, 1);
   if (mode == 0) {
     DXI_CUDA(cudaFuncSetAttribute(istft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     istft_kernel<0><<<grid, 256, smem, st>>>(mag, g_or_xbar, phase, mu, sigma, gtype, n_frames, B, Tmax, strips,
@@ -298,6 +299,7 @@ extern "C" DXI_API int dxi_stft(const void* wav, int wav_is_i16, const int32_t* 
   const int grid = (int)(total < 148 * 3 ? total : 148 * 3);
   const size_t smem = sizeof(StftSmem);
   const int elem = wav_is_i16 ? 2 : 4;
+  ProfScope prof("stft", st, 1);
   const int vec_ok = ((reinterpret_cast<uintptr_t>(wav) % 16) == 0 && ((wav_stride * elem) % 16) == 0) ? 1 : 0;
   if (wav_is_i16) {
     DXI_CUDA(cudaFuncSetAttribute(stft_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

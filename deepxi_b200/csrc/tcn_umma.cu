@@ -465,6 +465,7 @@ int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, floa
     auto kern = stem_head_kernel<KIN, NOUT, true>;
     DXI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int groups = (T + SM_ROWS - 1) / SM_ROWS;
+    ProfScope prof("tcn_stem", st, 1);
     kern<<<B * groups, 256, smem, st>>>(mag, net.dev_tensor(0, "kernel"), net.dev_tensor(0, "bias"), net.dev_tensor(1, "gamma"),
                                         h, T, tiles, groups);
     DXI_LAUNCHED("stem_head_kernel<stem>");
@@ -479,6 +480,8 @@ int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, floa
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
   const int nd = n_dilations(c.max_d_rate);
+  {
+  ProfScope prof_stages("tcn_stage", st, c.n_blocks + 1);
   for (int s = 0; s <= c.n_blocks; ++s) {
     StageArgs a{};
     a.img = reinterpret_cast<const unsigned char*>(net.d_umma) + (size_t)s * IMG_BYTES;
@@ -494,6 +497,7 @@ int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, floa
     else       tcn_stage_kernel<false><<<grid, 160, smem, st>>>(a);
     DXI_LAUNCHED("tcn_stage_kernel");
   }
+  }
   // ---- head (fp32 CUDA cores): tiled h -> sigmoid(W h + b)
   {
     constexpr int KIN = 256, NOUT = 257, LD = 258;
@@ -502,6 +506,7 @@ int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, floa
     DXI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     const int groups = (T + SM_ROWS - 1) / SM_ROWS;
     const int li = 2 + 3 * c.n_blocks;
+    ProfScope prof("tcn_head", st, 1);
     kern<<<B * groups, 256, smem2, st>>>(h, net.dev_tensor(li, "kernel"), net.dev_tensor(li, "bias"), nullptr, xbar, T, tiles, groups);
     DXI_LAUNCHED("stem_head_kernel<head>");
   }

@@ -168,6 +168,13 @@ DXI_API int dxi_net_destroy(dxi_net_t* h);
 DXI_API int64_t dxi_launch_count(void);
 DXI_API void dxi_launch_count_reset(void);
 
+/* Per-kernel timing for bench.py: when enabled, the library brackets each named group of launches
+ * ("stft", "istft", "map_gain", "tcn_stage", "tcn_stem", "tcn_head", ...) with CUDA events on the
+ * launching stream.  dxi_profile_read synchronises on those events, returns the summed milliseconds and
+ * the number of launches they covered, and clears the group.  Per calling thread. */
+DXI_API void dxi_profile_enable(int on);
+DXI_API int dxi_profile_read(const char* key, double* total_ms, int64_t* launches);
+
 /* Self test of the tcgen05 / TMEM building blocks: D[128,N] = A[128,K] * B[K,N] with fp16 operands
  * (A from tensor memory, B from shared memory) written to `d_out` (float32 [128,N]).
  * a_host_layout / b: device fp16 row-major [128,K] and [N,K].  variant selects descriptor encodings
