@@ -23,7 +23,7 @@ MASK_MODES = {'none': 0, 'causal+pad': 1}
 SYMBOLS = ['dxi_last_error', 'dxi_version', 'dxi_device_check', 'dxi_stft', 'dxi_istft', 'dxi_map_gain', 'dxi_gfunc',
            'dxi_cdf_map', 'dxi_enhance', 'dxi_net_create', 'dxi_net_load', 'dxi_net_finalize',
            'dxi_net_workspace_bytes', 'dxi_net_forward', 'dxi_net_destroy', 'dxi_launch_count',
-           'dxi_launch_count_reset', 'dxi_selftest_umma', 'dxi_profile_enable', 'dxi_profile_read']
+           'dxi_launch_count_reset', 'dxi_selftest_umma', 'dxi_profile_enable', 'dxi_profile_read', 'dxi_debug_tcn_clocks']
 
 
 class DxiError(RuntimeError):
@@ -72,6 +72,8 @@ def load():
     lib.dxi_profile_enable.restype = None
     lib.dxi_profile_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     lib.dxi_profile_read.restype = i32
+    lib.dxi_debug_tcn_clocks.argtypes = [vp, i32]
+    lib.dxi_debug_tcn_clocks.restype = None
     for name in ('dxi_stft', 'dxi_istft', 'dxi_map_gain', 'dxi_gfunc', 'dxi_cdf_map', 'dxi_enhance', 'dxi_net_create',
                  'dxi_net_load', 'dxi_net_finalize', 'dxi_net_forward', 'dxi_net_destroy', 'dxi_selftest_umma'):
         getattr(lib, name).restype = i32

@@ -17,7 +17,9 @@
 // straight into tensor memory (thread r owns frame r: TMEM lane r), so LayerNorm is a purely
 // thread-local reduction over the accumulator row and nothing is staged through shared memory.
 // TMEM columns: [0,256) accumulators / fp32 residual row, [256,512) A operands (hi | lo).
-// Warps 0-3: epilogue (one thread per frame); warp 4: weight load (bulk async copy) + MMA issue.
+// Warps 0-7: epilogue (two threads per frame, half the columns each; TMEM lane quarter = warp & 3);
+// warp 8: weight load (bulk async copy), L2 prefetch of the next tile, MMA issue.  GEMM2 is committed in four
+// column groups and GEMM3 is issued in eight K-chunks so that tensor-core time hides behind the epilogue.
 #include <vector>
 #include "net.cuh"
 #include "umma.cuh"
@@ -48,151 +50,246 @@ struct StageArgs {
   int T, tiles_per_utt, n_tiles, Ts;
   int shift0, shift1, shift2;    // frame offsets of the three taps: tap j reads frame t - shift_j
   int has_back, has_front;
+  long long* dbg;               // optional: clock64 stamps of the epilogue phases (16 per tile), see dxi_debug_tcn_clocks
 };
 
 __device__ __forceinline__ float relu(float x) { return fmaxf(x, 0.0f); }
 
-// u(x) over a 64-wide accumulator row (+bias): ReLU -> LayerNorm (two-pass, biased variance, eps 1e-6)
-__device__ __forceinline__ void relu_ln64(float (&a)[32], float (&b)[32], const float* bias) {
+constexpr int EPI_WARPS = 8;                      // 2 warps per TMEM lane quarter: each owns half the columns of a row
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int STAGE_THREADS = EPI_THREADS + 32;   // + 1 warp: weight load, L2 prefetch, MMA issue
+
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// LayerNorm statistics of one row that is split between two threads (n values each): every thread
+// contributes (mean, M2 = sum of squared deviations from its own mean); Chan's formula merges them.
+__device__ __forceinline__ void ln_merge(float2* red, int row, int hb, float n, float mean_h, float m2_h, float& inv, float& off) {
+  red[hb * TILE + row] = make_float2(mean_h, m2_h);
+  epi_barrier();
+  const float2 o = red[(hb ^ 1) * TILE + row];
+  const float mean = 0.5f * (mean_h + o.x);
+  const float dm = mean_h - o.x;
+  const float var = (m2_h + o.y + dm * dm * (0.5f * n)) / (2.0f * n);    // biased variance over 2n values
+  inv = rsqrtf(var + 1e-6f);
+  off = -mean * inv;
+}
+
+// u(x) = ReLU -> LayerNorm over a 64-wide row of which this thread holds 32 values (two-pass locally)
+__device__ __forceinline__ void relu_ln_half(float (&a)[32], const float* bias, float2* red, int row, int hb) {
   float s = 0.0f;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) { a[j] = relu(a[j] + bias[j]); b[j] = relu(b[j] + bias[32 + j]); s += a[j] + b[j]; }
-  const float mean = s * (1.0f / 64.0f);
+  for (int j = 0; j < 32; ++j) { a[j] = relu(a[j] + bias[j]); s += a[j]; }
+  const float mean_h = s * (1.0f / 32.0f);
   float q = 0.0f;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) { const float da = a[j] - mean, db = b[j] - mean; q = fmaf(da, da, q); q = fmaf(db, db, q); }
-  const float inv = rsqrtf(q * (1.0f / 64.0f) + 1e-6f);
-  const float off = -mean * inv;
+  for (int j = 0; j < 32; ++j) { const float d = a[j] - mean_h; q = fmaf(d, d, q); }
+  float inv, off;
+  ln_merge(red, row, hb, 32.0f, mean_h, q, inv, off);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) { a[j] = fmaf(a[j], inv, off); b[j] = fmaf(b[j], inv, off); }
+  for (int j = 0; j < 32; ++j) a[j] = fmaf(a[j], inv, off);
 }
 
 template <bool SPLIT>
-__global__ void __launch_bounds__(160, 1) tcn_stage_kernel(const StageArgs p) {
+__global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const StageArgs p) {
   extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, bar_a, bar_d;
+  __shared__ __align__(8) uint64_t bar_w, bar_a1, bar_a2, bar_a3[8], bar_d1, bar_d2[4], bar_d3;
   __shared__ uint32_t tmem_slot;
+  __shared__ float2 red[3][2 * TILE];
   unsigned char* sW = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const float* sBias = reinterpret_cast<const float*>(sW + IMG_BIAS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  if (warp == 4) tmem_alloc(&tmem_slot, 512);
+  if (warp == EPI_WARPS) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     mbar_init(&bar_w, 1);
-    mbar_init(&bar_a, 128);
-    mbar_init(&bar_d, 1);
+    mbar_init(&bar_a1, EPI_THREADS);
+    mbar_init(&bar_a2, EPI_THREADS);
+    for (int i = 0; i < 8; ++i) mbar_init(&bar_a3[i], EPI_THREADS / 2);
+    mbar_init(&bar_d1, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_d2[i], 1);
+    mbar_init(&bar_d3, 1);
     fence_mbar_init();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tb = tmem_slot;
+  // The CTA owns the SM's whole tensor memory (512 columns, one CTA per SM), so the allocation starts at
+  // lane 0 / column 0: TMEM addresses below are compile-time constants.
+  if (tmem_slot != 0) __trap();
+  constexpr uint32_t tb = 0;
 
-  if (warp == 4) {
-    // ================= weight load + MMA issue (one elected lane) =================
-    if (lane == 0) {
+  if (warp == EPI_WARPS) {
+    // ================= weight load, L2 prefetch of the next tile, MMA issue =================
+    // The whole warp runs this code convergently; single-thread operations elect a lane inside the asm.
+    if (elect_one()) {
       mbar_arrive_expect_tx(&bar_w, IMG_BYTES);
       for (int off = 0; off < IMG_BYTES; off += 16384) {
         const int n = IMG_BYTES - off < 16384 ? IMG_BYTES - off : 16384;
         bulk_g2s(sW + off, p.img + off, n, &bar_w);
       }
-      mbar_wait(&bar_w, 0);
-      const uint32_t w_hi = smem_u32(sW), w_lo = smem_u32(sW + IMG_PART);
-      const uint32_t id64 = make_idesc_f16(TILE, 64), id256 = make_idesc_f16(TILE, 256);
-      uint32_t pa = 0;
-      // one product = (a_hi, w_hi) [+ (a_lo, w_hi) + (a_hi, w_lo)]
-      auto gemm = [&](uint32_t d_col, uint32_t a_hi, uint32_t a_lo, uint32_t w_off, int n_rows, int k_steps, uint32_t idesc) {
-        uint32_t acc = 0;
-        for (int part = 0; part < (SPLIT ? 3 : 1); ++part) {
-          const uint32_t a0 = part == 1 ? a_lo : a_hi;
-          const uint32_t w0 = (part == 2 ? w_lo : w_hi) + w_off;
-          for (int ks = 0; ks < k_steps; ++ks) {
-            const uint64_t bdesc = make_smem_desc_sw128(w0 + (ks >> 2) * n_rows * 128 + (ks & 3) * 32);
-            mma_ts(tb + d_col, tb + a0 + 8 * ks, bdesc, idesc, acc);
-            acc = 1;
+    }
+    __syncwarp();
+    mbar_wait(&bar_w, 0);
+    const uint32_t w_hi = smem_u32(sW), w_lo = w_hi + IMG_PART;
+    constexpr uint32_t id64 = make_idesc_f16(TILE, 64);
+    constexpr int NPART = SPLIT ? 3 : 1;          // (a_hi, w_hi) [+ (a_lo, w_hi) + (a_hi, w_lo)]
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      {   // pull the next tile's residual rows and c1 rows into L2 while this tile is being computed
+        const int nt = tile + gridDim.x;
+        if (nt < p.n_tiles) {
+          const char* hn = reinterpret_cast<const char*>(p.h + (size_t)nt * (TILE * 256));
+          if (lane < 8) prefetch_l2(hn + lane * 16384, 16384);
+          if (p.has_back && lane >= 16 && lane < (SPLIT ? 32 : 24)) {
+            const int b = nt / p.tiles_per_utt, t0 = (nt - b * p.tiles_per_utt) * TILE;
+            const int lo_row = t0 - (p.shift0 > 0 ? p.shift0 : 0) + C1_PAD;
+            const int n_rows = TILE + (p.shift0 > 0 ? p.shift0 : 0) - (p.shift2 < 0 ? p.shift2 : 0);
+            const __half* cb = p.c1_in + (size_t)b * 2 * 8 * p.Ts * 8;
+            prefetch_l2(cb + ((size_t)(lane - 16) * p.Ts + lo_row) * 8, n_rows * 16);
           }
         }
-      };
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        if (p.has_back) {
-          mbar_wait(&bar_a, pa); pa ^= 1; tc_fence_after();
-          gemm(COL_ACC, COL_A1_HI, COL_A1_LO, IMG_W2, 64, 12, id64);      // c2 = W2 (*) c1 taps
-          mma_commit(&bar_d);
-          mbar_wait(&bar_a, pa); pa ^= 1; tc_fence_after();
-          gemm(COL_ACC, COL_A2_HI, COL_A2_LO, IMG_W3, 256, 4, id256);     // W3 u(c2)
-          mma_commit(&bar_d);
+        __syncwarp();
+      }
+      if (p.has_back) {
+        mbar_wait(&bar_a1, ph); tc_fence_after();
+        {   // c2 = W2 (*) [c1(t-s0) | c1(t-s1) | c1(t-s2)] : K = 192, N = 64
+          uint32_t acc = 0;
+#pragma unroll
+          for (int part = 0; part < NPART; ++part) {
+            const uint32_t a0 = part == 1 ? COL_A1_LO : COL_A1_HI, w0 = (part == 2 ? w_lo : w_hi) + IMG_W2;
+#pragma unroll
+            for (int ks = 0; ks < 12; ++ks) {
+              mma_ts_elect(COL_ACC, a0 + 8 * ks, make_smem_desc_sw128(w0 + (ks >> 2) * 64 * 128 + (ks & 3) * 32), id64, acc);
+              acc = 1;
+            }
+          }
         }
-        if (p.has_front) {
-          mbar_wait(&bar_a, pa); pa ^= 1; tc_fence_after();
-          gemm(COL_ACC, COL_A3_HI, COL_A3_LO, IMG_W1, 64, 16, id64);      // W1' u(h)
-          mma_commit(&bar_d);
+        mma_commit_elect(&bar_d1);
+        mbar_wait(&bar_a2, ph); tc_fence_after();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {   // W3 u(c2): K = 64, N = 256 in four column groups, each committed on its own
+          uint32_t acc = 0;
+#pragma unroll
+          for (int part = 0; part < NPART; ++part) {
+            const uint32_t a0 = part == 1 ? COL_A2_LO : COL_A2_HI, w0 = (part == 2 ? w_lo : w_hi) + IMG_W3 + g * 64 * 128;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              mma_ts_elect(COL_ACC + 64 * g, a0 + 8 * ks, make_smem_desc_sw128(w0 + ks * 32), id64, acc);
+              acc = 1;
+            }
+          }
+          mma_commit_elect(&bar_d2[g]);
         }
       }
+      if (p.has_front) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {   // W1' u(h): K = 256 in eight 32-channel chunks, issued as the epilogue produces them
+          mbar_wait(&bar_a3[cc], ph);
+          if (cc == 0) continue;           // D overwrites residual columns [0,64): wait until chunks 0 AND 1 are consumed
+          tc_fence_after();
+#pragma unroll
+          for (int c2 = (cc == 1 ? 0 : cc); c2 <= cc; ++c2)
+#pragma unroll
+            for (int part = 0; part < NPART; ++part) {
+              const uint32_t a0 = part == 1 ? COL_A3_LO : COL_A3_HI, w0 = (part == 2 ? w_lo : w_hi) + IMG_W1;
+#pragma unroll
+              for (int ks = 2 * c2; ks < 2 * c2 + 2; ++ks) {
+                mma_ts_elect(COL_ACC, a0 + 8 * ks, make_smem_desc_sw128(w0 + (ks >> 2) * 64 * 128 + (ks & 3) * 32), id64, acc);
+                acc = 1;
+              }
+            }
+        }
+        mma_commit_elect(&bar_d3);
+      }
+      ph ^= 1;
     }
   } else {
-    // ================= epilogue: thread tid owns frame (row) tid of the tile =================
+    // ================= epilogue: threads (q, lane) and (q+4, lane) share frame r = 32 q + lane =================
     mbar_wait(&bar_w, 0);        // biases live in the weight image
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const int hb = warp >> 2, row = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t t_acc = tb + lane_addr + COL_ACC;
-    uint32_t pd = 0;
+    uint32_t ph = 0;
+    const bool stamp = p.dbg != nullptr && tid == 0;
+#define DXI_STAMP(k) do { if (stamp) p.dbg[(size_t)tile * 16 + (k)] = clock64(); } while (0)
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TILE;
-      const int t = t0 + tid;
+      const int t = t0 + row;
+      DXI_STAMP(0);
       const bool valid = t < p.T;
-      float* hrow = p.h + (size_t)tile * (TILE * 256) + tid * 4;          // + c4 * 512
+      float* hrow = p.h + (size_t)tile * (TILE * 256) + row * 4;          // + c4 * 512
+      // residual values of the first chunk this thread owns: issue the loads before anything else
+      float4 hv[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) hv[q] = *reinterpret_cast<const float4*>(hrow + (size_t)(hb * 8 + q) * (TILE * 4));
       if (p.has_back) {
-        // ---- A1: three shifted copies of c1 (hi | lo planes) -> TMEM
+        // ---- A1: three shifted copies of c1 (hi | lo planes) -> TMEM; this thread moves units 4hb..4hb+3
         const __half* cb = p.c1_in + (size_t)b * 2 * 8 * p.Ts * 8;
+        uint4 qv[3][SPLIT ? 2 : 1][4];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           const int shift = j == 0 ? p.shift0 : (j == 1 ? p.shift1 : p.shift2);
-          const size_t row = (size_t)(t - shift + C1_PAD);
+          const size_t r_in = (size_t)(t - shift + C1_PAD);
+#pragma unroll
+          for (int plane = 0; plane < (SPLIT ? 2 : 1); ++plane)
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              qv[j][plane][u] = __ldg(reinterpret_cast<const uint4*>(cb + ((size_t)(plane * 8 + 4 * hb + u) * p.Ts + r_in) * 8));
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
 #pragma unroll
           for (int plane = 0; plane < (SPLIT ? 2 : 1); ++plane) {
-            uint32_t r[32];
+            uint32_t r[16];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const uint4 q = __ldg(reinterpret_cast<const uint4*>(cb + ((size_t)(plane * 8 + u) * p.Ts + row) * 8));
-              r[4 * u] = q.x; r[4 * u + 1] = q.y; r[4 * u + 2] = q.z; r[4 * u + 3] = q.w;
-            }
-            tmem_st32(tb + lane_addr + (plane ? COL_A1_LO : COL_A1_HI) + 32 * j, r);
+            for (int u = 0; u < 4; ++u) { r[4 * u] = qv[j][plane][u].x; r[4 * u + 1] = qv[j][plane][u].y; r[4 * u + 2] = qv[j][plane][u].z; r[4 * u + 3] = qv[j][plane][u].w; }
+            tmem_st16(tb + lane_addr + (plane ? COL_A1_LO : COL_A1_HI) + 32 * j + 16 * hb, r);
           }
-        }
-        tmem_wait_st(); tc_fence_before(); mbar_arrive(&bar_a);
-        // ---- E1: c2 = acc + b2 -> u(.) -> A2
-        mbar_wait(&bar_d, pd); pd ^= 1; tc_fence_after();
+        tmem_wait_st(); tc_fence_before(); mbar_arrive(&bar_a1);
+        DXI_STAMP(1);
+        // ---- E1: c2 = acc + b2 -> u(.) -> A2 (this thread: channels 32hb .. 32hb+31)
+        mbar_wait(&bar_d1, ph); tc_fence_after();
+        DXI_STAMP(2);
         {
-          float a[32], c[32];
-          tmem_ld32(t_acc, a); tmem_ld32(t_acc + 32, c); tmem_wait_ld();
-          relu_ln64(a, c, sBias);
-          uint32_t hi[32], lo[32];
+          float a[32];
+          tmem_ld32(t_acc + 32 * hb, a); tmem_wait_ld();
+          relu_ln_half(a, sBias + 32 * hb, red[0], row, hb);
+          uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            split_h2(a[2 * j], a[2 * j + 1], hi[j], lo[j]);
-            split_h2(c[2 * j], c[2 * j + 1], hi[16 + j], lo[16 + j]);
-          }
-          tmem_st32(tb + lane_addr + COL_A2_HI, hi);
-          if (SPLIT) tmem_st32(tb + lane_addr + COL_A2_LO, lo);
+          for (int j = 0; j < 16; ++j) split_h2(a[2 * j], a[2 * j + 1], hi[j], lo[j]);
+          tmem_st16(tb + lane_addr + COL_A2_HI + 16 * hb, hi);
+          if (SPLIT) tmem_st16(tb + lane_addr + COL_A2_LO + 16 * hb, lo);
         }
-        tmem_wait_st(); tc_fence_before(); mbar_arrive(&bar_a);
-        mbar_wait(&bar_d, pd); pd ^= 1; tc_fence_after();
+        tmem_wait_st(); tc_fence_before(); mbar_arrive(&bar_a2);
+        DXI_STAMP(3);
       }
-      // ---- E2: h_new = h + acc + b3 (fp32, back to HBM and kept in TMEM); statistics of ReLU(h_new)
+      // ---- E2: h_new = h + acc + b3 (fp32: back to HBM and kept in TMEM); this thread owns the 32-column
+      //      chunks cc = 2 i + hb.  Statistics of ReLU(h_new) as shifted sums.
       float s1 = 0.0f, s2 = 0.0f, kshift = 0.0f;
-#pragma unroll 1
-      for (int cc = 0; cc < 8; ++cc) {
-        float v[32];
-        float4 hv[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) hv[q] = *reinterpret_cast<const float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4));
+      for (int i = 0; i < 4; ++i) {
+        const int cc = 2 * i + hb;
+        float4 hn[8];
+        if (i < 3) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) hn[q] = *reinterpret_cast<const float4*>(hrow + (size_t)((cc + 2) * 8 + q) * (TILE * 4));
+        }
+        float v[32];
         if (p.has_back) {
+          mbar_wait(&bar_d2[cc >> 1], ph); tc_fence_after();
+          if (i == 0) DXI_STAMP(4);
           tmem_ld32(t_acc + 32 * cc, v); tmem_wait_ld();
+          const float* bb = sBias + 64 + 32 * cc;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            v[4 * q] += hv[q].x + sBias[64 + 32 * cc + 4 * q];
-            v[4 * q + 1] += hv[q].y + sBias[64 + 32 * cc + 4 * q + 1];
-            v[4 * q + 2] += hv[q].z + sBias[64 + 32 * cc + 4 * q + 2];
-            v[4 * q + 3] += hv[q].w + sBias[64 + 32 * cc + 4 * q + 3];
+            v[4 * q] += hv[q].x + bb[4 * q];
+            v[4 * q + 1] += hv[q].y + bb[4 * q + 1];
+            v[4 * q + 2] += hv[q].z + bb[4 * q + 2];
+            v[4 * q + 3] += hv[q].w + bb[4 * q + 3];
           }
         } else {
 #pragma unroll
@@ -208,22 +305,29 @@ __global__ void __launch_bounds__(160, 1) tcn_stage_kernel(const StageArgs p) {
             *reinterpret_cast<float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
         if (p.has_front) {
-          if (cc == 0) kshift = relu(v[0]);
+          if (i == 0) kshift = relu(v[0]);
 #pragma unroll
           for (int j = 0; j < 32; ++j) { const float r = relu(v[j]) - kshift; s1 += r; s2 = fmaf(r, r, s2); }
           tmem_st32(t_acc + 32 * cc, reinterpret_cast<const uint32_t(&)[32]>(v));
         }
+        if (i < 3) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) hv[q] = hn[q];
+        }
       }
+      DXI_STAMP(5);
       if (p.has_front) {
         tmem_wait_st();
-        // mean / variance of ReLU(h_new) from shifted sums: var = E[(r-k)^2] - (E[r-k])^2
-        const float m1 = s1 * (1.0f / 256.0f);
-        const float var = fmaxf(s2 * (1.0f / 256.0f) - m1 * m1, 0.0f);
-        const float inv = rsqrtf(var + 1e-6f);
-        const float off = -(m1 + kshift) * inv;
-        // ---- A3 = u(h_new) as fp16 hi | lo
-#pragma unroll 1
-        for (int cc = 0; cc < 8; ++cc) {
+        float inv, off;
+        {
+          const float m1 = s1 * (1.0f / 128.0f);
+          ln_merge(red[1], row, hb, 128.0f, kshift + m1, fmaxf(s2 - s1 * m1, 0.0f), inv, off);
+        }
+        DXI_STAMP(6);
+        // ---- A3 = u(h_new) as fp16 hi | lo, chunk by chunk (the MMA warp starts on a chunk as soon as it lands)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int cc = 2 * i + hb;
           float v[32];
           tmem_ld32(t_acc + 32 * cc, v); tmem_wait_ld();
           uint32_t hi[16], lo[16];
@@ -232,34 +336,35 @@ __global__ void __launch_bounds__(160, 1) tcn_stage_kernel(const StageArgs p) {
             split_h2(fmaf(relu(v[2 * j]), inv, off), fmaf(relu(v[2 * j + 1]), inv, off), hi[j], lo[j]);
           tmem_st16(tb + lane_addr + COL_A3_HI + 16 * cc, hi);
           if (SPLIT) tmem_st16(tb + lane_addr + COL_A3_LO + 16 * cc, lo);
+          tmem_wait_st(); tc_fence_before(); mbar_arrive(&bar_a3[cc]);
         }
-        tmem_wait_st(); tc_fence_before(); mbar_arrive(&bar_a);
         // ---- E3: c1' = u(acc + b1') -> fp16 hi | lo planes in HBM (zeros for frames beyond T)
-        mbar_wait(&bar_d, pd); pd ^= 1; tc_fence_after();
-        float a[32], c[32];
-        tmem_ld32(t_acc, a); tmem_ld32(t_acc + 32, c); tmem_wait_ld();
-        relu_ln64(a, c, sBias + 320);
+        DXI_STAMP(7);
+        mbar_wait(&bar_d3, ph); tc_fence_after();
+        DXI_STAMP(8);
+        float a[32];
+        tmem_ld32(t_acc + 32 * hb, a); tmem_wait_ld();
+        relu_ln_half(a, sBias + 320 + 32 * hb, red[2], row, hb);
         __half* ob = p.c1_out + (size_t)b * 2 * 8 * p.Ts * 8;
-        const size_t row = (size_t)(t + C1_PAD);
+        const size_t r_out = (size_t)(t + C1_PAD);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 4; ++u) {
           uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int e = 8 * u + 2 * j;      // channels e, e+1
-            const float x0 = e < 32 ? a[e] : c[e - 32], x1 = e < 32 ? a[e + 1] : c[e - 31];
-            split_h2(valid ? x0 : 0.0f, valid ? x1 : 0.0f, hi[j], lo[j]);
-          }
-          *reinterpret_cast<uint4*>(ob + ((size_t)u * p.Ts + row) * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (SPLIT) *reinterpret_cast<uint4*>(ob + ((size_t)(8 + u) * p.Ts + row) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          for (int j = 0; j < 4; ++j) split_h2(valid ? a[8 * u + 2 * j] : 0.0f, valid ? a[8 * u + 2 * j + 1] : 0.0f, hi[j], lo[j]);
+          *reinterpret_cast<uint4*>(ob + ((size_t)(4 * hb + u) * p.Ts + r_out) * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (SPLIT) *reinterpret_cast<uint4*>(ob + ((size_t)(8 + 4 * hb + u) * p.Ts + r_out) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
         tc_fence_before();
       }
+      DXI_STAMP(9);
+      ph ^= 1;
     }
+#undef DXI_STAMP
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tb, 512);
+  if (warp == EPI_WARPS) tmem_dealloc(tb, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -434,6 +539,9 @@ int resnet_umma_prepare(dxi_net& net, cudaStream_t st) {
   return DXI_OK;
 }
 
+static thread_local long long* g_dbg_clocks = nullptr;
+static thread_local int g_dbg_stage = -1;
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 int64_t resnet_umma_workspace_bytes(const dxi_net& net, int B, int T) {
@@ -490,11 +598,12 @@ int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, floa
     a.c1_out = c1[s & 1];
     a.T = T; a.tiles_per_utt = tiles; a.n_tiles = n_tiles; a.Ts = Ts;
     a.has_back = s >= 1; a.has_front = s < c.n_blocks;
+    a.dbg = (s == g_dbg_stage) ? g_dbg_clocks : nullptr;
     const int d = s >= 1 ? 1 << ((s - 1) % nd) : 1;
     if (c.padding == DXI_PAD_CAUSAL) { a.shift0 = 2 * d; a.shift1 = d; a.shift2 = 0; }       // tap j reads t-(2-j)d
     else                             { a.shift0 = d;     a.shift1 = 0; a.shift2 = -d; }      // tap j reads t+(j-1)d
-    if (split) tcn_stage_kernel<true><<<grid, 160, smem, st>>>(a);
-    else       tcn_stage_kernel<false><<<grid, 160, smem, st>>>(a);
+    if (split) tcn_stage_kernel<true><<<grid, STAGE_THREADS, smem, st>>>(a);
+    else       tcn_stage_kernel<false><<<grid, STAGE_THREADS, smem, st>>>(a);
     DXI_LAUNCHED("tcn_stage_kernel");
   }
   }
@@ -514,3 +623,10 @@ int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, floa
 }
 
 }  // namespace dxi
+
+// Debug aid: the epilogue of stage `stage` of the following forward calls (this thread) writes 16 clock64
+// stamps per tile into dev_buf[n_tiles * 16]; pass nullptr to switch it off.
+extern "C" DXI_API void dxi_debug_tcn_clocks(long long* dev_buf, int stage) {
+  dxi::g_dbg_clocks = dev_buf;
+  dxi::g_dbg_stage = dev_buf ? stage : -1;
+}

@@ -175,6 +175,10 @@ DXI_API void dxi_launch_count_reset(void);
 DXI_API void dxi_profile_enable(int on);
 DXI_API int dxi_profile_read(const char* key, double* total_ms, int64_t* launches);
 
+/* Debug aid for kernel tuning: the epilogue of stage `stage` of subsequent dxi_net_forward calls from this
+ * thread writes 16 clock64 stamps per tile into dev_buf (int64 [n_tiles * 16]); NULL switches it off. */
+DXI_API void dxi_debug_tcn_clocks(long long* dev_buf, int stage);
+
 /* Self test of the tcgen05 / TMEM building blocks: D[128,N] = A[128,K] * B[K,N] with fp16 operands
  * (A from tensor memory, B from shared memory) written to `d_out` (float32 [128,N]).
  * a_host_layout / b: device fp16 row-major [128,K] and [N,K].  variant selects descriptor encodings
