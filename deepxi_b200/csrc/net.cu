@@ -91,6 +91,25 @@ extern "C" DXI_API int dxi_net_finalize(dxi_net_t* h, void* stream) {
   for (auto& kv : exp)
     if (!h->host.count(kv.first)) { set_error("dxi_net_finalize: tensor '%s' was not loaded", kv.first.c_str()); return DXI_E_STATE; }
   cudaStream_t st = as_stream(stream);
+  if (h->kind == DXI_NET_MHANETV3) {
+    // fused [d_model][3*d_model] projection per block: column = which*d_model + head*d_k + o
+    // (query/key/value_kernel are [heads][d_model][d_k], the tfa einsum "...NI,HIO->...NHO")
+    const int d = h->cfg.d_model, H = h->cfg.n_heads, dk = d / H;
+    for (int blk = 0; blk < h->cfg.n_blocks; ++blk) {
+      const int li = 3 + 5 * blk;
+      char nm[64];
+      snprintf(nm, sizeof(nm), "packed-%d/qkv", li);
+      std::vector<float> packed((size_t)d * 3 * d);
+      const char* names[3] = {"query_kernel", "key_kernel", "value_kernel"};
+      for (int w = 0; w < 3; ++w) {
+        const std::vector<float>& src = *h->host_tensor(li, names[w]);
+        for (int hh = 0; hh < H; ++hh)
+          for (int i = 0; i < d; ++i)
+            for (int o = 0; o < dk; ++o) packed[(size_t)i * 3 * d + w * d + hh * dk + o] = src[((size_t)hh * d + i) * dk + o];
+      }
+      h->host[nm] = std::move(packed);
+    }
+  }
   // fp32 arena (every tensor 256-byte aligned)
   size_t total = 0;
   h->d_offset.clear();

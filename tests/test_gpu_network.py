@@ -145,3 +145,37 @@ def test_full_size_properties(xi_stats):
     assert torch.equal(full[:4], full[60:64])                     # same utterance anywhere in the batch: same bits
     cut = net(inp[:3, :300].contiguous())
     assert torch.equal(cut, full[:3, :300])                       # causal: a prefix is unaffected by what follows
+
+
+MHA_KW = dict(d_model=256, n_blocks=5, n_heads=8, warmup_steps=40000, max_len=2048, causal=1, outp_act='Sigmoid')
+
+
+@pytest.mark.parametrize('mask_mode', ['none', 'causal+pad'])
+def test_mhanetv3_forward_vs_oracle(xi_stats, mask_mode):
+    from oracle import attention as oatt
+    mu, sg = xi_stats['mhanet-1.1c/mu'], xi_stats['mhanet-1.1c/sigma']
+    w = weights.synthetic_mhanetv3(0)
+    lens = [30000, 17000, 500]
+    x = synth.noisy_speech(3, 30000, seed=61)
+    inp, _, nfr = osig.observation_batch(x, lens)                  # zero-padded frames are all-zero rows
+    ref = oatt.mhanetv3_forward(inp, w, mask_mode=mask_mode, dtype=torch.float64)
+    net = network_selector('MHANetV3', None, 257, mask_mode=mask_mode, precision='f32', **MHA_KW).load_weights(w)
+    xbar = net(inp)
+    assert xbar.shape == ref.shape == (3, 118, 257)
+    for i, n in enumerate(nfr):
+        rows = slice(0, n) if mask_mode == 'causal+pad' else slice(0, 118)     # padded query rows: don't-care when masked
+        err = _db_err(xbar[i, rows], ref[i, rows], mu, sg)
+        assert err.max() < 5e-3, (mask_mode, i, err.max())
+
+
+def test_mhanetv3_infer_and_limits(xi_stats):
+    w = weights.synthetic_mhanetv3(1)
+    dx = DeepXi(512, 256, 512, 16000, 'MagXi', 'MHANetV3', ver='mhanet-1.1c', map_type='DBNormalCDF', map_params=None,
+                **MHA_KW)
+    dx.set_weights(w)
+    x = synth.noisy_speech(2, 20000, seed=62)
+    y, nfr = dx.infer_batch(x, [20000, 11111], 'y', 'mmse-lsa')
+    assert y.shape == (2, (79 + 1) * 256) and torch.isfinite(y).all()
+    too_long = torch.zeros((1, 2049, 257), device='cuda')
+    with pytest.raises(_lib.DxiError):                 # more frames than positional-embedding rows (attention.py:432)
+        dx.network(too_long)
