@@ -140,13 +140,18 @@ __global__ void __launch_bounds__(256) stft_kernel(const void* __restrict__ wav_
     }
     __syncthreads();
     // ---- split step, magnitude and phase; flat coalesced stores over (frame, bin)
-    for (int i = tid; i < nf * NBINS; i += 256) {
-      const int fi = i / NBINS, k = i - fi * NBINS;
-      const float2* z = sm.buf + fi * FFT_FRAME_SLOTS;
-      float2 X = rfft_split(z[k & 255], z[(256 - k) & 255], sm.tw512[k]);
-      if (k == 0 || k == 256) X.y = 0.0f;
-      __stcs(mag + out0 + i, sqrtf(fmaf(X.x, X.x, X.y * X.y)));
-      __stcs(phase + out0 + i, atan2_poly(X.y, X.x));
+    {
+      int fi = 0, k = tid;                       // flat index i = fi * 257 + k, advanced by 256 per iteration
+      for (int i = tid; i < nf * NBINS; i += 256) {
+        const float2* z = sm.buf + fi * FFT_FRAME_SLOTS;
+        float2 X = rfft_split(z[k & 255], z[(256 - k) & 255], sm.tw512[k]);
+        if (k == 0 || k == 256) X.y = 0.0f;
+        const float p2 = fmaf(X.x, X.x, X.y * X.y);
+        __stcs(mag + out0 + i, p2 > 0.0f ? p2 * rsqrtf(p2) : 0.0f);       // |X|, 2 ulp
+        __stcs(phase + out0 + i, atan2_poly(X.y, X.x));
+        k += 256;
+        if (k >= NBINS) { k -= NBINS; ++fi; }
+      }
     }
     __syncthreads();
   }
@@ -196,8 +201,9 @@ __global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ ma
     for (int f0 = hs - 1; f0 < he; f0 += FR) {
       const int nf = min(FR, he - f0);
       // ---- spectrum of every frame: Y = (|X| G) e^{j phase}
-      for (int i = tid; i < nf * NBINS; i += 256) {
-        const int fi = i / NBINS, k = i - fi * NBINS;
+      int fi = 0, k = tid;
+      for (int i = tid; i < nf * NBINS; i += 256, k += 256) {
+        if (k >= NBINS) { k -= NBINS; ++fi; }
         const int t = f0 + fi;
         float2 Y = make_float2(0.0f, 0.0f);
         if (t >= 0 && t < T) {
@@ -211,7 +217,7 @@ __global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ ma
             m = __fmul_rn(m, gfunc_eval(gtype, xi, __fadd_rn(xi, 1.0f)));
           }
           float sn, cs;
-          sincosf(p, &sn, &cs);
+          __sincosf(p, &sn, &cs);                                        // |p| <= pi: abs error < 5e-7
           Y = make_float2(m * cs, (k == 0 || k == 256) ? 0.0f : m * sn);   // c2r ignores Im of DC / Nyquist
         }
         sm.buf[fi * FFT_FRAME_SLOTS + k] = Y;

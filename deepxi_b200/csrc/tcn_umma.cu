@@ -14,12 +14,21 @@
 //
 // Per CTA (persistent over tiles): the packed fp16 weights of the stage (176 KB hi+lo) stay in shared
 // memory as tcgen05 B operands (128-byte swizzle); every A operand is produced by the epilogue threads
-// straight into tensor memory (thread r owns frame r: TMEM lane r), so LayerNorm is a purely
-// thread-local reduction over the accumulator row and nothing is staged through shared memory.
-// TMEM columns: [0,256) accumulators / fp32 residual row, [256,512) A operands (hi | lo).
-// Warps 0-7: epilogue (two threads per frame, half the columns each; TMEM lane quarter = warp & 3);
-// warp 8: weight load (bulk async copy), L2 prefetch of the next tile, MMA issue.  GEMM2 is committed in four
-// column groups and GEMM3 is issued in eight K-chunks so that tensor-core time hides behind the epilogue.
+// straight into tensor memory (TMEM lane r = frame r), so nothing is staged through shared memory.
+//
+// Deferred normalisation.  u(x) = (r - mu) * inv with r = ReLU(x), so  W^T u = inv * (W^T r) - inv * mu * colsum(W).
+// The MMAs therefore consume the UN-normalised ReLU output (written to TMEM the moment it exists) and the
+// row statistics are applied to the small GEMM outputs afterwards; no second pass over the 256-wide row, and the
+// statistics merge runs while the tensor core is already busy.  colsum(W3), colsum(W1') ride in the weight image
+// (summed over the effective fp16 hi[+lo] weights so the mean component cancels to rounding).
+//
+// TMEM columns: [0,256) GEMM2 accumulators, overwritten IN PLACE by the A operand of GEMM3 (32 fp32 columns
+// -> 16 hi + 16 lo); [256,320) A operand of GEMM2, later GEMM3 accumulators; [320,512) the three c1 taps of
+// the NEXT tile (loaded while this tile's GEMM3 drains); GEMM1 accumulators reuse [0,64).
+// Warps 0-15: epilogue, four threads per frame (a quarter of the columns each; TMEM lane quarter = warp & 3;
+// LayerNorm statistics merged with Chan's formula through shared memory).  Warp 16: weight load (bulk async
+// copy), L2 prefetch of the next tile, warp-convergent MMA issue.  GEMM2 is committed in four column groups and
+// GEMM3 is issued in eight K-chunks as the epilogue produces them.
 #include <vector>
 #include "net.cuh"
 #include "umma.cuh"
@@ -33,14 +42,16 @@ constexpr int IMG_W2 = 0;                 // [192 -> 64] : 3 K-chunks x [64 rows
 constexpr int IMG_W3 = 24576;             // [ 64 -> 256]: 1 K-chunk  x [256 rows x 128 B]
 constexpr int IMG_W1 = 57344;             // [256 -> 64] : 4 K-chunks x [64 rows x 128 B]
 constexpr int IMG_PART = 90112;           // bytes of one precision part (hi, then lo)
-constexpr int IMG_BIAS = 2 * IMG_PART;    // b2[64], b3[256], b1[64] fp32
-constexpr int IMG_BYTES = IMG_BIAS + 384 * 4;
+constexpr int IMG_BIAS = 2 * IMG_PART;    // fp32: b2[64], b3[256], b1'[64], colsum(W3)[256], colsum(W1')[64]
+constexpr int OFF_B2 = 0, OFF_B3 = 64, OFF_B1 = 320, OFF_CS3 = 384, OFF_CS1 = 640, N_AUX = 704;
+constexpr int IMG_BYTES = IMG_BIAS + N_AUX * 4;
 
 // TMEM column map
-constexpr uint32_t COL_ACC = 0;
-constexpr uint32_t COL_A1_HI = 256, COL_A1_LO = 352;     // 3 taps x 32 columns each
-constexpr uint32_t COL_A2_HI = 448, COL_A2_LO = 480;     // 32 columns each
-constexpr uint32_t COL_A3_HI = 256, COL_A3_LO = 384;     // 128 columns each
+constexpr uint32_t COL_D2 = 0;                            // 256 fp32; chunk cc becomes A3: hi at 32cc, lo at 32cc+16
+constexpr uint32_t COL_D1 = 0;                            // 64 fp32 (dead before GEMM2 writes)
+constexpr uint32_t COL_A2_HI = 256, COL_A2_LO = 288;      // 32 columns each
+constexpr uint32_t COL_D3 = 256;                          // 64 fp32 (A2 is dead by then)
+constexpr uint32_t COL_A1_HI = 320, COL_A1_LO = 416;      // 3 taps x 32 columns each
 
 struct StageArgs {
   const unsigned char* img;      // packed weights of this stage
@@ -55,7 +66,8 @@ struct StageArgs {
 
 __device__ __forceinline__ float relu(float x) { return fmaxf(x, 0.0f); }
 
-constexpr int EPI_WARPS = 8;                      // 2 warps per TMEM lane quarter: each owns half the columns of a row
+constexpr int NSPLIT = 4;                         // threads per frame
+constexpr int EPI_WARPS = 4 * NSPLIT;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int STAGE_THREADS = EPI_THREADS + 32;   // + 1 warp: weight load, L2 prefetch, MMA issue
 
@@ -64,32 +76,24 @@ __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-// LayerNorm statistics of one row that is split between two threads (n values each): every thread
-// contributes (mean, M2 = sum of squared deviations from its own mean); Chan's formula merges them.
-__device__ __forceinline__ void ln_merge(float2* red, int row, int hb, float n, float mean_h, float m2_h, float& inv, float& off) {
-  red[hb * TILE + row] = make_float2(mean_h, m2_h);
+// LayerNorm statistics of one row split between NSPLIT threads (n values each): every thread contributes
+// (mean_i, M2_i = sum of squared deviations from mean_i); Chan's formula merges them.  Returns mean and
+// 1/sqrt(biased variance + 1e-6) of the whole row.
+__device__ __forceinline__ void ln_merge(float2* red, int row, int qd, float n, float mean_i, float m2_i, float& mean, float& inv) {
+  red[qd * TILE + row] = make_float2(mean_i, m2_i);
   epi_barrier();
-  const float2 o = red[(hb ^ 1) * TILE + row];
-  const float mean = 0.5f * (mean_h + o.x);
-  const float dm = mean_h - o.x;
-  const float var = (m2_h + o.y + dm * dm * (0.5f * n)) / (2.0f * n);    // biased variance over 2n values
-  inv = rsqrtf(var + 1e-6f);
-  off = -mean * inv;
-}
-
-// u(x) = ReLU -> LayerNorm over a 64-wide row of which this thread holds 32 values (two-pass locally)
-__device__ __forceinline__ void relu_ln_half(float (&a)[32], const float* bias, float2* red, int row, int hb) {
-  float s = 0.0f;
+  float2 pt[NSPLIT];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) { a[j] = relu(a[j] + bias[j]); s += a[j]; }
-  const float mean_h = s * (1.0f / 32.0f);
-  float q = 0.0f;
+  for (int i = 0; i < NSPLIT; ++i) pt[i] = red[i * TILE + row];
+  float m = 0.0f;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) { const float d = a[j] - mean_h; q = fmaf(d, d, q); }
-  float inv, off;
-  ln_merge(red, row, hb, 32.0f, mean_h, q, inv, off);
+  for (int i = 0; i < NSPLIT; ++i) m += pt[i].x;
+  m *= (1.0f / NSPLIT);
+  float m2 = 0.0f;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) a[j] = fmaf(a[j], inv, off);
+  for (int i = 0; i < NSPLIT; ++i) { const float d = pt[i].x - m; m2 += pt[i].y + n * d * d; }
+  mean = m;
+  inv = rsqrtf(m2 / (n * NSPLIT) + 1e-6f);
 }
 
 template <bool SPLIT>
@@ -97,9 +101,9 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_w, bar_a1, bar_a2, bar_a3[8], bar_d1, bar_d2[4], bar_d3;
   __shared__ uint32_t tmem_slot;
-  __shared__ float2 red[3][2 * TILE];
+  __shared__ float2 red[3][NSPLIT * TILE];
   unsigned char* sW = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const float* sBias = reinterpret_cast<const float*>(sW + IMG_BIAS);
+  const float* sAux = reinterpret_cast<const float*>(sW + IMG_BIAS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == EPI_WARPS) tmem_alloc(&tmem_slot, 512);
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
     mbar_init(&bar_w, 1);
     mbar_init(&bar_a1, EPI_THREADS);
     mbar_init(&bar_a2, EPI_THREADS);
-    for (int i = 0; i < 8; ++i) mbar_init(&bar_a3[i], EPI_THREADS / 2);
+    for (int i = 0; i < 8; ++i) mbar_init(&bar_a3[i], TILE);
     mbar_init(&bar_d1, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&bar_d2[i], 1);
     mbar_init(&bar_d3, 1);
@@ -119,7 +123,6 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
   // The CTA owns the SM's whole tensor memory (512 columns, one CTA per SM), so the allocation starts at
   // lane 0 / column 0: TMEM addresses below are compile-time constants.
   if (tmem_slot != 0) __trap();
-  constexpr uint32_t tb = 0;
 
   if (warp == EPI_WARPS) {
     // ================= weight load, L2 prefetch of the next tile, MMA issue =================
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
     constexpr int NPART = SPLIT ? 3 : 1;          // (a_hi, w_hi) [+ (a_lo, w_hi) + (a_hi, w_lo)]
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      {   // pull the next tile's residual rows and c1 rows into L2 while this tile is being computed
+      {   // pull the tile after next's residual rows / next tile's rows into L2 ahead of their use
         const int nt = tile + gridDim.x;
         if (nt < p.n_tiles) {
           const char* hn = reinterpret_cast<const char*>(p.h + (size_t)nt * (TILE * 256));
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
             const uint32_t a0 = part == 1 ? COL_A1_LO : COL_A1_HI, w0 = (part == 2 ? w_lo : w_hi) + IMG_W2;
 #pragma unroll
             for (int ks = 0; ks < 12; ++ks) {
-              mma_ts_elect(COL_ACC, a0 + 8 * ks, make_smem_desc_sw128(w0 + (ks >> 2) * 64 * 128 + (ks & 3) * 32), id64, acc);
+              mma_ts_elect(COL_D1, a0 + 8 * ks, make_smem_desc_sw128(w0 + (ks >> 2) * 64 * 128 + (ks & 3) * 32), id64, acc);
               acc = 1;
             }
           }
@@ -170,14 +173,14 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
         mma_commit_elect(&bar_d1);
         mbar_wait(&bar_a2, ph); tc_fence_after();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {   // W3 u(c2): K = 64, N = 256 in four column groups, each committed on its own
+        for (int g = 0; g < 4; ++g) {   // W3 ReLU(c2): K = 64, N = 256 in four column groups, each committed on its own
           uint32_t acc = 0;
 #pragma unroll
           for (int part = 0; part < NPART; ++part) {
             const uint32_t a0 = part == 1 ? COL_A2_LO : COL_A2_HI, w0 = (part == 2 ? w_lo : w_hi) + IMG_W3 + g * 64 * 128;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              mma_ts_elect(COL_ACC + 64 * g, a0 + 8 * ks, make_smem_desc_sw128(w0 + ks * 32), id64, acc);
+              mma_ts_elect(COL_D2 + 64 * g, a0 + 8 * ks, make_smem_desc_sw128(w0 + ks * 32), id64, acc);
               acc = 1;
             }
           }
@@ -187,109 +190,113 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
       if (p.has_front) {
         uint32_t acc = 0;
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {   // W1' u(h): K = 256 in eight 32-channel chunks, issued as the epilogue produces them
-          mbar_wait(&bar_a3[cc], ph);
-          if (cc == 0) continue;           // D overwrites residual columns [0,64): wait until chunks 0 AND 1 are consumed
-          tc_fence_after();
+        for (int cc = 0; cc < 8; ++cc) {   // W1' ReLU(h): K = 256 in eight 32-channel chunks, issued as the epilogue produces them
+          mbar_wait(&bar_a3[cc], ph); tc_fence_after();
 #pragma unroll
-          for (int c2 = (cc == 1 ? 0 : cc); c2 <= cc; ++c2)
+          for (int part = 0; part < NPART; ++part) {
+            const uint32_t a0 = COL_D2 + 32 * cc + (part == 1 ? 16 : 0), w0 = (part == 2 ? w_lo : w_hi) + IMG_W1;
 #pragma unroll
-            for (int part = 0; part < NPART; ++part) {
-              const uint32_t a0 = part == 1 ? COL_A3_LO : COL_A3_HI, w0 = (part == 2 ? w_lo : w_hi) + IMG_W1;
-#pragma unroll
-              for (int ks = 2 * c2; ks < 2 * c2 + 2; ++ks) {
-                mma_ts_elect(COL_ACC, a0 + 8 * ks, make_smem_desc_sw128(w0 + (ks >> 2) * 64 * 128 + (ks & 3) * 32), id64, acc);
-                acc = 1;
-              }
+            for (int k2 = 0; k2 < 2; ++k2) {
+              const int ks = 2 * cc + k2;
+              mma_ts_elect(COL_D3, a0 + 8 * k2, make_smem_desc_sw128(w0 + (ks >> 2) * 64 * 128 + (ks & 3) * 32), id64, acc);
+              acc = 1;
             }
+          }
         }
         mma_commit_elect(&bar_d3);
       }
       ph ^= 1;
     }
   } else {
-    // ================= epilogue: threads (q, lane) and (q+4, lane) share frame r = 32 q + lane =================
-    mbar_wait(&bar_w, 0);        // biases live in the weight image
-    const int hb = warp >> 2, row = (warp & 3) * 32 + lane;
+    // ================= epilogue: warps (q, qd): TMEM lane quarter q = warp & 3, column quarter qd = warp >> 2 =================
+    mbar_wait(&bar_w, 0);        // biases / column sums live in the weight image
+    const int qd = warp >> 2, row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t t_acc = tb + lane_addr + COL_ACC;
     uint32_t ph = 0;
     const bool stamp = p.dbg != nullptr && tid == 0;
 #define DXI_STAMP(k) do { if (stamp) p.dbg[(size_t)tile * 16 + (k)] = clock64(); } while (0)
+
+    // c1 taps of a tile -> TMEM [320,512): this thread moves units 2qd, 2qd+1 of every (tap, plane)
+    auto load_a1 = [&](int tile_) {
+      const int b = tile_ / p.tiles_per_utt, t = (tile_ - b * p.tiles_per_utt) * TILE + row;
+      const __half* cb = p.c1_in + (size_t)b * 2 * 8 * p.Ts * 8;
+      uint4 qv[3][SPLIT ? 2 : 1][2];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int shift = j == 0 ? p.shift0 : (j == 1 ? p.shift1 : p.shift2);
+        const size_t r_in = (size_t)(t - shift + C1_PAD);
+#pragma unroll
+        for (int plane = 0; plane < (SPLIT ? 2 : 1); ++plane)
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            qv[j][plane][u] = __ldg(reinterpret_cast<const uint4*>(cb + ((size_t)(plane * 8 + 2 * qd + u) * p.Ts + r_in) * 8));
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int plane = 0; plane < (SPLIT ? 2 : 1); ++plane) {
+          const uint32_t r[8] = {qv[j][plane][0].x, qv[j][plane][0].y, qv[j][plane][0].z, qv[j][plane][0].w,
+                                 qv[j][plane][1].x, qv[j][plane][1].y, qv[j][plane][1].z, qv[j][plane][1].w};
+          tmem_st8(lane_addr + (plane ? COL_A1_LO : COL_A1_HI) + 32 * j + 8 * qd, r);
+        }
+      tmem_wait_st(); tc_fence_before();
+    };
+
+    if (p.has_back && (int)blockIdx.x < p.n_tiles) { load_a1(blockIdx.x); mbar_arrive(&bar_a1); }
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TILE;
       const int t = t0 + row;
-      DXI_STAMP(0);
       const bool valid = t < p.T;
       float* hrow = p.h + (size_t)tile * (TILE * 256) + row * 4;          // + c4 * 512
-      // residual values of the first chunk this thread owns: issue the loads before anything else
-      float4 hv[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) hv[q] = *reinterpret_cast<const float4*>(hrow + (size_t)(hb * 8 + q) * (TILE * 4));
+      DXI_STAMP(0);
+      float mu2 = 0.0f, inv2 = 0.0f;
       if (p.has_back) {
-        // ---- A1: three shifted copies of c1 (hi | lo planes) -> TMEM; this thread moves units 4hb..4hb+3
-        const __half* cb = p.c1_in + (size_t)b * 2 * 8 * p.Ts * 8;
-        uint4 qv[3][SPLIT ? 2 : 1][4];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const int shift = j == 0 ? p.shift0 : (j == 1 ? p.shift1 : p.shift2);
-          const size_t r_in = (size_t)(t - shift + C1_PAD);
-#pragma unroll
-          for (int plane = 0; plane < (SPLIT ? 2 : 1); ++plane)
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              qv[j][plane][u] = __ldg(reinterpret_cast<const uint4*>(cb + ((size_t)(plane * 8 + 4 * hb + u) * p.Ts + r_in) * 8));
-        }
-#pragma unroll
-        for (int j = 0; j < 3; ++j)
-#pragma unroll
-          for (int plane = 0; plane < (SPLIT ? 2 : 1); ++plane) {
-            uint32_t r[16];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) { r[4 * u] = qv[j][plane][u].x; r[4 * u + 1] = qv[j][plane][u].y; r[4 * u + 2] = qv[j][plane][u].z; r[4 * u + 3] = qv[j][plane][u].w; }
-            tmem_st16(tb + lane_addr + (plane ? COL_A1_LO : COL_A1_HI) + 32 * j + 16 * hb, r);
-          }
-        tmem_wait_st(); tc_fence_before(); mbar_arrive(&bar_a1);
-        DXI_STAMP(1);
-        // ---- E1: c2 = acc + b2 -> u(.) -> A2 (this thread: channels 32hb .. 32hb+31)
+        // ---- P1: r2 = ReLU(acc1 + b2) -> A2 at once (un-normalised); statistics merged while GEMM2 runs
         mbar_wait(&bar_d1, ph); tc_fence_after();
-        DXI_STAMP(2);
-        {
-          float a[32];
-          tmem_ld32(t_acc + 32 * hb, a); tmem_wait_ld();
-          relu_ln_half(a, sBias + 32 * hb, red[0], row, hb);
-          uint32_t hi[16], lo[16];
+        DXI_STAMP(1);
+        float a[16];
+        tmem_ld16(lane_addr + COL_D1 + 16 * qd, a); tmem_wait_ld();
+        float s = 0.0f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) split_h2(a[2 * j], a[2 * j + 1], hi[j], lo[j]);
-          tmem_st16(tb + lane_addr + COL_A2_HI + 16 * hb, hi);
-          if (SPLIT) tmem_st16(tb + lane_addr + COL_A2_LO + 16 * hb, lo);
+        for (int j = 0; j < 16; ++j) { a[j] = relu(a[j] + sAux[OFF_B2 + 16 * qd + j]); s += a[j]; }
+        {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) split_h2(a[2 * j], a[2 * j + 1], hi[j], lo[j]);
+          tmem_st8(lane_addr + COL_A2_HI + 8 * qd, hi);
+          if (SPLIT) tmem_st8(lane_addr + COL_A2_LO + 8 * qd, lo);
         }
         tmem_wait_st(); tc_fence_before(); mbar_arrive(&bar_a2);
-        DXI_STAMP(3);
+        DXI_STAMP(2);
+        const float mean_i = s * (1.0f / 16.0f);
+        float q2 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const float d = a[j] - mean_i; q2 = fmaf(d, d, q2); }
+        ln_merge(red[0], row, qd, 16.0f, mean_i, q2, mu2, inv2);
       }
-      // ---- E2: h_new = h + acc + b3 (fp32: back to HBM and kept in TMEM); this thread owns the 32-column
-      //      chunks cc = 2 i + hb.  Statistics of ReLU(h_new) as shifted sums.
+      DXI_STAMP(3);
+      // ---- P2: h_new = h + b3 + inv2 (acc2 - mu2 colsum(W3)); r3 = ReLU(h_new) -> A3 in place, chunk by chunk
       float s1 = 0.0f, s2 = 0.0f, kshift = 0.0f;
+      const float nim = -inv2 * mu2;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int cc = 2 * i + hb;
-        float4 hn[8];
-        if (i < 3) {
+      for (int i = 0; i < 2; ++i) {
+        const int cc = qd + 4 * i;
+        float4 hv[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) hn[q] = *reinterpret_cast<const float4*>(hrow + (size_t)((cc + 2) * 8 + q) * (TILE * 4));
-        }
+        for (int q = 0; q < 8; ++q) hv[q] = *reinterpret_cast<const float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4));
         float v[32];
         if (p.has_back) {
           mbar_wait(&bar_d2[cc >> 1], ph); tc_fence_after();
           if (i == 0) DXI_STAMP(4);
-          tmem_ld32(t_acc + 32 * cc, v); tmem_wait_ld();
-          const float* bb = sBias + 64 + 32 * cc;
+          tmem_ld32(lane_addr + COL_D2 + 32 * cc, v); tmem_wait_ld();
+          const float* b3 = sAux + OFF_B3 + 32 * cc;
+          const float* cs = sAux + OFF_CS3 + 32 * cc;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            v[4 * q] += hv[q].x + bb[4 * q];
-            v[4 * q + 1] += hv[q].y + bb[4 * q + 1];
-            v[4 * q + 2] += hv[q].z + bb[4 * q + 2];
-            v[4 * q + 3] += hv[q].w + bb[4 * q + 3];
+            v[4 * q]     = fmaf(inv2, v[4 * q],     fmaf(nim, cs[4 * q],     hv[q].x + b3[4 * q]));
+            v[4 * q + 1] = fmaf(inv2, v[4 * q + 1], fmaf(nim, cs[4 * q + 1], hv[q].y + b3[4 * q + 1]));
+            v[4 * q + 2] = fmaf(inv2, v[4 * q + 2], fmaf(nim, cs[4 * q + 2], hv[q].z + b3[4 * q + 2]));
+            v[4 * q + 3] = fmaf(inv2, v[4 * q + 3], fmaf(nim, cs[4 * q + 3], hv[q].w + b3[4 * q + 3]));
           }
         } else {
 #pragma unroll
@@ -306,56 +313,68 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
         }
         if (p.has_front) {
           if (i == 0) kshift = relu(v[0]);
+          uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { const float r = relu(v[j]) - kshift; s1 += r; s2 = fmaf(r, r, s2); }
-          tmem_st32(t_acc + 32 * cc, reinterpret_cast<const uint32_t(&)[32]>(v));
-        }
-        if (i < 3) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) hv[q] = hn[q];
+          for (int j = 0; j < 16; ++j) {
+            const float r0 = relu(v[2 * j]), r1 = relu(v[2 * j + 1]);
+            const float d0 = r0 - kshift, d1 = r1 - kshift;
+            s1 += d0 + d1; s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2);
+            split_h2(r0, r1, hi[j], lo[j]);
+          }
+          tmem_st16(lane_addr + COL_D2 + 32 * cc, hi);
+          if (SPLIT) tmem_st16(lane_addr + COL_D2 + 32 * cc + 16, lo);
+          tmem_wait_st(); tc_fence_before(); mbar_arrive(&bar_a3[cc]);
         }
       }
       DXI_STAMP(5);
+      float mu3 = 0.0f, inv3 = 0.0f;
       if (p.has_front) {
-        tmem_wait_st();
-        float inv, off;
-        {
-          const float m1 = s1 * (1.0f / 128.0f);
-          ln_merge(red[1], row, hb, 128.0f, kshift + m1, fmaxf(s2 - s1 * m1, 0.0f), inv, off);
-        }
-        DXI_STAMP(6);
-        // ---- A3 = u(h_new) as fp16 hi | lo, chunk by chunk (the MMA warp starts on a chunk as soon as it lands)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int cc = 2 * i + hb;
-          float v[32];
-          tmem_ld32(t_acc + 32 * cc, v); tmem_wait_ld();
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            split_h2(fmaf(relu(v[2 * j]), inv, off), fmaf(relu(v[2 * j + 1]), inv, off), hi[j], lo[j]);
-          tmem_st16(tb + lane_addr + COL_A3_HI + 16 * cc, hi);
-          if (SPLIT) tmem_st16(tb + lane_addr + COL_A3_LO + 16 * cc, lo);
-          tmem_wait_st(); tc_fence_before(); mbar_arrive(&bar_a3[cc]);
-        }
-        // ---- E3: c1' = u(acc + b1') -> fp16 hi | lo planes in HBM (zeros for frames beyond T)
-        DXI_STAMP(7);
+        const float m1 = s1 * (1.0f / 64.0f);
+        ln_merge(red[1], row, qd, 64.0f, kshift + m1, fmaxf(s2 - s1 * m1, 0.0f), mu3, inv3);
+      }
+      DXI_STAMP(6);
+      // ---- the next tile's c1 taps travel to TMEM while this tile's GEMM3 drains
+      const int next = tile + gridDim.x;
+      const bool has_next = p.has_back && next < p.n_tiles;
+      if (has_next) load_a1(next);
+      DXI_STAMP(7);
+      if (p.has_front) {
+        // ---- P3: c1' = LN(ReLU(inv3 (acc3 - mu3 colsum(W1')) + b1')) -> fp16 hi | lo planes in HBM (zeros beyond T)
         mbar_wait(&bar_d3, ph); tc_fence_after();
         DXI_STAMP(8);
-        float a[32];
-        tmem_ld32(t_acc + 32 * hb, a); tmem_wait_ld();
-        relu_ln_half(a, sBias + 320 + 32 * hb, red[2], row, hb);
+        float a[16];
+        tmem_ld16(lane_addr + COL_D3 + 16 * qd, a); tmem_wait_ld();
+        tc_fence_before();
+        if (has_next) mbar_arrive(&bar_a1);      // every D3 read is done: GEMM1 / A2 of the next tile may reuse the columns
+        const float nim3 = -inv3 * mu3;
+        float s = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          a[j] = relu(fmaf(inv3, a[j], fmaf(nim3, sAux[OFF_CS1 + 16 * qd + j], sAux[OFF_B1 + 16 * qd + j])));
+          s += a[j];
+        }
+        const float mean_i = s * (1.0f / 16.0f);
+        float q2 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const float d = a[j] - mean_i; q2 = fmaf(d, d, q2); }
+        float mean, inv;
+        ln_merge(red[2], row, qd, 16.0f, mean_i, q2, mean, inv);
+        const float off = -mean * inv;
         __half* ob = p.c1_out + (size_t)b * 2 * 8 * p.Ts * 8;
         const size_t r_out = (size_t)(t + C1_PAD);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 2; ++u) {
           uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) split_h2(valid ? a[8 * u + 2 * j] : 0.0f, valid ? a[8 * u + 2 * j + 1] : 0.0f, hi[j], lo[j]);
-          *reinterpret_cast<uint4*>(ob + ((size_t)(4 * hb + u) * p.Ts + r_out) * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (SPLIT) *reinterpret_cast<uint4*>(ob + ((size_t)(8 + 4 * hb + u) * p.Ts + r_out) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          for (int j = 0; j < 4; ++j) {
+            const float x0 = valid ? fmaf(a[8 * u + 2 * j], inv, off) : 0.0f, x1 = valid ? fmaf(a[8 * u + 2 * j + 1], inv, off) : 0.0f;
+            split_h2(x0, x1, hi[j], lo[j]);
+          }
+          *reinterpret_cast<uint4*>(ob + ((size_t)(2 * qd + u) * p.Ts + r_out) * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (SPLIT) *reinterpret_cast<uint4*>(ob + ((size_t)(8 + 2 * qd + u) * p.Ts + r_out) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-        tc_fence_before();
+      } else if (has_next) {
+        mbar_arrive(&bar_a1);
       }
       DXI_STAMP(9);
       ph ^= 1;
@@ -364,7 +383,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == EPI_WARPS) tmem_dealloc(tb, 512);
+  if (warp == EPI_WARPS) tmem_dealloc(0, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -492,7 +511,11 @@ __global__ void __launch_bounds__(256) stem_head_kernel(const float* __restrict_
 // ---------------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------------
-static void pack_b_sw128(unsigned char* hi, unsigned char* lo, int N, int K, const float* W /* [K][N] */) {
+// Packs W [K][N] (fp32) as fp16 hi / lo UMMA B images and returns the column sums of the EFFECTIVE weights
+// (hi, or hi + lo) in colsum[N]: that is what the deferred normalisation has to subtract.
+static void pack_b_sw128(unsigned char* hi, unsigned char* lo, int N, int K, const float* W /* [K][N] */, bool split,
+                         float* colsum) {
+  std::vector<double> cs(N, 0.0);
   for (int n = 0; n < N; ++n)
     for (int k = 0; k < K; ++k) {
       const int c = k >> 6, kk = k & 63, u = kk >> 3, e = kk & 7;
@@ -502,7 +525,10 @@ static void pack_b_sw128(unsigned char* hi, unsigned char* lo, int N, int K, con
       const __half l = __float2half_rn(w - __half2float(h));
       memcpy(hi + off, &h, 2);
       memcpy(lo + off, &l, 2);
+      cs[n] += (double)__half2float(h) + (split ? (double)__half2float(l) : 0.0);
     }
+  if (colsum)
+    for (int n = 0; n < N; ++n) colsum[n] = (float)cs[n];
 }
 
 static int n_dilations(int max_d_rate) { int n = 0; for (int m = max_d_rate; m > 0; m >>= 1) ++n; return n; }
@@ -517,18 +543,19 @@ int resnet_umma_prepare(dxi_net& net, cudaStream_t st) {
   std::vector<unsigned char> img((size_t)n_stages * IMG_BYTES, 0);
   for (int s = 0; s < n_stages; ++s) {
     unsigned char* base = img.data() + (size_t)s * IMG_BYTES;
-    float* bias = reinterpret_cast<float*>(base + IMG_BIAS);
+    float* aux = reinterpret_cast<float*>(base + IMG_BIAS);
+    const bool split = c.precision == DXI_PREC_F16X3;
     if (s >= 1) {
       const int li = 2 + 3 * (s - 1);
-      pack_b_sw128(base + IMG_W2, base + IMG_PART + IMG_W2, 64, 192, net.host_tensor(li + 1, "kernel")->data());   // [3*64][64]
-      pack_b_sw128(base + IMG_W3, base + IMG_PART + IMG_W3, 256, 64, net.host_tensor(li + 2, "kernel")->data());   // [64][256]
-      memcpy(bias, net.host_tensor(li + 1, "bias")->data(), 64 * 4);
-      memcpy(bias + 64, net.host_tensor(li + 2, "bias")->data(), 256 * 4);
+      pack_b_sw128(base + IMG_W2, base + IMG_PART + IMG_W2, 64, 192, net.host_tensor(li + 1, "kernel")->data(), split, nullptr);        // [3*64][64]
+      pack_b_sw128(base + IMG_W3, base + IMG_PART + IMG_W3, 256, 64, net.host_tensor(li + 2, "kernel")->data(), split, aux + OFF_CS3);  // [64][256]
+      memcpy(aux + OFF_B2, net.host_tensor(li + 1, "bias")->data(), 64 * 4);
+      memcpy(aux + OFF_B3, net.host_tensor(li + 2, "bias")->data(), 256 * 4);
     }
     if (s < c.n_blocks) {
       const int li = 2 + 3 * s;
-      pack_b_sw128(base + IMG_W1, base + IMG_PART + IMG_W1, 64, 256, net.host_tensor(li, "kernel")->data());       // [256][64]
-      memcpy(bias + 320, net.host_tensor(li, "bias")->data(), 64 * 4);
+      pack_b_sw128(base + IMG_W1, base + IMG_PART + IMG_W1, 64, 256, net.host_tensor(li, "kernel")->data(), split, aux + OFF_CS1);      // [256][64]
+      memcpy(aux + OFF_B1, net.host_tensor(li, "bias")->data(), 64 * 4);
     }
   }
   if (net.d_umma) { cudaFree(net.d_umma); net.d_umma = nullptr; }

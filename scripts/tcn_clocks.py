@@ -18,7 +18,7 @@ net(x); torch.cuda.synchronize()
 lib.dxi_debug_tcn_clocks(None, -1)
 c = buf.cpu().numpy().reshape(n_tiles, 16)[:, :10]
 d = np.diff(c, axis=1)
-names = ['A1 load+st', 'wait GEMM1', 'E1', 'wait GEMM2 g0', 'E2 pass1', 'LN merge', 'E2 pass2 (A3)', 'wait GEMM3', 'E3']
+names = ['wait GEMM1', 'P1 (A2)', 'merge2', 'wait GEMM2 g0', 'P2 (h, A3)', 'merge3', 'A1 next', 'wait GEMM3', 'P3 (c1 out)']
 print('tiles', n_tiles, 'stage', stage, ' total per tile: median %.0f cycles' % np.median(c[:, 9] - c[:, 0]))
 for i, n in enumerate(names):
     print('%-16s median %7.0f  mean %7.0f  p90 %7.0f' % (n, np.median(d[:, i]), d[:, i].mean(), np.percentile(d[:, i], 90)))
