@@ -61,6 +61,9 @@ struct StageArgs {
   int T, tiles_per_utt, n_tiles, Ts;
   int shift0, shift1, shift2;    // frame offsets of the three taps: tap j reads frame t - shift_j
   int has_back, has_front;
+  const float2* stem_stats;     // stage 0 only: per-row partial statistics of the stem pre-activation (8 parts of 32 channels);
+                                // the row is then LayerNorm(gamma) + ReLU'd on load (tcn.py:176-179), gamma in the b3 slot
+  int dbg_flags;                // tuning experiments only: 1 = skip residual loads, 2 = skip residual stores, 4 = skip c1 tap loads
   long long* dbg;               // optional: clock64 stamps of the epilogue phases (16 per tile), see dxi_debug_tcn_clocks
 };
 
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
         for (int plane = 0; plane < (SPLIT ? 2 : 1); ++plane)
 #pragma unroll
           for (int u = 0; u < 2; ++u)
-            qv[j][plane][u] = __ldg(reinterpret_cast<const uint4*>(cb + ((size_t)(plane * 8 + 2 * qd + u) * p.Ts + r_in) * 8));
+            qv[j][plane][u] = (p.dbg_flags & 4) ? make_uint4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uint4*>(cb + ((size_t)(plane * 8 + 2 * qd + u) * p.Ts + r_in) * 8));
       }
 #pragma unroll
       for (int j = 0; j < 3; ++j)
@@ -276,27 +279,60 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
       }
       DXI_STAMP(3);
       // ---- P2: h_new = h + b3 + inv2 (acc2 - mu2 colsum(W3)); r3 = ReLU(h_new) -> A3 in place, chunk by chunk
-      float s1 = 0.0f, s2 = 0.0f, kshift = 0.0f;
+      float mean0 = 0.0f, inv0 = 0.0f;
+      if (p.stem_stats) {     // merge the 8 partial statistics (32 channels each) the stem kernels left for this row
+        const float2* sp = p.stem_stats + ((size_t)tile * TILE + row) * 8;
+        float2 pt[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pt[i] = sp[i];
+        float m = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m += pt[i].x;
+        m *= 0.125f;
+        float m2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = pt[i].x - m; m2 += pt[i].y + 32.0f * d * d; }
+        mean0 = m;
+        inv0 = rsqrtf(m2 * (1.0f / 256.0f) + 1e-6f);
+      }
+      float2 s1v = make_float2(0.0f, 0.0f), s2v = make_float2(0.0f, 0.0f);     // sums of r and r^2 over this thread's 64 channels
       const float nim = -inv2 * mu2;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int cc = qd + 4 * i;
         float4 hv[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) hv[q] = *reinterpret_cast<const float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4));
+        for (int q = 0; q < 8; ++q) hv[q] = (p.dbg_flags & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4));
         float v[32];
         if (p.has_back) {
           mbar_wait(&bar_d2[cc >> 1], ph); tc_fence_after();
           if (i == 0) DXI_STAMP(4);
           tmem_ld32(lane_addr + COL_D2 + 32 * cc, v); tmem_wait_ld();
-          const float* b3 = sAux + OFF_B3 + 32 * cc;
-          const float* cs = sAux + OFF_CS3 + 32 * cc;
+          // packed fp32x2 arithmetic (FADD2 / FFMA2): v = inv2 * acc + (nim * colsum + (h + b3))
+          const float4* b3 = reinterpret_cast<const float4*>(sAux + OFF_B3 + 32 * cc);
+          const float4* cs = reinterpret_cast<const float4*>(sAux + OFF_CS3 + 32 * cc);
+          const float2 inv2v = make_float2(inv2, inv2), nimv = make_float2(nim, nim);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            v[4 * q]     = fmaf(inv2, v[4 * q],     fmaf(nim, cs[4 * q],     hv[q].x + b3[4 * q]));
-            v[4 * q + 1] = fmaf(inv2, v[4 * q + 1], fmaf(nim, cs[4 * q + 1], hv[q].y + b3[4 * q + 1]));
-            v[4 * q + 2] = fmaf(inv2, v[4 * q + 2], fmaf(nim, cs[4 * q + 2], hv[q].z + b3[4 * q + 2]));
-            v[4 * q + 3] = fmaf(inv2, v[4 * q + 3], fmaf(nim, cs[4 * q + 3], hv[q].w + b3[4 * q + 3]));
+            const float4 bq = b3[q], cq = cs[q];
+            float2 t0 = __fadd2_rn(make_float2(hv[q].x, hv[q].y), make_float2(bq.x, bq.y));
+            float2 t1 = __fadd2_rn(make_float2(hv[q].z, hv[q].w), make_float2(bq.z, bq.w));
+            t0 = __ffma2_rn(nimv, make_float2(cq.x, cq.y), t0);
+            t1 = __ffma2_rn(nimv, make_float2(cq.z, cq.w), t1);
+            t0 = __ffma2_rn(inv2v, make_float2(v[4 * q], v[4 * q + 1]), t0);
+            t1 = __ffma2_rn(inv2v, make_float2(v[4 * q + 2], v[4 * q + 3]), t1);
+            v[4 * q] = t0.x; v[4 * q + 1] = t0.y; v[4 * q + 2] = t1.x; v[4 * q + 3] = t1.y;
+          }
+        } else if (p.stem_stats) {
+          // stage 0: the loaded row is the stem pre-activation z; h0 = ReLU(z * inv0 * gamma - mean0 * inv0 * gamma)
+          const float* gm = sAux + OFF_B3 + 32 * cc;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float g0 = inv0 * gm[4 * q], g1 = inv0 * gm[4 * q + 1], g2 = inv0 * gm[4 * q + 2], g3 = inv0 * gm[4 * q + 3];
+            v[4 * q]     = relu(fmaf(hv[q].x, g0, -mean0 * g0));
+            v[4 * q + 1] = relu(fmaf(hv[q].y, g1, -mean0 * g1));
+            v[4 * q + 2] = relu(fmaf(hv[q].z, g2, -mean0 * g2));
+            v[4 * q + 3] = relu(fmaf(hv[q].w, g3, -mean0 * g3));
           }
         } else {
 #pragma unroll
@@ -306,20 +342,19 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.0f;
         }
-        if (p.has_back) {
+        if ((p.has_back || p.stem_stats) && !(p.dbg_flags & 2)) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
         if (p.has_front) {
-          if (i == 0) kshift = relu(v[0]);
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float r0 = relu(v[2 * j]), r1 = relu(v[2 * j + 1]);
-            const float d0 = r0 - kshift, d1 = r1 - kshift;
-            s1 += d0 + d1; s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2);
-            split_h2(r0, r1, hi[j], lo[j]);
+            const float2 r = make_float2(relu(v[2 * j]), relu(v[2 * j + 1]));
+            s1v = __fadd2_rn(s1v, r);
+            s2v = __ffma2_rn(r, r, s2v);
+            split_h2x(r, hi[j], lo[j]);
           }
           tmem_st16(lane_addr + COL_D2 + 32 * cc, hi);
           if (SPLIT) tmem_st16(lane_addr + COL_D2 + 32 * cc + 16, lo);
@@ -329,8 +364,8 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
       DXI_STAMP(5);
       float mu3 = 0.0f, inv3 = 0.0f;
       if (p.has_front) {
-        const float m1 = s1 * (1.0f / 64.0f);
-        ln_merge(red[1], row, qd, 64.0f, kshift + m1, fmaxf(s2 - s1 * m1, 0.0f), mu3, inv3);
+        const float s1 = s1v.x + s1v.y, s2 = s2v.x + s2v.y, m1 = s1 * (1.0f / 64.0f);
+        ln_merge(red[1], row, qd, 64.0f, m1, fmaxf(s2 - s1 * m1, 0.0f), mu3, inv3);
       }
       DXI_STAMP(6);
       // ---- the next tile's c1 taps travel to TMEM while this tile's GEMM3 drains
@@ -387,125 +422,261 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Stem and head on the CUDA cores in fp32 (the stem is the layer the 0.1 dB budget is most sensitive to,
-// SURVEY F8): Conv1D(256,1)+b -> LN(gamma) -> ReLU into the tiled residual layout, and
-// Conv1D(257,1)+b -> sigmoid out of it.  One CTA = 32 frames.
+// Stem (tcn.py:166-180) and output layer (tcn.py:158-161) on the tensor cores.
+//
+// stem_umma_kernel<half>: z[:, 128 half .. +128) = mag[:, 0..255] W0[0..255, ...] (fp16 hi/lo split, 3 MMAs: the
+//   stem is the layer the 0.1 dB budget is most sensitive to) + mag[:, 256] W0[256, ...] + b0 (CUDA cores, exact).
+//   Two launches (the hi+lo weights of one half are 128 KB of shared memory); z goes to the tiled residual
+//   buffer, per-row partial statistics to a side buffer; stage 0 applies LayerNorm(gamma) + ReLU on load.
+// head_umma_kernel: x_bar = sigmoid(h Wo + bo): columns 0..255 by tcgen05 (activation hi + lo times fp16
+//   weights, 2 MMAs: measured max 0.012 dB), column 256 as an fp32 dot product on the CUDA cores.
+// Both: 16 epilogue warps (4 threads per frame) + 1 MMA / loader warp, A operand written straight to TMEM.
 // ---------------------------------------------------------------------------------------------------
-constexpr int SM_ROWS = 32;
+constexpr int STEM_PART = 4 * 128 * 128;             // one precision part: 4 K-chunks x [128 rows x 128 B]
+constexpr int STEM_AUX = 2 * STEM_PART;              // fp32: b0[128], W0[256][128 half]
+constexpr int STEM_IMG_BYTES = STEM_AUX + 256 * 4;
+constexpr int STEM_STAGE_LD = TILE + 1;              // transposed input staging [64 cols][129]
+constexpr int HEAD_W = 4 * 256 * 128;                // hi only: 4 K-chunks x [256 rows x 128 B]
+constexpr int HEAD_IMG_BYTES = HEAD_W + (260 + 256) * 4;   // fp32: bo[257 (+3 pad)], Wo[:, 256]
+constexpr int HEAD_W_PAD = 134144;                   // staging buffer starts here (past the image)
+static_assert(HEAD_W_PAD >= HEAD_IMG_BYTES, "head staging buffer overlaps the weight image");
+constexpr int HEAD_STAGE_LD = 33;
 
-__device__ __forceinline__ float warp_sum_f(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
+struct StemArgs {
+  const unsigned char* img;
+  const float* mag;        // [B, T, 257]
+  float* h;                // tiled residual buffer (receives the pre-activation z)
+  float2* stats;           // [n_tiles * 128][8] (mean_i, M2_i) of 32-channel parts
+  int T, tiles_per_utt, n_tiles, half, n_feat;
+};
 
-__device__ __forceinline__ size_t h_tiled_index(int tile, int row, int c) {
-  return (size_t)tile * (TILE * 256) + ((size_t)(c >> 2) * TILE + row) * 4 + (c & 3);
-}
-
-// out[r][n] = sum_k A[r][k] W[k][n]; A tile in shared memory [SM_ROWS][LDA]; thread computes 4 rows x (NOUT/32) cols
-template <int KIN, int NOUT, bool STEM>
-__global__ void __launch_bounds__(256) stem_head_kernel(const float* __restrict__ in, const float* __restrict__ W,
-                                                        const float* __restrict__ bias, const float* __restrict__ gamma,
-                                                        float* __restrict__ out, int T, int tiles_per_utt, int groups_per_utt) {
-  constexpr int LDA = KIN + 1;
-  constexpr int CPT = (NOUT + 31) / 32;       // columns per thread, interleaved by 32
-  constexpr int LDO = NOUT + 1;
-  extern __shared__ __align__(16) float sm[];
-  float* A = sm;                                // [SM_ROWS][LDA], reused for the output tile [SM_ROWS][LDO]
-  float* Wc = sm + SM_ROWS * (LDA > LDO ? LDA : LDO);   // [16][NOUT]
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int b = blockIdx.x / groups_per_utt, t0 = (blockIdx.x - b * groups_per_utt) * SM_ROWS;
-  // ---- load the input rows (coalesced in either layout)
-  if (STEM) {
-    for (int r = warp; r < SM_ROWS; r += 8) {
-      const int t = t0 + r;
-      for (int c = lane; c < KIN; c += 32) A[r * LDA + c] = t < T ? __ldcs(in + ((size_t)b * T + t) * KIN + c) : 0.0f;
-    }
-  } else {
-    for (int i = tid; i < SM_ROWS * (KIN / 4); i += 256) {
-      const int c4 = i / SM_ROWS, r = i - c4 * SM_ROWS;
-      const int t = t0 + r;
-      float4 x = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      if (t < T) x = *reinterpret_cast<const float4*>(in + h_tiled_index(b * tiles_per_utt + t / TILE, t % TILE, 4 * c4));
-      float* dst = A + r * LDA + 4 * c4;
-      dst[0] = x.x; dst[1] = x.y; dst[2] = x.z; dst[3] = x.w;
-    }
-  }
-  const int ty = tid >> 5, tx = tid & 31;       // 8 row groups x 32 column lanes
-  float acc[4][CPT];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) acc[i][c] = 0.0f;
-  for (int k0 = 0; k0 < KIN; k0 += 16) {
-    __syncthreads();
-    for (int i = tid; i < 16 * NOUT; i += 256) {
-      const int kk = i / NOUT, c = i - kk * NOUT;
-      Wc[i] = (k0 + kk < KIN) ? __ldg(W + (size_t)(k0 + kk) * NOUT + c) : 0.0f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      if (k0 + kk >= KIN) break;
-      float a[4], w[CPT];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = A[(ty * 4 + i) * LDA + k0 + kk];
-#pragma unroll
-      for (int c = 0; c < CPT; ++c) w[c] = (tx + 32 * c < NOUT) ? Wc[kk * NOUT + tx + 32 * c] : 0.0f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) acc[i][c] = fmaf(a[i], w[c], acc[i][c]);
-    }
-  }
+__global__ void __launch_bounds__(STAGE_THREADS, 1) stem_umma_kernel(const StemArgs p) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar_w, bar_a, bar_d;
+  __shared__ uint32_t tmem_slot;
+  unsigned char* sW = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const float* sAux = reinterpret_cast<const float*>(sW + STEM_AUX);
+  float* stage = reinterpret_cast<float*>(sW + STEM_IMG_BYTES);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t COL_A_HI = 0, COL_A_LO = 128, COL_D = 256;
+  if (warp == EPI_WARPS) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) { mbar_init(&bar_w, 1); mbar_init(&bar_a, EPI_THREADS); mbar_init(&bar_d, 1); fence_mbar_init(); }
+  tc_fence_before();
   __syncthreads();
-  float* O = A;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) {
-      const int col = tx + 32 * c;
-      if (col < NOUT) O[(ty * 4 + i) * LDO + col] = acc[i][c] + __ldg(bias + col);
-    }
-  __syncthreads();
-  if (STEM) {
-    // LayerNorm(scale gamma, no centre, eps 1e-6) -> ReLU (tcn.py:176-179); tiled store: for a fixed group of
-    // 4 channels, consecutive frames are consecutive float4 -> each warp writes 32 frames x 16 B = 512 B runs
-    for (int r = warp; r < SM_ROWS; r += 8) {
-      const float* row = O + r * LDO;
-      float s = 0.0f;
-      for (int c = lane; c < NOUT; c += 32) s += row[c];
-      const float mean = warp_sum_f(s) * (1.0f / NOUT);
-      float q = 0.0f;
-      for (int c = lane; c < NOUT; c += 32) { const float d = row[c] - mean; q = fmaf(d, d, q); }
-      const float rs = rsqrtf(warp_sum_f(q) * (1.0f / NOUT) + 1e-6f);
-      if (lane == 0) { Wc[r] = mean; Wc[SM_ROWS + r] = rs; }
-    }
-    __syncthreads();
-    for (int i = tid; i < SM_ROWS * (NOUT / 4); i += 256) {
-      const int c4 = i / SM_ROWS, r = i - c4 * SM_ROWS;
-      const int t = t0 + r;
-      if (t >= T) continue;
-      const float mean = Wc[r], rs = Wc[SM_ROWS + r];
-      float4 o;
-      float* po = &o.x;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int c = 4 * c4 + e;
-        const float inv = rs * __ldg(gamma + c);
-        po[e] = fmaxf(fmaf(O[r * LDO + c], inv, -mean * inv), 0.0f);
+  tc_fence_after();
+  if (tmem_slot != 0) __trap();
+  if (warp == EPI_WARPS) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&bar_w, STEM_IMG_BYTES);
+      for (int off = 0; off < STEM_IMG_BYTES; off += 16384) {
+        const int n = STEM_IMG_BYTES - off < 16384 ? STEM_IMG_BYTES - off : 16384;
+        bulk_g2s(sW + off, p.img + off, n, &bar_w);
       }
-      *reinterpret_cast<float4*>(out + h_tiled_index(b * tiles_per_utt + t / TILE, t % TILE, 4 * c4)) = o;
+    }
+    __syncwarp();
+    mbar_wait(&bar_w, 0);
+    const uint32_t w_hi = smem_u32(sW), w_lo = w_hi + STEM_PART;
+    constexpr uint32_t id128 = make_idesc_f16(TILE, 128);
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      mbar_wait(&bar_a, ph); tc_fence_after();
+      uint32_t acc = 0;
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {
+        const uint32_t a0 = part == 1 ? COL_A_LO : COL_A_HI, w0 = part == 2 ? w_lo : w_hi;
+#pragma unroll
+        for (int ks = 0; ks < 16; ++ks) {
+          mma_ts_elect(COL_D, a0 + 8 * ks, make_smem_desc_sw128(w0 + (ks >> 2) * 128 * 128 + (ks & 3) * 32), id128, acc);
+          acc = 1;
+        }
+      }
+      mma_commit_elect(&bar_d);
+      ph ^= 1;
     }
   } else {
-    for (int r = warp; r < SM_ROWS; r += 8) {
-      const int t = t0 + r;
-      if (t >= T) continue;
-      for (int c = lane; c < NOUT; c += 32)
-        __stcs(out + ((size_t)b * T + t) * NOUT + c, 1.0f / (1.0f + expf(-O[r * LDO + c])));
+    mbar_wait(&bar_w, 0);
+    const int qd = warp >> 2, row = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TILE;
+      const int t = t0 + row;
+      const bool valid = t < p.T;
+      const float* mb = p.mag + (size_t)b * p.T * p.n_feat;
+      // ---- A operand: magnitudes of bins 0..255 as fp16 hi | lo, through a transposed shared-memory stage
+      for (int kq = 0; kq < 4; ++kq) {
+        {   // 16 independent loads per thread in flight, then the transposed stores
+          float x[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int i = tid + u * EPI_THREADS, r = i >> 6, c = i & 63;
+            x[u] = (t0 + r < p.T) ? __ldcs(mb + (size_t)(t0 + r) * p.n_feat + 64 * kq + c) : 0.0f;
+          }
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int i = tid + u * EPI_THREADS, r = i >> 6, c = i & 63;
+            stage[c * STEM_STAGE_LD + r] = x[u];
+          }
+        }
+        epi_barrier();
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          split_h2(stage[(16 * qd + 2 * j) * STEM_STAGE_LD + row], stage[(16 * qd + 2 * j + 1) * STEM_STAGE_LD + row], hi[j], lo[j]);
+        tmem_st8(lane_addr + COL_A_HI + 32 * kq + 8 * qd, hi);
+        tmem_st8(lane_addr + COL_A_LO + 32 * kq + 8 * qd, lo);
+        epi_barrier();
+      }
+      const float x256 = valid ? __ldg(mb + (size_t)t * p.n_feat + 256) : 0.0f;
+      tmem_wait_st(); tc_fence_before(); mbar_arrive(&bar_a);
+      // ---- z = acc + b0 + mag[256] W0[256, :]; partial statistics; tiled store
+      mbar_wait(&bar_d, ph); tc_fence_after();
+      float z[32];
+      tmem_ld32(lane_addr + COL_D + 32 * qd, z); tmem_wait_ld();
+      tc_fence_before();
+      float s = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        z[j] = valid ? z[j] + fmaf(x256, sAux[128 + 32 * qd + j], sAux[32 * qd + j]) : 0.0f;
+        s += z[j];
+      }
+      const float mean_i = s * (1.0f / 32.0f);
+      float m2 = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { const float d = z[j] - mean_i; m2 = fmaf(d, d, m2); }
+      p.stats[((size_t)tile * TILE + row) * 8 + p.half * 4 + qd] = make_float2(mean_i, m2);
+      float* hrow = p.h + (size_t)tile * (TILE * 256) + row * 4 + (size_t)(32 * p.half + 8 * qd) * (TILE * 4);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(hrow + (size_t)q * (TILE * 4)) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+      ph ^= 1;
     }
   }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS) tmem_dealloc(0, 512);
+}
+
+struct HeadArgs {
+  const unsigned char* img;
+  const float* h;          // tiled residual buffer
+  float* xbar;             // [B, T, 257]
+  int T, tiles_per_utt, n_tiles, n_outp;
+};
+
+__global__ void __launch_bounds__(STAGE_THREADS, 1) head_umma_kernel(const HeadArgs p) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar_w, bar_a, bar_d[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float dot[NSPLIT * TILE];
+  unsigned char* sW = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const float* sBias = reinterpret_cast<const float*>(sW + HEAD_W);          // [260]
+  const float* sLast = sBias + 260;                                           // Wo[:, 256]
+  float* stage = reinterpret_cast<float*>(sW + HEAD_W_PAD);                   // [4][128][33]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t COL_A_HI = 0, COL_A_LO = 128, COL_D = 256;
+  if (warp == EPI_WARPS) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) { mbar_init(&bar_w, 1); mbar_init(&bar_a, EPI_THREADS); mbar_init(&bar_d[0], 1); mbar_init(&bar_d[1], 1); fence_mbar_init(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tmem_slot != 0) __trap();
+  if (warp == EPI_WARPS) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&bar_w, HEAD_IMG_BYTES);
+      for (int off = 0; off < HEAD_IMG_BYTES; off += 16384) {
+        const int n = HEAD_IMG_BYTES - off < 16384 ? HEAD_IMG_BYTES - off : 16384;
+        bulk_g2s(sW + off, p.img + off, n, &bar_w);
+      }
+    }
+    __syncwarp();
+    mbar_wait(&bar_w, 0);
+    const uint32_t w_hi = smem_u32(sW);
+    constexpr uint32_t id128 = make_idesc_f16(TILE, 128);
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      {
+        const int nt = tile + gridDim.x;
+        if (nt < p.n_tiles && lane < 8) prefetch_l2(reinterpret_cast<const char*>(p.h + (size_t)nt * (TILE * 256)) + lane * 16384, 16384);
+        __syncwarp();
+      }
+      mbar_wait(&bar_a, ph); tc_fence_after();
+#pragma unroll
+      for (int nh = 0; nh < 2; ++nh) {      // output columns 128 nh .. +128, committed separately
+        uint32_t acc = 0;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          const uint32_t a0 = part == 1 ? COL_A_LO : COL_A_HI;
+#pragma unroll
+          for (int ks = 0; ks < 16; ++ks) {
+            mma_ts_elect(COL_D + 128 * nh, a0 + 8 * ks, make_smem_desc_sw128(w_hi + (ks >> 2) * 256 * 128 + nh * 128 * 128 + (ks & 3) * 32), id128, acc);
+            acc = 1;
+          }
+        }
+        mma_commit_elect(&bar_d[nh]);
+      }
+      ph ^= 1;
+    }
+  } else {
+    mbar_wait(&bar_w, 0);
+    const int qd = warp >> 2, row = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TILE;
+      const int t = t0 + row;
+      const bool valid = t < p.T;
+      const float* hrow = p.h + (size_t)tile * (TILE * 256) + row * 4 + (size_t)(16 * qd) * (TILE * 4);
+      // ---- A operand: h (raw residual sum, tcn.py:158-159) as fp16 hi | lo; column 256 as an fp32 dot product
+      float d256 = 0.0f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float4 hv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) hv[q] = *reinterpret_cast<const float4*>(hrow + (size_t)(4 * g + q) * (TILE * 4));
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float* wl = sLast + 64 * qd + 16 * g + 4 * q;
+          d256 = fmaf(hv[q].x, wl[0], d256); d256 = fmaf(hv[q].y, wl[1], d256);
+          d256 = fmaf(hv[q].z, wl[2], d256); d256 = fmaf(hv[q].w, wl[3], d256);
+          split_h2(hv[q].x, hv[q].y, hi[2 * q], lo[2 * q]);
+          split_h2(hv[q].z, hv[q].w, hi[2 * q + 1], lo[2 * q + 1]);
+        }
+        tmem_st8(lane_addr + COL_A_HI + 32 * qd + 8 * g, hi);
+        tmem_st8(lane_addr + COL_A_LO + 32 * qd + 8 * g, lo);
+      }
+      dot[qd * TILE + row] = d256;
+      tmem_wait_st(); tc_fence_before(); mbar_arrive(&bar_a);
+      epi_barrier();
+      float* xb = p.xbar + (size_t)b * p.T * p.n_outp;
+      if (qd == 0 && valid) {
+        const float z = dot[row] + dot[TILE + row] + dot[2 * TILE + row] + dot[3 * TILE + row] + sBias[256];
+        xb[(size_t)t * p.n_outp + 256] = 1.0f / (1.0f + expf(-z));
+      }
+      // ---- x_bar = sigmoid(acc + bo), staged through shared memory for row-major coalesced stores
+#pragma unroll
+      for (int nh = 0; nh < 2; ++nh) {
+        mbar_wait(&bar_d[nh], ph); tc_fence_after();
+        float z[32];
+        tmem_ld32(lane_addr + COL_D + 128 * nh + 32 * qd, z); tmem_wait_ld();
+        tc_fence_before();
+        float* st = stage + ((size_t)qd * TILE + row) * HEAD_STAGE_LD;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st[j] = 1.0f / (1.0f + expf(-(z[j] + sBias[128 * nh + 32 * qd + j])));
+        epi_barrier();
+        for (int i = tid; i < TILE * 128; i += EPI_THREADS) {
+          const int r = i >> 7, c = i & 127;
+          if (t0 + r < p.T) __stcs(xb + (size_t)(t0 + r) * p.n_outp + 128 * nh + c, stage[((size_t)(c >> 5) * TILE + r) * HEAD_STAGE_LD + (c & 31)]);
+        }
+        epi_barrier();
+      }
+      ph ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS) tmem_dealloc(0, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -530,6 +701,8 @@ static void pack_b_sw128(unsigned char* hi, unsigned char* lo, int N, int K, con
   if (colsum)
     for (int n = 0; n < N; ++n) colsum[n] = (float)cs[n];
 }
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static int n_dilations(int max_d_rate) { int n = 0; for (int m = max_d_rate; m > 0; m >>= 1) ++n; return n; }
 
@@ -558,6 +731,38 @@ int resnet_umma_prepare(dxi_net& net, cudaStream_t st) {
       memcpy(aux + OFF_B1, net.host_tensor(li, "bias")->data(), 64 * 4);
     }
   }
+  // ---- stem (two 128-column halves) and output layer images
+  const size_t off_stem = align_up(img.size(), 1024), stem_stride = align_up(STEM_IMG_BYTES, 1024);
+  const size_t off_head = off_stem + 2 * stem_stride;
+  img.resize(off_head + align_up(HEAD_IMG_BYTES, 1024), 0);
+  {
+    const float* W0 = net.host_tensor(0, "kernel")->data();      // [1][257][256]
+    const float* b0 = net.host_tensor(0, "bias")->data();
+    std::vector<float> sub((size_t)256 * 128);
+    for (int half = 0; half < 2; ++half) {
+      unsigned char* base = img.data() + off_stem + half * stem_stride;
+      for (int k = 0; k < 256; ++k)
+        for (int n = 0; n < 128; ++n) sub[(size_t)k * 128 + n] = W0[(size_t)k * 256 + 128 * half + n];
+      pack_b_sw128(base, base + STEM_PART, 128, 256, sub.data(), true, nullptr);
+      float* aux = reinterpret_cast<float*>(base + STEM_AUX);
+      for (int n = 0; n < 128; ++n) { aux[n] = b0[128 * half + n]; aux[128 + n] = W0[(size_t)256 * 256 + 128 * half + n]; }
+    }
+    // stage 0 applies the stem's LayerNorm scale: gamma rides in its (otherwise unused) b3 slot
+    memcpy(reinterpret_cast<float*>(img.data() + IMG_BIAS) + OFF_B3, net.host_tensor(1, "gamma")->data(), 256 * 4);
+    const int lo_ = 2 + 3 * c.n_blocks;
+    const float* Wo = net.host_tensor(lo_, "kernel")->data();    // [1][256][257]
+    const float* bo = net.host_tensor(lo_, "bias")->data();
+    std::vector<float> sq((size_t)256 * 256);
+    std::vector<unsigned char> scratch(HEAD_W);
+    for (int k = 0; k < 256; ++k)
+      for (int n = 0; n < 256; ++n) sq[(size_t)k * 256 + n] = Wo[(size_t)k * 257 + n];
+    unsigned char* hb = img.data() + off_head;
+    pack_b_sw128(hb, scratch.data(), 256, 256, sq.data(), false, nullptr);
+    float* aux = reinterpret_cast<float*>(hb + HEAD_W);
+    for (int n = 0; n < 257; ++n) aux[n] = bo[n];
+    for (int k = 0; k < 256; ++k) aux[260 + k] = Wo[(size_t)k * 257 + 256];
+  }
+  net.umma_stage_offset = {off_stem, off_stem + stem_stride, off_head};
   if (net.d_umma) { cudaFree(net.d_umma); net.d_umma = nullptr; }
   DXI_CUDA(cudaMalloc(&net.d_umma, img.size()));
   DXI_CUDA(cudaMemcpyAsync(net.d_umma, img.data(), img.size(), cudaMemcpyHostToDevice, st));
@@ -567,16 +772,15 @@ int resnet_umma_prepare(dxi_net& net, cudaStream_t st) {
 }
 
 static thread_local long long* g_dbg_clocks = nullptr;
-static thread_local int g_dbg_stage = -1;
-
-static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static thread_local int g_dbg_stage = -1, g_dbg_flags = 0;
 
 int64_t resnet_umma_workspace_bytes(const dxi_net& net, int B, int T) {
   const int tiles = (T + TILE - 1) / TILE;
   const size_t Ts = (size_t)tiles * TILE + 2 * C1_PAD;
   const size_t h_bytes = (size_t)B * tiles * TILE * 256 * 4;
   const size_t c1_bytes = align_up((size_t)B * 2 * 8 * Ts * 16, 256);
-  return (int64_t)(256 + h_bytes + 2 * c1_bytes);
+  const size_t stats_bytes = (size_t)B * tiles * TILE * 8 * sizeof(float2);
+  return (int64_t)(256 + h_bytes + 2 * c1_bytes + stats_bytes);
 }
 
 int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, float* xbar, void* ws, size_t ws_bytes,
@@ -590,42 +794,45 @@ int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, floa
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   float* h = reinterpret_cast<float*>(base);
   __half* c1[2] = {reinterpret_cast<__half*>(base + h_bytes), reinterpret_cast<__half*>(base + h_bytes + c1_bytes)};
+  float2* stem_stats = reinterpret_cast<float2*>(base + h_bytes + 2 * c1_bytes);
   // zero padding rows of the c1 planes (and everything else in them)
   DXI_CUDA(cudaMemsetAsync(c1[0], 0, 2 * c1_bytes, st));
 
-  // ---- stem (fp32 CUDA cores) -> tiled h
+  const int n_tiles = B * tiles;
+  int n_sm = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+  const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+  const unsigned char* images = reinterpret_cast<const unsigned char*>(net.d_umma);
+  // ---- stem (tcgen05, two 128-column halves) -> pre-activation z in the tiled buffer + partial row statistics
   {
-    constexpr int KIN = 257, NOUT = 256, LD = 258;
-    const size_t smem = sizeof(float) * (SM_ROWS * LD + 16 * NOUT);
-    auto kern = stem_head_kernel<KIN, NOUT, true>;
-    DXI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int groups = (T + SM_ROWS - 1) / SM_ROWS;
-    ProfScope prof("tcn_stem", st, 1);
-    kern<<<B * groups, 256, smem, st>>>(mag, net.dev_tensor(0, "kernel"), net.dev_tensor(0, "bias"), net.dev_tensor(1, "gamma"),
-                                        h, T, tiles, groups);
-    DXI_LAUNCHED("stem_head_kernel<stem>");
+    const size_t smem_stem = STEM_IMG_BYTES + 64 * STEM_STAGE_LD * sizeof(float) + 1024;
+    DXI_CUDA(cudaFuncSetAttribute(stem_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_stem));
+    ProfScope prof("tcn_stem", st, 2);
+    for (int half = 0; half < 2; ++half) {
+      StemArgs a{images + net.umma_stage_offset[half], mag, h, stem_stats, T, tiles, n_tiles, half, c.n_feat};
+      stem_umma_kernel<<<grid, STAGE_THREADS, smem_stem, st>>>(a);
+      DXI_LAUNCHED("stem_umma_kernel");
+    }
   }
   // ---- 41 tensor-core stages
   const bool split = c.precision == DXI_PREC_F16X3;
   const size_t smem = IMG_BYTES + 1024;
   DXI_CUDA(cudaFuncSetAttribute(tcn_stage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   DXI_CUDA(cudaFuncSetAttribute(tcn_stage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int n_tiles = B * tiles;
-  int n_sm = 148;
-  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
-  const int grid = n_tiles < n_sm ? n_tiles : n_sm;
   const int nd = n_dilations(c.max_d_rate);
   {
   ProfScope prof_stages("tcn_stage", st, c.n_blocks + 1);
   for (int s = 0; s <= c.n_blocks; ++s) {
     StageArgs a{};
-    a.img = reinterpret_cast<const unsigned char*>(net.d_umma) + (size_t)s * IMG_BYTES;
+    a.img = images + (size_t)s * IMG_BYTES;
+    a.stem_stats = s == 0 ? stem_stats : nullptr;
     a.h = h;
     a.c1_in = c1[(s + 1) & 1];
     a.c1_out = c1[s & 1];
     a.T = T; a.tiles_per_utt = tiles; a.n_tiles = n_tiles; a.Ts = Ts;
     a.has_back = s >= 1; a.has_front = s < c.n_blocks;
     a.dbg = (s == g_dbg_stage) ? g_dbg_clocks : nullptr;
+    a.dbg_flags = g_dbg_flags;
     const int d = s >= 1 ? 1 << ((s - 1) % nd) : 1;
     if (c.padding == DXI_PAD_CAUSAL) { a.shift0 = 2 * d; a.shift1 = d; a.shift2 = 0; }       // tap j reads t-(2-j)d
     else                             { a.shift0 = d;     a.shift1 = 0; a.shift2 = -d; }      // tap j reads t+(j-1)d
@@ -634,17 +841,14 @@ int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, floa
     DXI_LAUNCHED("tcn_stage_kernel");
   }
   }
-  // ---- head (fp32 CUDA cores): tiled h -> sigmoid(W h + b)
+  // ---- output layer (tcgen05 + one fp32 column): tiled h -> sigmoid(W h + b), row-major x_bar
   {
-    constexpr int KIN = 256, NOUT = 257, LD = 258;
-    const size_t smem2 = sizeof(float) * (SM_ROWS * LD + 16 * NOUT);
-    auto kern = stem_head_kernel<KIN, NOUT, false>;
-    DXI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    const int groups = (T + SM_ROWS - 1) / SM_ROWS;
-    const int li = 2 + 3 * c.n_blocks;
+    const size_t smem_head = HEAD_W_PAD + (size_t)NSPLIT * TILE * HEAD_STAGE_LD * sizeof(float) + 1024;
+    DXI_CUDA(cudaFuncSetAttribute(head_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head));
+    HeadArgs a{images + net.umma_stage_offset[2], h, xbar, T, tiles, n_tiles, c.n_outp};
     ProfScope prof("tcn_head", st, 1);
-    kern<<<B * groups, 256, smem2, st>>>(h, net.dev_tensor(li, "kernel"), net.dev_tensor(li, "bias"), nullptr, xbar, T, tiles, groups);
-    DXI_LAUNCHED("stem_head_kernel<head>");
+    head_umma_kernel<<<grid, STAGE_THREADS, smem_head, st>>>(a);
+    DXI_LAUNCHED("head_umma_kernel");
   }
   return DXI_OK;
 }
@@ -655,5 +859,6 @@ int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, floa
 // stamps per tile into dev_buf[n_tiles * 16]; pass nullptr to switch it off.
 extern "C" DXI_API void dxi_debug_tcn_clocks(long long* dev_buf, int stage) {
   dxi::g_dbg_clocks = dev_buf;
-  dxi::g_dbg_stage = dev_buf ? stage : -1;
+  dxi::g_dbg_stage = dev_buf ? (stage & 0xff) : -1;
+  dxi::g_dbg_flags = dev_buf ? (stage >> 8) : 0;     // bits 8.. : tuning-experiment flags (results are then wrong)
 }

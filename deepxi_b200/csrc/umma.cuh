@@ -209,5 +209,14 @@ __device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_
   lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
+// Same on a float2, with the residual computed by one packed subtract (FADD2).
+__device__ __forceinline__ void split_h2x(float2 a, uint32_t& hi, uint32_t& lo) {
+  __half2 h = __float22half2_rn(a);
+  float2 f = __half22float2(h);
+  __half2 l = __float22half2_rn(__fadd2_rn(a, make_float2(-f.x, -f.y)));
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
 }  // namespace umma
 }  // namespace dxi
