@@ -75,6 +75,9 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int STAGE_THREADS = EPI_THREADS + 32;   // + 1 warp: weight load, L2 prefetch, MMA issue
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+// The NSPLIT threads that share a frame sit in the NSPLIT warps with the same lane quarter q = warp & 3: statistics
+// merges only need those 128 threads (named barrier 2 + q), not the whole epilogue.
+__device__ __forceinline__ void quarter_barrier(int q) { asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(NSPLIT * 32) : "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
@@ -84,7 +87,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
 // 1/sqrt(biased variance + 1e-6) of the whole row.
 __device__ __forceinline__ void ln_merge(float2* red, int row, int qd, float n, float mean_i, float m2_i, float& mean, float& inv) {
   red[qd * TILE + row] = make_float2(mean_i, m2_i);
-  epi_barrier();
+  quarter_barrier(row >> 5);
   float2 pt[NSPLIT];
 #pragma unroll
   for (int i = 0; i < NSPLIT; ++i) pt[i] = red[i * TILE + row];

@@ -47,11 +47,13 @@ class MagTgt(InputTarget):
         inp [B, Tmax, 257], phase [B, Tmax, 257] and the per-utterance frame counts (host list)."""
         x, _ = to_dev(x_batch, torch.int16)
         lens_host = [int(l) for l in x_batch_len]
-        key = (str(x.device), tuple(lens_host))
-        if getattr(self, '_lens_key', None) != key:      # the lengths of a repeated batch are uploaded once
-            self._lens_dev = torch.tensor(lens_host, dtype=torch.int32).to(x.device, non_blocking=True)
-            self._lens_key = key
-        lens = self._lens_dev
+        key = (str(x.device), torch.cuda.current_stream(x.device).cuda_stream, tuple(lens_host))
+        cache = self.__dict__.setdefault('_lens_cache', {})
+        if key not in cache:                              # the lengths of a repeated batch are uploaded once per stream
+            if len(cache) > 16:
+                cache.clear()
+            cache[key] = torch.tensor(lens_host, dtype=torch.int32).to(x.device, non_blocking=True)
+        lens = cache[key]
         if x.dim() != 2 or x.shape[0] != len(lens_host):
             raise ValueError('x_batch must be [B, Lmax] with one length per row')
         Tmax = self.n_frames(max(lens_host)) if lens_host else 0

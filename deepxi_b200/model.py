@@ -131,3 +131,39 @@ class DeepXi:
                         save_wav(out_path + '/' + base_name + '.wav', out[i, :n], self.inp_tgt.f_s)
                     else:
                         save_mat(out_path + '/' + base_name + '.mat', out[i, :n_frames[i]], key)
+
+
+class HostPipeline:
+    """Throughput-oriented serving loop over host buffers: every submitted batch is copied host -> device,
+    enhanced, and copied back on one of `n_streams` CUDA streams, so the PCIe copies of one batch overlap the
+    kernels of another.  Inputs / outputs are pinned host tensors owned by the caller.
+
+        pipe = HostPipeline(deepxi, n_streams=3)
+        for x, lens, y in batches:          # x int16 [B, L] pinned, y int16 [B, (Tmax+1)*256] pinned
+            pipe.submit(x, lens, y)
+        pipe.drain()                        # all outputs are now valid
+    """
+
+    def __init__(self, deepxi, n_streams=3, out_type='y', gain='mmse-lsa'):
+        self.dx, self.out_type, self.gain = deepxi, out_type, gain
+        self.streams = [torch.cuda.Stream() for _ in range(n_streams)]
+        self._i = 0
+        self._keep = [None] * n_streams
+
+    def submit(self, x_host, x_len, out_host):
+        if not (x_host.is_pinned() and out_host.is_pinned()):
+            raise ValueError('HostPipeline needs pinned host tensors')
+        k = self._i % len(self.streams)
+        self._i += 1
+        st = self.streams[k]
+        with torch.cuda.stream(st):
+            xd = x_host.to('cuda', non_blocking=True)
+            out, n_frames = self.dx.infer_batch(xd, x_len, self.out_type, self.gain, int16=out_host.dtype == torch.int16)
+            out_host.copy_(out, non_blocking=True)
+            self._keep[k] = (xd, out)       # keep the device buffers alive until the stream is reused
+        return n_frames
+
+    def drain(self):
+        for st in self.streams:
+            st.synchronize()
+

@@ -22,7 +22,7 @@ class DeviceNetwork:
         cfg.precision = _lib.PRECISIONS[precision]
         self._cfg = cfg
         self._h = ctypes.c_void_p(0)
-        self._ws = None
+        self._ws = {}          # one workspace per (device, stream): concurrent streams must not share scratch
         self._loaded = False
         self.n_feat, self.n_outp = cfg.n_feat, cfg.n_outp
         lib = _lib.load()
@@ -58,10 +58,12 @@ class DeviceNetwork:
         out = torch.empty((B, T, self.n_outp), dtype=torch.float32, device=x.device)
         if B and T:
             need = self.workspace_bytes(B, T)
-            if self._ws is None or self._ws.numel() < need or self._ws.device != x.device:
-                self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
-            _lib.check(_lib.load().dxi_net_forward(self._h, _lib.ptr(x), B, T, _lib.ptr(out), _lib.ptr(self._ws),
-                                                   self._ws.numel(), _lib.stream_ptr(x.device)))
+            key = (str(x.device), torch.cuda.current_stream(x.device).cuda_stream)
+            ws = self._ws.get(key)
+            if ws is None or ws.numel() < need:
+                ws = self._ws[key] = torch.empty(need, dtype=torch.uint8, device=x.device)
+            _lib.check(_lib.load().dxi_net_forward(self._h, _lib.ptr(x), B, T, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+                                                   _lib.stream_ptr(x.device)))
         return ret(out[0] if squeeze else out, was_np)
 
     predict = __call__

@@ -179,3 +179,21 @@ def test_mhanetv3_infer_and_limits(xi_stats):
     too_long = torch.zeros((1, 2049, 257), device='cuda')
     with pytest.raises(_lib.DxiError):                 # more frames than positional-embedding rows (attention.py:432)
         dx.network(too_long)
+
+
+def test_host_pipeline_matches_infer_batch():
+    from deepxi_b200.model import HostPipeline
+    w = weights.synthetic_resnetv2(0)
+    dx = DeepXi(512, 256, 512, 16000, 'MagXi', 'ResNetV2', ver='resnet-1.1c', map_type='DBNormalCDF', map_params=None,
+                padding='causal', precision='f16x3', **RES_KW)
+    dx.set_weights(w)
+    lens = [16000] * 6
+    xs = [torch.from_numpy(synth.noisy_speech(6, 16000, seed=80 + i)).pin_memory() for i in range(5)]
+    ys = [torch.empty((6, 64 * 256), dtype=torch.int16).pin_memory() for _ in range(5)]
+    pipe = HostPipeline(dx, n_streams=3)
+    for x, y in zip(xs, ys):
+        pipe.submit(x, lens, y)
+    pipe.drain()
+    for x, y in zip(xs, ys):
+        ref, _ = dx.infer_batch(x.cuda(), lens, 'y', 'mmse-lsa', int16=True)
+        assert torch.equal(ref.cpu(), y)
