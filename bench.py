@@ -157,7 +157,19 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     if world > 1 and not dist.is_initialized():
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL prints a version banner on stdout when the communicator is created; stdout must carry exactly
+        # ONE JSON line, so fd 1 points at stderr until the first collective has run.
+        sys.stdout.flush()
+        keep = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier(device_ids=[local_rank])
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(keep, 1)
+            os.close(keep)
 
     def barrier():
         if world > 1:
@@ -210,16 +222,20 @@ def run_ours(args, rank, world, local_rank):
     from deepxi_b200.model import HostPipeline
     pipe = HostPipeline(dx, n_streams=3)
     y_hosts = [torch.empty((B, (T + 1) * 256), dtype=torch.int16).pin_memory() for _ in range(3)]
-    for i in range(max(3, args.warmup)):
+    for i in range(max(6, args.warmup)):          # two rounds per stream: the allocator pools of all streams settle
         pipe.submit(x_host, lens, y_hosts[i % 3])
     pipe.drain()
     torch.cuda.synchronize(); barrier()
     t0 = time.perf_counter()
+    marks = []
     for i in range(args.steps):
         pipe.submit(x_host, lens, y_hosts[i % 3])
+        marks.append(time.perf_counter() - t0)
     pipe.drain()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if os.environ.get('DXI_BENCH_DEBUG'):
+        sys.stderr.write('rank %d e2e submit marks %s total %.4f\n' % (rank, ['%.4f' % m for m in marks], e2e_s))
     barrier()
     assert int(y_hosts[0].abs().max()) > 0
 
@@ -278,6 +294,7 @@ def run_ours(args, rank, world, local_rank):
 
 
 def main():
+    os.environ.setdefault('NCCL_DEBUG', 'WARN')      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
