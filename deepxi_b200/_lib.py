@@ -23,7 +23,7 @@ MASK_MODES = {'none': 0, 'causal+pad': 1}
 SYMBOLS = ['dxi_last_error', 'dxi_version', 'dxi_device_check', 'dxi_stft', 'dxi_istft', 'dxi_map_gain', 'dxi_gfunc',
            'dxi_cdf_map', 'dxi_enhance', 'dxi_net_create', 'dxi_net_load', 'dxi_net_finalize',
            'dxi_net_workspace_bytes', 'dxi_net_forward', 'dxi_net_destroy', 'dxi_launch_count',
-           'dxi_launch_count_reset', 'dxi_selftest_umma', 'dxi_profile_enable', 'dxi_profile_read', 'dxi_debug_tcn_clocks']
+           'dxi_launch_count_reset', 'dxi_selftest_umma', 'dxi_profile_enable', 'dxi_profile_read', 'dxi_debug_tcn_clocks', 'dxi_debug_tmem_bw', 'dxi_debug_tcn_stop_after']
 
 
 class DxiError(RuntimeError):
@@ -74,6 +74,10 @@ def load():
     lib.dxi_profile_read.restype = i32
     lib.dxi_debug_tcn_clocks.argtypes = [vp, i32]
     lib.dxi_debug_tcn_clocks.restype = None
+    lib.dxi_debug_tmem_bw.argtypes = [i32, i32, i32, vp, vp]
+    lib.dxi_debug_tmem_bw.restype = i32
+    lib.dxi_debug_tcn_stop_after.argtypes = [i32]
+    lib.dxi_debug_tcn_stop_after.restype = None
     for name in ('dxi_stft', 'dxi_istft', 'dxi_map_gain', 'dxi_gfunc', 'dxi_cdf_map', 'dxi_enhance', 'dxi_net_create',
                  'dxi_net_load', 'dxi_net_finalize', 'dxi_net_forward', 'dxi_net_destroy', 'dxi_selftest_umma'):
         getattr(lib, name).restype = i32

@@ -209,13 +209,20 @@ __device__ __forceinline__ void split_h2(float a, float b, uint32_t& hi, uint32_
   lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
-// Same on a float2, with the residual computed by one packed subtract (FADD2).
+// hi/lo split of a float2 with few conversion-pipe (XU) instructions: hi = a truncated to an 11-bit significand by a
+// bit mask (ALU), so its fp16 conversion is exact, lo = a - hi (one packed FADD2, exact) rounded to fp16: hi + lo
+// carries >= 21 significant bits.  Two F2FP per pair instead of two F2FP + two fp16->fp32 conversions.
 __device__ __forceinline__ void split_h2x(float2 a, uint32_t& hi, uint32_t& lo) {
-  __half2 h = __float22half2_rn(a);
-  float2 f = __half22float2(h);
-  __half2 l = __float22half2_rn(__fadd2_rn(a, make_float2(-f.x, -f.y)));
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  lo = *reinterpret_cast<uint32_t*>(&l);
+  const float2 h = make_float2(__uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u));
+  const float2 l = __fadd2_rn(a, make_float2(-h.x, -h.y));
+  __half2 hh = __float22half2_rn(h), ll = __float22half2_rn(l);
+  hi = *reinterpret_cast<uint32_t*>(&hh);
+  lo = *reinterpret_cast<uint32_t*>(&ll);
+}
+template <bool SPLIT>
+__device__ __forceinline__ void to_h2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  if (SPLIT) split_h2x(make_float2(a, b), hi, lo);
+  else { hi = pack_h2(a, b); lo = 0; }       // single-product mode: round to nearest
 }
 
 }  // namespace umma

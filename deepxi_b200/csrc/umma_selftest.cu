@@ -98,9 +98,55 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __half* __rest
   if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
+
+// TMEM port micro-benchmark: `warps` warps (multiple of 4) each run `rounds` x (tcgen05.ld|st .32x32b.x32) on their
+// lane quarter; out[0] = cycles for the whole CTA (max over warps).  mode 0 = loads, 1 = stores, 2 = load + store.
+__global__ void __launch_bounds__(1024) tmem_bw_kernel(int mode, int rounds, long long* out) {
+  __shared__ uint32_t slot;
+  __shared__ long long t_start, t_end;
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) tmem_alloc(&slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t col0 = (uint32_t)((warp >> 2) * 32) & 511;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = (float)j;
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int r = 0; r < rounds; ++r) {
+    const uint32_t col = (col0 + 128 * (r & 3)) & 511;
+    if (mode == 0 || mode == 2) { tmem_ld32(lane_addr + col, v); }
+    if (mode == 1 || mode == 2) { tmem_st32(lane_addr + ((col + 64) & 511), reinterpret_cast<const uint32_t(&)[32]>(v)); }
+  }
+  tmem_wait_ld(); tmem_wait_st();
+  const long long t1 = clock64();
+  if (threadIdx.x == 0) { t_start = t0; t_end = t1; }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { atomicMin(&t_start, t0); atomicMax(&t_end, t1); }
+  __syncthreads();
+  float acc = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc += v[j];
+  if (threadIdx.x == 0) { out[0] = t_end - t_start; out[1] = (long long)acc; }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(slot, 512);
+}
+
 }  // namespace dxi
 
 using namespace dxi;
+
+extern "C" DXI_API int dxi_debug_tmem_bw(int mode, int warps, int rounds, long long* dev_out, void* stream) {
+  if (int rc = check_device()) return rc;
+  DXI_REQUIRE(warps >= 4 && warps <= 32 && warps % 4 == 0 && rounds > 0 && dev_out, "dxi_debug_tmem_bw: bad argument");
+  tmem_bw_kernel<<<1, warps * 32, 0, as_stream(stream)>>>(mode, rounds, dev_out);
+  DXI_LAUNCHED("tmem_bw_kernel");
+  return DXI_OK;
+}
 
 extern "C" DXI_API int dxi_selftest_umma(const void* a_f16, const void* b_f16, int N, int K, int variant, float* d_out,
                                  void* stream) {

@@ -179,6 +179,13 @@ DXI_API int dxi_profile_read(const char* key, double* total_ms, int64_t* launche
  * thread writes 16 clock64 stamps per tile into dev_buf (int64 [n_tiles * 16]); NULL switches it off. */
 DXI_API void dxi_debug_tcn_clocks(long long* dev_buf, int stage);
 
+/* Debug aid: subsequent dxi_net_forward calls of this thread run only the stem and stages 0..stage (-1: all). */
+DXI_API void dxi_debug_tcn_stop_after(int stage);
+
+/* Tuning aid: cycles for `warps` warps x `rounds` x 4 KB tcgen05.ld (mode 0) / st (mode 1) / both (mode 2) on one SM;
+ * dev_out[0] = cycles. */
+DXI_API int dxi_debug_tmem_bw(int mode, int warps, int rounds, long long* dev_out, void* stream);
+
 /* Self test of the tcgen05 / TMEM building blocks: D[128,N] = A[128,K] * B[K,N] with fp16 operands
  * (A from tensor memory, B from shared memory) written to `d_out` (float32 [128,N]).
  * a_host_layout / b: device fp16 row-major [128,K] and [N,K].  variant selects descriptor encodings

@@ -197,3 +197,21 @@ def test_host_pipeline_matches_infer_batch():
     for x, y in zip(xs, ys):
         ref, _ = dx.infer_batch(x.cuda(), lens, 'y', 'mmse-lsa', int16=True)
         assert torch.equal(ref.cpu(), y)
+
+
+def test_resnetv2_repeatable_after_a_larger_batch():
+    """Regression: stale workspace / tensor-memory contents must never leak into a run (a missing barrier in stage 0
+    once made the first small batch after a large one depend on timing)."""
+    w = weights.synthetic_resnetv2(0)
+    net = network_selector('ResNetV2', None, 257, padding='causal', precision='f16x3', **RES_KW).load_weights(w)
+    from deepxi_b200.inp_tgt import inp_tgt_selector
+    it = inp_tgt_selector('MagXi', 512, 256, 512, 16000, map_type='DBNormalCDF', map_params=None)
+    x = np.tile(synth.noisy_speech(4, 160000, seed=52), (12, 1))
+    inp, _, _ = it.observation_batch(torch.from_numpy(x).cuda(), [160000] * 48)
+    for T in (300, 129, 500, 77):
+        small = inp[:3, :T].contiguous()
+        ref = net(small).clone()
+        for _ in range(3):
+            big = net(inp)
+            assert torch.equal(net(small), ref)
+            assert torch.equal(big[:3, :T], ref)
