@@ -22,18 +22,13 @@
 // statistics merge runs while the tensor core is already busy.  colsum(W3), colsum(W1') ride in the weight image
 // (summed over the effective fp16 hi[+lo] weights so the mean component cancels to rounding).
 //
-// Two tiles in flight per SM.  Tensor memory is split into two 256-column slots; each slot runs the whole
-// per-tile chain (taps -> GEMM1 -> A2 -> GEMM2 -> h update / A3 -> GEMM3 -> c1') independently with its own 8
-// epilogue warps (two threads per frame), its own MMA-issuing warp and its own mbarriers, so the latency of one
-// tile's chain (global loads, MMA round trips, statistics merges) is covered by the other tile's work.  A slot
-// fits in 256 columns because GEMM2 runs in two 128-column halves: half h of the fp32 accumulators is turned IN
-// PLACE into the fp16 hi|lo A operand of GEMM3 (16 fp32 columns -> 8 hi + 8 lo), GEMM3 accumulates over both
-// halves, and the tensor pipe's in-order execution lets GEMM2's second half reuse the columns as soon as it is
-// issued behind GEMM3's first half.  Slot-relative columns: taps hi [0,96) lo [96,192) | GEMM1 acc [192,256);
-// then A2 hi [0,32) lo [32,64) | GEMM2-half acc / A3 [64,192) | GEMM3 acc [192,256).
-// Warps 0-7 / 8-15: epilogue of slot 0 / 1 (TMEM lane quarter = warp & 3, column half = (warp >> 2) & 1; LayerNorm
-// statistics merged pairwise through shared memory with Chan's formula); warps 16 / 17: MMA issue for slot 0 / 1
-// (warp-convergent, elected lane inside the asm); warp 16 also loads the weights (bulk async copy).
+// TMEM columns: [0,256) GEMM2 accumulators, overwritten IN PLACE by the A operand of GEMM3 (32 fp32 columns
+// -> 16 hi + 16 lo); [256,320) A operand of GEMM2, later GEMM3 accumulators; [320,512) the three c1 taps of
+// the NEXT tile (loaded while this tile's GEMM3 drains); GEMM1 accumulators reuse [0,64).
+// Warps 0-15: epilogue, four threads per frame (a quarter of the columns each; TMEM lane quarter = warp & 3;
+// LayerNorm statistics merged with Chan's formula through shared memory).  Warp 16: weight load (bulk async
+// copy), L2 prefetch of the next tile, warp-convergent MMA issue.  GEMM2 is committed in four column groups and
+// GEMM3 is issued in eight K-chunks as the epilogue produces them.
 #include <vector>
 #include "net.cuh"
 #include "umma.cuh"
@@ -87,61 +82,59 @@ __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-// ---- two-slot stage kernel --------------------------------------------------------------------------------
-constexpr int S2_EPI_WARPS = 16, S2_THREADS = (S2_EPI_WARPS + 2) * 32;
-constexpr uint32_t S_A1_HI = 0, S_A1_LO = 96, S_D1 = 192, S_A2_HI = 0, S_A2_LO = 32, S_D2H = 64, S_D3 = 192;
-
-// LayerNorm statistics of a row shared by the two threads (hb = 0, 1) of a slot that own it: each contributes
-// (mean_i, M2_i) of its n values; Chan's formula merges them.  bar_id: named barrier of the 64 threads
-// (2 warps) of this slot and lane quarter.
-__device__ __forceinline__ void ln_merge2(float2* red, int row, int hb, int bar_id, float n, float mean_i, float m2_i,
-                                          float& mean, float& inv) {
-  red[hb * TILE + row] = make_float2(mean_i, m2_i);
-  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-  const float2 o = red[(hb ^ 1) * TILE + row];
-  const float d = mean_i - o.x;
-  mean = 0.5f * (mean_i + o.x);
-  inv = rsqrtf((m2_i + o.y + 0.5f * n * d * d) / (2.0f * n) + 1e-6f);
+// LayerNorm statistics of one row split between NSPLIT threads (n values each): every thread contributes
+// (mean_i, M2_i = sum of squared deviations from mean_i); Chan's formula merges them.  Returns mean and
+// 1/sqrt(biased variance + 1e-6) of the whole row.
+__device__ __forceinline__ void ln_merge(float2* red, int row, int qd, float n, float mean_i, float m2_i, float& mean, float& inv) {
+  red[qd * TILE + row] = make_float2(mean_i, m2_i);
+  quarter_barrier(row >> 5);
+  float2 pt[NSPLIT];
+#pragma unroll
+  for (int i = 0; i < NSPLIT; ++i) pt[i] = red[i * TILE + row];
+  float m = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NSPLIT; ++i) m += pt[i].x;
+  m *= (1.0f / NSPLIT);
+  float m2 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NSPLIT; ++i) { const float d = pt[i].x - m; m2 += pt[i].y + n * d * d; }
+  mean = m;
+  inv = rsqrtf(m2 / (n * NSPLIT) + 1e-6f);
 }
 
 template <bool SPLIT>
-__global__ void __launch_bounds__(S2_THREADS, 1) tcn_stage_kernel(const StageArgs p) {
+__global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const StageArgs p) {
   extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, bar_a1[2], bar_a2[2], bar_a3[2][8], bar_x[2], bar_d1[2], bar_d2[2][4], bar_d3[2];
+  __shared__ __align__(8) uint64_t bar_w, bar_a1, bar_a2, bar_a3[8], bar_d1, bar_d2[4], bar_d3;
   __shared__ uint32_t tmem_slot;
-  __shared__ float2 red[2][3][2 * TILE];
+  __shared__ float2 red[3][NSPLIT * TILE];
   unsigned char* sW = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const float* sAux = reinterpret_cast<const float*>(sW + IMG_BIAS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  if (warp == S2_EPI_WARPS) tmem_alloc(&tmem_slot, 512);
+  if (warp == EPI_WARPS) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     mbar_init(&bar_w, 1);
-    for (int s = 0; s < 2; ++s) {
-      // epilogue -> MMA barriers count WARPS: after the warp-wide tcgen05.wait one lane arrives for the warp
-      mbar_init(&bar_a1[s], 8);
-      mbar_init(&bar_a2[s], 8);
-      for (int i = 0; i < 8; ++i) mbar_init(&bar_a3[s][i], 4);      // a 32-channel chunk belongs to the 4 warps of one column half
-      mbar_init(&bar_x[s], 8);
-      mbar_init(&bar_d1[s], 1);
-      for (int i = 0; i < 4; ++i) mbar_init(&bar_d2[s][i], 1);
-      mbar_init(&bar_d3[s], 1);
-    }
+    // epilogue -> MMA barriers count WARPS: after the warp-wide tcgen05.wait one lane arrives for its warp
+    mbar_init(&bar_a1, EPI_WARPS);
+    mbar_init(&bar_a2, EPI_WARPS);
+    for (int i = 0; i < 8; ++i) mbar_init(&bar_a3[i], 4);        // a 32-channel chunk belongs to the 4 warps of one column quarter
+    mbar_init(&bar_d1, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_d2[i], 1);
+    mbar_init(&bar_d3, 1);
     fence_mbar_init();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // The CTA owns the SM's whole tensor memory (512 columns, one CTA per SM): the allocation starts at lane 0 /
-  // column 0 and TMEM addresses are slot * 256 + compile-time constants.
+  // The CTA owns the SM's whole tensor memory (512 columns, one CTA per SM), so the allocation starts at
+  // lane 0 / column 0: TMEM addresses below are compile-time constants.
   if (tmem_slot != 0) __trap();
-  const int slot = warp >= S2_EPI_WARPS ? warp - S2_EPI_WARPS : warp >> 3;
-  const uint32_t cb = 256u * slot;
-  const int tile0 = blockIdx.x + slot * gridDim.x, tstep = 2 * gridDim.x;     // this slot's tiles
 
-  if (warp >= S2_EPI_WARPS) {
-    // ================= MMA issue for one slot (whole warp convergent; lane elected inside the asm) =================
-    if (warp == S2_EPI_WARPS && elect_one()) {
+  if (warp == EPI_WARPS) {
+    // ================= weight load, L2 prefetch of the next tile, MMA issue =================
+    // The whole warp runs this code convergently; single-thread operations elect a lane inside the asm.
+    if (elect_one()) {
       mbar_arrive_expect_tx(&bar_w, IMG_BYTES);
       for (int off = 0; off < IMG_BYTES; off += 16384) {
         const int n = IMG_BYTES - off < 16384 ? IMG_BYTES - off : 16384;
@@ -154,9 +147,9 @@ __global__ void __launch_bounds__(S2_THREADS, 1) tcn_stage_kernel(const StageArg
     constexpr uint32_t id64 = make_idesc_f16(TILE, 64);
     constexpr int NPART = SPLIT ? 3 : 1;          // (a_hi, w_hi) [+ (a_lo, w_hi) + (a_hi, w_lo)]
     uint32_t ph = 0;
-    for (int tile = tile0; tile < p.n_tiles; tile += tstep) {
-      {   // pull this slot's next tile (residual rows, c1 rows) into L2 ahead of its use
-        const int nt = tile + tstep;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      {   // pull the tile after next's residual rows / next tile's rows into L2 ahead of their use
+        const int nt = tile + gridDim.x;
         if (nt < p.n_tiles) {
           const char* hn = reinterpret_cast<const char*>(p.h + (size_t)nt * (TILE * 256));
           if (lane < 8) prefetch_l2(hn + lane * 16384, 16384);
@@ -164,117 +157,102 @@ __global__ void __launch_bounds__(S2_THREADS, 1) tcn_stage_kernel(const StageArg
             const int b = nt / p.tiles_per_utt, t0 = (nt - b * p.tiles_per_utt) * TILE;
             const int lo_row = t0 - (p.shift0 > 0 ? p.shift0 : 0) + C1_PAD;
             const int n_rows = TILE + (p.shift0 > 0 ? p.shift0 : 0) - (p.shift2 < 0 ? p.shift2 : 0);
-            const __half* c1b = p.c1_in + (size_t)b * 2 * 8 * p.Ts * 8;
-            prefetch_l2(c1b + ((size_t)(lane - 16) * p.Ts + lo_row) * 8, n_rows * 16);
+            const __half* cb = p.c1_in + (size_t)b * 2 * 8 * p.Ts * 8;
+            prefetch_l2(cb + ((size_t)(lane - 16) * p.Ts + lo_row) * 8, n_rows * 16);
           }
         }
         __syncwarp();
       }
       if (p.has_back) {
-        mbar_wait(&bar_a1[slot], ph); tc_fence_after();
+        mbar_wait(&bar_a1, ph); tc_fence_after();
         {   // c2 = W2 (*) [c1(t-s0) | c1(t-s1) | c1(t-s2)] : K = 192, N = 64
           uint32_t acc = 0;
 #pragma unroll
           for (int part = 0; part < NPART; ++part) {
-            const uint32_t a0 = cb + (part == 1 ? S_A1_LO : S_A1_HI), w0 = (part == 2 ? w_lo : w_hi) + IMG_W2;
+            const uint32_t a0 = part == 1 ? COL_A1_LO : COL_A1_HI, w0 = (part == 2 ? w_lo : w_hi) + IMG_W2;
 #pragma unroll
             for (int ks = 0; ks < 12; ++ks) {
-              mma_ts_elect(cb + S_D1, a0 + 8 * ks, make_smem_desc_sw128(w0 + (ks >> 2) * 64 * 128 + (ks & 3) * 32), id64, acc);
+              mma_ts_elect(COL_D1, a0 + 8 * ks, make_smem_desc_sw128(w0 + (ks >> 2) * 64 * 128 + (ks & 3) * 32), id64, acc);
               acc = 1;
             }
           }
         }
-        mma_commit_elect(&bar_d1[slot]);
-        mbar_wait(&bar_a2[slot], ph); tc_fence_after();
-      }
-      uint32_t acc3 = 0;
+        mma_commit_elect(&bar_d1);
+        mbar_wait(&bar_a2, ph); tc_fence_after();
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        if (p.has_back) {
+        for (int g = 0; g < 4; ++g) {   // W3 ReLU(c2): K = 64, N = 256 in four column groups, each committed on its own
+          uint32_t acc = 0;
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {   // W3 ReLU(c2), output channels 128 hf + 64 g .. +64: K = 64, N = 64
-            uint32_t acc = 0;
+          for (int part = 0; part < NPART; ++part) {
+            const uint32_t a0 = part == 1 ? COL_A2_LO : COL_A2_HI, w0 = (part == 2 ? w_lo : w_hi) + IMG_W3 + g * 64 * 128;
 #pragma unroll
-            for (int part = 0; part < NPART; ++part) {
-              const uint32_t a0 = cb + (part == 1 ? S_A2_LO : S_A2_HI), w0 = (part == 2 ? w_lo : w_hi) + IMG_W3 + (2 * hf + g) * 64 * 128;
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                mma_ts_elect(cb + S_D2H + 64 * g, a0 + 8 * ks, make_smem_desc_sw128(w0 + ks * 32), id64, acc);
-                acc = 1;
-              }
+            for (int ks = 0; ks < 4; ++ks) {
+              mma_ts_elect(COL_D2 + 64 * g, a0 + 8 * ks, make_smem_desc_sw128(w0 + ks * 32), id64, acc);
+              acc = 1;
             }
-            mma_commit_elect(&bar_d2[slot][2 * hf + g]);
           }
+          mma_commit_elect(&bar_d2[g]);
         }
-        if (p.has_front) {
+      }
+      if (p.has_front) {
+        uint32_t acc = 0;
 #pragma unroll
-          for (int c32 = 0; c32 < 4; ++c32) {   // W1' ReLU(h): channels 128 hf + 32 c32 .. +32 (two 16-channel k-steps), as they land
-            mbar_wait(&bar_a3[slot][4 * hf + c32], ph); tc_fence_after();
+        for (int cc = 0; cc < 8; ++cc) {   // W1' ReLU(h): K = 256 in eight 32-channel chunks, issued as the epilogue produces them
+          mbar_wait(&bar_a3[cc], ph); tc_fence_after();
+#pragma unroll
+          for (int part = 0; part < NPART; ++part) {
+            const uint32_t a0 = COL_D2 + 32 * cc + (part == 1 ? 16 : 0), w0 = (part == 2 ? w_lo : w_hi) + IMG_W1;
 #pragma unroll
             for (int k2 = 0; k2 < 2; ++k2) {
-              const int j = 2 * c32 + k2, ks = 8 * hf + j;         // 16-channel sub-chunk j: hi at 16 j, lo at 16 j + 8
-#pragma unroll
-              for (int part = 0; part < NPART; ++part) {
-                const uint32_t a0 = cb + S_D2H + 16 * j + (part == 1 ? 8 : 0), w0 = (part == 2 ? w_lo : w_hi) + IMG_W1;
-                mma_ts_elect(cb + S_D3, a0, make_smem_desc_sw128(w0 + (ks >> 2) * 64 * 128 + (ks & 3) * 32), id64, acc3);
-                acc3 = 1;
-              }
+              const int ks = 2 * cc + k2;
+              mma_ts_elect(COL_D3, a0 + 8 * k2, make_smem_desc_sw128(w0 + (ks >> 2) * 64 * 128 + (ks & 3) * 32), id64, acc);
+              acc = 1;
             }
           }
-        } else if (p.has_back && hf == 0) {
-          // no GEMM3 behind which to order: wait until the epilogue has drained half 0 before GEMM2 reuses its columns
-          mbar_wait(&bar_x[slot], ph); tc_fence_after();
         }
-        if (!p.has_back && p.has_front && hf == 0) {
-          // stage 0 has no GEMM2 whose commit would tell the epilogue that GEMM3 has finished reading half 0 of A3:
-          // commit explicitly before the epilogue may overwrite those columns with half 1
-          mma_commit_elect(&bar_d2[slot][2]);
-        }
+        mma_commit_elect(&bar_d3);
       }
-      if (p.has_front) mma_commit_elect(&bar_d3[slot]);
       ph ^= 1;
     }
   } else {
-    // ================= epilogue of one slot: thread (q, hb) owns half the columns of frame 32 q + lane =================
+    // ================= epilogue: warps (q, qd): TMEM lane quarter q = warp & 3, column quarter qd = warp >> 2 =================
     mbar_wait(&bar_w, 0);        // biases / column sums live in the weight image
-    const int q = warp & 3, hb = (warp >> 2) & 1, row = q * 32 + lane;
-    const uint32_t ta = ((uint32_t)(q * 32) << 16) + cb;       // TMEM address of (this lane quarter, slot column 0)
-    const int qbar = 2 + slot * 4 + q;
-    float2 (*rd)[2 * TILE] = red[slot];
+    const int qd = warp >> 2, row = (warp & 3) * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t ph = 0;
     // one arrival per warp: tcgen05.wait is warp-wide, so once it returns every lane's TMEM traffic is done
     auto warp_arrive = [&](uint64_t* bar) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar); };
-    uint32_t ph = 0;
-    const bool stamp = p.dbg != nullptr && (tid & 255) == 0;
+    const bool stamp = p.dbg != nullptr && tid == 0;
 #define DXI_STAMP(k) do { if (stamp) p.dbg[(size_t)tile * 16 + (k)] = clock64(); } while (0)
 
-    // c1 taps of a tile -> TMEM: this thread moves units 4hb .. 4hb+3 of every (tap, plane), one tap at a time
+    // c1 taps of a tile -> TMEM [320,512): this thread moves units 2qd, 2qd+1 of every (tap, plane)
     auto load_a1 = [&](int tile_) {
       const int b = tile_ / p.tiles_per_utt, t = (tile_ - b * p.tiles_per_utt) * TILE + row;
-      const __half* c1b = p.c1_in + (size_t)b * 2 * 8 * p.Ts * 8;
+      const __half* cb = p.c1_in + (size_t)b * 2 * 8 * p.Ts * 8;
+      uint4 qv[3][SPLIT ? 2 : 1][2];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         const int shift = j == 0 ? p.shift0 : (j == 1 ? p.shift1 : p.shift2);
         const size_t r_in = (size_t)(t - shift + C1_PAD);
-        uint4 qv[SPLIT ? 2 : 1][4];
 #pragma unroll
         for (int plane = 0; plane < (SPLIT ? 2 : 1); ++plane)
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            qv[plane][u] = (p.dbg_flags & 4) ? make_uint4(0, 0, 0, 0)
-                                             : __ldg(reinterpret_cast<const uint4*>(c1b + ((size_t)(plane * 8 + 4 * hb + u) * p.Ts + r_in) * 8));
+          for (int u = 0; u < 2; ++u)
+            qv[j][plane][u] = (p.dbg_flags & 4) ? make_uint4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uint4*>(cb + ((size_t)(plane * 8 + 2 * qd + u) * p.Ts + r_in) * 8));
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
 #pragma unroll
         for (int plane = 0; plane < (SPLIT ? 2 : 1); ++plane) {
-          uint32_t r[16];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) { r[4 * u] = qv[plane][u].x; r[4 * u + 1] = qv[plane][u].y; r[4 * u + 2] = qv[plane][u].z; r[4 * u + 3] = qv[plane][u].w; }
-          tmem_st16(ta + (plane ? S_A1_LO : S_A1_HI) + 32 * j + 16 * hb, r);
+          const uint32_t r[8] = {qv[j][plane][0].x, qv[j][plane][0].y, qv[j][plane][0].z, qv[j][plane][0].w,
+                                 qv[j][plane][1].x, qv[j][plane][1].y, qv[j][plane][1].z, qv[j][plane][1].w};
+          tmem_st8(lane_addr + (plane ? COL_A1_LO : COL_A1_HI) + 32 * j + 8 * qd, r);
         }
-      }
       tmem_wait_st(); tc_fence_before();
     };
 
-    if (p.has_back && tile0 < p.n_tiles) { load_a1(tile0); warp_arrive(&bar_a1[slot]); }
-    for (int tile = tile0; tile < p.n_tiles; tile += tstep) {
+    if (p.has_back && (int)blockIdx.x < p.n_tiles) { load_a1(blockIdx.x); warp_arrive(&bar_a1); }
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TILE;
       const int t = t0 + row;
       const bool valid = t < p.T;
@@ -283,29 +261,30 @@ __global__ void __launch_bounds__(S2_THREADS, 1) tcn_stage_kernel(const StageArg
       float mu2 = 0.0f, inv2 = 0.0f;
       if (p.has_back) {
         // ---- P1: r2 = ReLU(acc1 + b2) -> A2 at once (un-normalised); statistics merged while GEMM2 runs
-        mbar_wait(&bar_d1[slot], ph); tc_fence_after();
+        mbar_wait(&bar_d1, ph); tc_fence_after();
         DXI_STAMP(1);
-        float a[32];
-        tmem_ld32(ta + S_D1 + 32 * hb, a); tmem_wait_ld();
+        float a[16];
+        tmem_ld16(lane_addr + COL_D1 + 16 * qd, a); tmem_wait_ld();
         float s = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { a[j] = relu(a[j] + sAux[OFF_B2 + 32 * hb + j]); s += a[j]; }
+        for (int j = 0; j < 16; ++j) { a[j] = relu(a[j] + sAux[OFF_B2 + 16 * qd + j]); s += a[j]; }
         {
-          uint32_t hi[16], lo[16];
+          uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) to_h2<SPLIT>(a[2 * j], a[2 * j + 1], hi[j], lo[j]);
-          tmem_st16(ta + S_A2_HI + 16 * hb, hi);
-          if (SPLIT) tmem_st16(ta + S_A2_LO + 16 * hb, lo);
+          for (int j = 0; j < 8; ++j) to_h2<SPLIT>(a[2 * j], a[2 * j + 1], hi[j], lo[j]);
+          tmem_st8(lane_addr + COL_A2_HI + 8 * qd, hi);
+          if (SPLIT) tmem_st8(lane_addr + COL_A2_LO + 8 * qd, lo);
         }
-        tmem_wait_st(); warp_arrive(&bar_a2[slot]);
+        tmem_wait_st(); warp_arrive(&bar_a2);
         DXI_STAMP(2);
-        const float mean_i = s * (1.0f / 32.0f);
+        const float mean_i = s * (1.0f / 16.0f);
         float q2 = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { const float d = a[j] - mean_i; q2 = fmaf(d, d, q2); }
-        ln_merge2(rd[0], row, hb, qbar, 32.0f, mean_i, q2, mu2, inv2);
+        for (int j = 0; j < 16; ++j) { const float d = a[j] - mean_i; q2 = fmaf(d, d, q2); }
+        ln_merge(red[0], row, qd, 16.0f, mean_i, q2, mu2, inv2);
       }
       DXI_STAMP(3);
+      // ---- P2: h_new = h + b3 + inv2 (acc2 - mu2 colsum(W3)); r3 = ReLU(h_new) -> A3 in place, chunk by chunk
       float mean0 = 0.0f, inv0 = 0.0f;
       if (p.stem_stats) {     // merge the 8 partial statistics (32 channels each) the stem kernels left for this row
         const float2* sp = p.stem_stats + ((size_t)tile * TILE + row) * 8;
@@ -322,139 +301,120 @@ __global__ void __launch_bounds__(S2_THREADS, 1) tcn_stage_kernel(const StageArg
         mean0 = m;
         inv0 = rsqrtf(m2 * (1.0f / 256.0f) + 1e-6f);
       }
-      // ---- P2: h_new = h + b3 + inv2 (acc2 - mu2 colsum(W3)); r3 = ReLU(h_new) -> A3 in place.
-      //      This thread owns the 32-column chunks c32 = hb, hb + 2 of each 128-column half processed as two
-      //      16-channel sub-chunks (16 fp32 columns -> 8 hi + 8 lo in place).
-      float2 s1v = make_float2(0.0f, 0.0f), s2v = make_float2(0.0f, 0.0f);     // sums of r and r^2 over this thread's 128 channels
+      float2 s1v = make_float2(0.0f, 0.0f), s2v = make_float2(0.0f, 0.0f);     // sums of r and r^2 over this thread's 64 channels
       const float nim = -inv2 * mu2;
-      const float2 inv2v = make_float2(inv2, inv2), nimv = make_float2(nim, nim);
-#pragma unroll 1
-      for (int hf = 0; hf < 2; ++hf) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int c32 = hb + 2 * i;                                       // this thread's 32-channel chunk of the half
-          if (!p.has_back && hf == 1 && i == 0) { mbar_wait(&bar_d2[slot][2], ph); tc_fence_after(); }   // stage 0: see the MMA warp
-          if (p.has_back) {
-            mbar_wait(&bar_d2[slot][2 * hf + (c32 >> 1)], ph); tc_fence_after();
-            if (hf == 0 && i == 0) DXI_STAMP(4);
+      for (int i = 0; i < 2; ++i) {
+        const int cc = qd + 4 * i;
+        float4 hv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) hv[q] = (p.dbg_flags & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4));
+        float v[32];
+        if (p.has_back) {
+          mbar_wait(&bar_d2[cc >> 1], ph); tc_fence_after();
+          if (i == 0) DXI_STAMP(4);
+          tmem_ld32(lane_addr + COL_D2 + 32 * cc, v); tmem_wait_ld();
+          // packed fp32x2 arithmetic (FADD2 / FFMA2): v = inv2 * acc + (nim * colsum + (h + b3))
+          const float4* b3 = reinterpret_cast<const float4*>(sAux + OFF_B3 + 32 * cc);
+          const float4* cs = reinterpret_cast<const float4*>(sAux + OFF_CS3 + 32 * cc);
+          const float2 inv2v = make_float2(inv2, inv2), nimv = make_float2(nim, nim);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bq = b3[q], cq = cs[q];
+            float2 t0 = __fadd2_rn(make_float2(hv[q].x, hv[q].y), make_float2(bq.x, bq.y));
+            float2 t1 = __fadd2_rn(make_float2(hv[q].z, hv[q].w), make_float2(bq.z, bq.w));
+            t0 = __ffma2_rn(nimv, make_float2(cq.x, cq.y), t0);
+            t1 = __ffma2_rn(nimv, make_float2(cq.z, cq.w), t1);
+            t0 = __ffma2_rn(inv2v, make_float2(v[4 * q], v[4 * q + 1]), t0);
+            t1 = __ffma2_rn(inv2v, make_float2(v[4 * q + 2], v[4 * q + 3]), t1);
+            v[4 * q] = t0.x; v[4 * q + 1] = t0.y; v[4 * q + 2] = t1.x; v[4 * q + 3] = t1.y;
           }
+        } else if (p.stem_stats) {
+          // stage 0: the loaded row is the stem pre-activation z; h0 = ReLU(z * inv0 * gamma - mean0 * inv0 * gamma)
+          const float* gm = sAux + OFF_B3 + 32 * cc;
 #pragma unroll
-          for (int sub = 0; sub < 2; ++sub) {                               // two 16-channel sub-chunks: registers stay small
-            const int j = 2 * c32 + sub, c0 = 128 * hf + 16 * j;            // channels c0 .. c0+15, TMEM columns S_D2H + 16 j
-            float4 hv[4];
-#pragma unroll
-            for (int qq = 0; qq < 4; ++qq)
-              hv[qq] = (p.dbg_flags & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(hrow + (size_t)(c0 / 4 + qq) * (TILE * 4));
-            float v[16];
-            if (p.has_back) {
-              tmem_ld16(ta + S_D2H + 16 * j, v); tmem_wait_ld();
-              const float4* b3 = reinterpret_cast<const float4*>(sAux + OFF_B3 + c0);
-              const float4* cs = reinterpret_cast<const float4*>(sAux + OFF_CS3 + c0);
-#pragma unroll
-              for (int qq = 0; qq < 4; ++qq) {
-                const float4 bq = b3[qq], cq = cs[qq];
-                float2 t0v = __fadd2_rn(make_float2(hv[qq].x, hv[qq].y), make_float2(bq.x, bq.y));
-                float2 t1v = __fadd2_rn(make_float2(hv[qq].z, hv[qq].w), make_float2(bq.z, bq.w));
-                t0v = __ffma2_rn(nimv, make_float2(cq.x, cq.y), t0v);
-                t1v = __ffma2_rn(nimv, make_float2(cq.z, cq.w), t1v);
-                t0v = __ffma2_rn(inv2v, make_float2(v[4 * qq], v[4 * qq + 1]), t0v);
-                t1v = __ffma2_rn(inv2v, make_float2(v[4 * qq + 2], v[4 * qq + 3]), t1v);
-                v[4 * qq] = t0v.x; v[4 * qq + 1] = t0v.y; v[4 * qq + 2] = t1v.x; v[4 * qq + 3] = t1v.y;
-              }
-            } else if (p.stem_stats) {
-              // stage 0: the loaded row is the stem pre-activation z; h0 = ReLU(z * inv0 * gamma - mean0 * inv0 * gamma)
-              const float* gm = sAux + OFF_B3 + c0;
-#pragma unroll
-              for (int qq = 0; qq < 4; ++qq) {
-                const float g0 = inv0 * gm[4 * qq], g1 = inv0 * gm[4 * qq + 1], g2 = inv0 * gm[4 * qq + 2], g3 = inv0 * gm[4 * qq + 3];
-                v[4 * qq]     = relu(fmaf(hv[qq].x, g0, -mean0 * g0));
-                v[4 * qq + 1] = relu(fmaf(hv[qq].y, g1, -mean0 * g1));
-                v[4 * qq + 2] = relu(fmaf(hv[qq].z, g2, -mean0 * g2));
-                v[4 * qq + 3] = relu(fmaf(hv[qq].w, g3, -mean0 * g3));
-              }
-            } else {
-#pragma unroll
-              for (int qq = 0; qq < 4; ++qq) { v[4 * qq] = hv[qq].x; v[4 * qq + 1] = hv[qq].y; v[4 * qq + 2] = hv[qq].z; v[4 * qq + 3] = hv[qq].w; }
-            }
-            if (!valid) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] = 0.0f;
-            }
-            if ((p.has_back || p.stem_stats) && !(p.dbg_flags & 2)) {
-#pragma unroll
-              for (int qq = 0; qq < 4; ++qq)
-                *reinterpret_cast<float4*>(hrow + (size_t)(c0 / 4 + qq) * (TILE * 4)) = make_float4(v[4 * qq], v[4 * qq + 1], v[4 * qq + 2], v[4 * qq + 3]);
-            }
-            if (p.has_front) {
-              uint32_t hi[8], lo[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float2 r = make_float2(relu(v[2 * e]), relu(v[2 * e + 1]));
-                s1v = __fadd2_rn(s1v, r);
-                s2v = __ffma2_rn(r, r, s2v);
-                to_h2<SPLIT>(r.x, r.y, hi[e], lo[e]);
-              }
-              tmem_st8(ta + S_D2H + 16 * j, hi);
-              if (SPLIT) tmem_st8(ta + S_D2H + 16 * j + 8, lo);
-            }
+          for (int q = 0; q < 8; ++q) {
+            const float g0 = inv0 * gm[4 * q], g1 = inv0 * gm[4 * q + 1], g2 = inv0 * gm[4 * q + 2], g3 = inv0 * gm[4 * q + 3];
+            v[4 * q]     = relu(fmaf(hv[q].x, g0, -mean0 * g0));
+            v[4 * q + 1] = relu(fmaf(hv[q].y, g1, -mean0 * g1));
+            v[4 * q + 2] = relu(fmaf(hv[q].z, g2, -mean0 * g2));
+            v[4 * q + 3] = relu(fmaf(hv[q].w, g3, -mean0 * g3));
           }
-          if (p.has_front) {
-            tmem_wait_st(); warp_arrive(&bar_a3[slot][4 * hf + c32]);
-          } else if (p.has_back && hf == 0 && i == 1) {
-            warp_arrive(&bar_x[slot]);      // last stage: tells the MMA warp that half 0 of the accumulators is drained
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { v[4 * q] = hv[q].x; v[4 * q + 1] = hv[q].y; v[4 * q + 2] = hv[q].z; v[4 * q + 3] = hv[q].w; }
+        }
+        if (!valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+        }
+        if ((p.has_back || p.stem_stats) && !(p.dbg_flags & 2)) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        if (p.has_front) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 r = make_float2(relu(v[2 * j]), relu(v[2 * j + 1]));
+            s1v = __fadd2_rn(s1v, r);
+            s2v = __ffma2_rn(r, r, s2v);
+            to_h2<SPLIT>(r.x, r.y, hi[j], lo[j]);
           }
+          tmem_st16(lane_addr + COL_D2 + 32 * cc, hi);
+          if (SPLIT) tmem_st16(lane_addr + COL_D2 + 32 * cc + 16, lo);
+          tmem_wait_st(); warp_arrive(&bar_a3[cc]);
         }
       }
       DXI_STAMP(5);
       float mu3 = 0.0f, inv3 = 0.0f;
       if (p.has_front) {
-        const float s1 = s1v.x + s1v.y, s2 = s2v.x + s2v.y, m1 = s1 * (1.0f / 128.0f);
-        ln_merge2(rd[1], row, hb, qbar, 128.0f, m1, fmaxf(s2 - s1 * m1, 0.0f), mu3, inv3);
+        const float s1 = s1v.x + s1v.y, s2 = s2v.x + s2v.y, m1 = s1 * (1.0f / 64.0f);
+        ln_merge(red[1], row, qd, 64.0f, m1, fmaxf(s2 - s1 * m1, 0.0f), mu3, inv3);
       }
       DXI_STAMP(6);
-      const int next = tile + tstep;
+      // ---- the next tile's c1 taps travel to TMEM while this tile's GEMM3 drains
+      const int next = tile + gridDim.x;
       const bool has_next = p.has_back && next < p.n_tiles;
+      if (has_next) load_a1(next);
+      DXI_STAMP(7);
       if (p.has_front) {
         // ---- P3: c1' = LN(ReLU(inv3 (acc3 - mu3 colsum(W1')) + b1')) -> fp16 hi | lo planes in HBM (zeros beyond T)
-        mbar_wait(&bar_d3[slot], ph); tc_fence_after();
-        DXI_STAMP(7);
-        // GEMM3 is done: columns [0,192) of the slot are dead and the next tile's taps may land there (before D3 is
-        // pulled into registers, to keep register pressure low); GEMM1 of the next tile may start once D3 is read too
-        if (has_next) load_a1(next);
-        float a[32];
-        tmem_ld32(ta + S_D3 + 32 * hb, a); tmem_wait_ld();
-        if (has_next) warp_arrive(&bar_a1[slot]);
+        mbar_wait(&bar_d3, ph); tc_fence_after();
         DXI_STAMP(8);
+        float a[16];
+        tmem_ld16(lane_addr + COL_D3 + 16 * qd, a); tmem_wait_ld();
+        if (has_next) warp_arrive(&bar_a1);      // every D3 read is done: GEMM1 / A2 of the next tile may reuse the columns
         const float nim3 = -inv3 * mu3;
         float s = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          a[j] = relu(fmaf(inv3, a[j], fmaf(nim3, sAux[OFF_CS1 + 32 * hb + j], sAux[OFF_B1 + 32 * hb + j])));
+        for (int j = 0; j < 16; ++j) {
+          a[j] = relu(fmaf(inv3, a[j], fmaf(nim3, sAux[OFF_CS1 + 16 * qd + j], sAux[OFF_B1 + 16 * qd + j])));
           s += a[j];
         }
-        const float mean_i = s * (1.0f / 32.0f);
+        const float mean_i = s * (1.0f / 16.0f);
         float q2 = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { const float d = a[j] - mean_i; q2 = fmaf(d, d, q2); }
+        for (int j = 0; j < 16; ++j) { const float d = a[j] - mean_i; q2 = fmaf(d, d, q2); }
         float mean, inv;
-        ln_merge2(rd[2], row, hb, qbar, 32.0f, mean_i, q2, mean, inv);
+        ln_merge(red[2], row, qd, 16.0f, mean_i, q2, mean, inv);
         const float off = -mean * inv;
         __half* ob = p.c1_out + (size_t)b * 2 * 8 * p.Ts * 8;
         const size_t r_out = (size_t)(t + C1_PAD);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 2; ++u) {
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float x0 = valid ? fmaf(a[8 * u + 2 * j], inv, off) : 0.0f, x1 = valid ? fmaf(a[8 * u + 2 * j + 1], inv, off) : 0.0f;
             to_h2<SPLIT>(x0, x1, hi[j], lo[j]);
           }
-          *reinterpret_cast<uint4*>(ob + ((size_t)(4 * hb + u) * p.Ts + r_out) * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (SPLIT) *reinterpret_cast<uint4*>(ob + ((size_t)(8 + 4 * hb + u) * p.Ts + r_out) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(ob + ((size_t)(2 * qd + u) * p.Ts + r_out) * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (SPLIT) *reinterpret_cast<uint4*>(ob + ((size_t)(8 + 2 * qd + u) * p.Ts + r_out) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
       } else if (has_next) {
-        // last stage: the GEMM2 accumulators of half 1 were read by P2 above; taps of the next tile may land
-        load_a1(next); warp_arrive(&bar_a1[slot]);
+        warp_arrive(&bar_a1);
       }
       DXI_STAMP(9);
       ph ^= 1;
@@ -463,7 +423,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) tcn_stage_kernel(const StageArg
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == S2_EPI_WARPS) tmem_dealloc(0, 512);
+  if (warp == EPI_WARPS) tmem_dealloc(0, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -882,10 +842,8 @@ int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, floa
     const int d = s >= 1 ? 1 << ((s - 1) % nd) : 1;
     if (c.padding == DXI_PAD_CAUSAL) { a.shift0 = 2 * d; a.shift1 = d; a.shift2 = 0; }       // tap j reads t-(2-j)d
     else                             { a.shift0 = d;     a.shift1 = 0; a.shift2 = -d; }      // tap j reads t+(j-1)d
-    // two tiles in flight per CTA: the persistent grid needs at most ceil(n_tiles / 2) CTAs
-    const int grid2 = (n_tiles + 1) / 2 < n_sm ? (n_tiles + 1) / 2 : n_sm;
-    if (split) tcn_stage_kernel<true><<<grid2, S2_THREADS, smem, st>>>(a);
-    else       tcn_stage_kernel<false><<<grid2, S2_THREADS, smem, st>>>(a);
+    if (split) tcn_stage_kernel<true><<<grid, STAGE_THREADS, smem, st>>>(a);
+    else       tcn_stage_kernel<false><<<grid, STAGE_THREADS, smem, st>>>(a);
     DXI_LAUNCHED("tcn_stage_kernel");
   }
   }

@@ -19,11 +19,11 @@ net(x); torch.cuda.synchronize()
 lib.dxi_debug_tcn_clocks(None, -1)
 c = buf.cpu().numpy().reshape(n_tiles, 16)[:, :10]
 d = np.diff(c, axis=1)
-names = ['wait GEMM1', 'P1 (A2)', 'merge2', 'wait GEMM2 g0', 'P2 (h, A3)', 'merge3', 'wait GEMM3', 'A1 next', 'P3 (c1 out)']
+names = ['wait GEMM1', 'P1 (A2)', 'merge2', 'wait GEMM2 g0', 'P2 (h, A3)', 'merge3', 'A1 next', 'wait GEMM3', 'P3 (c1 out)']
 print('flags', flags, 'tiles', n_tiles, 'stage', stage, ' total per tile: median %.0f cycles' % np.median(c[:, 9] - c[:, 0]))
 for i, n in enumerate(names):
     print('%-16s median %7.0f  mean %7.0f  p90 %7.0f' % (n, np.median(d[:, i]), d[:, i].mean(), np.percentile(d[:, i], 90)))
 # gap between consecutive tiles of the same CTA
-g = 296
+g = 148
 gaps = [c[t + g, 0] - c[t, 9] for t in range(0, n_tiles - g)]
 print('inter-tile gap median %.0f' % np.median(gaps))
