@@ -130,6 +130,10 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
   // The CTA owns the SM's whole tensor memory (512 columns, one CTA per SM), so the allocation starts at
   // lane 0 / column 0: TMEM addresses below are compile-time constants.
   if (tmem_slot != 0) __trap();
+  // Programmatic dependent launch: the next stage's CTAs may be scheduled as SMs drain (their prologue -- barrier
+  // init, TMEM allocation, weight load -- overlaps this launch's tail); nothing written by the PREVIOUS launch is
+  // touched before griddepcontrol.wait below.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == EPI_WARPS) {
     // ================= weight load, L2 prefetch of the next tile, MMA issue =================
@@ -147,8 +151,9 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
     constexpr uint32_t id64 = make_idesc_f16(TILE, 64);
     constexpr int NPART = SPLIT ? 3 : 1;          // (a_hi, w_hi) [+ (a_lo, w_hi) + (a_hi, w_lo)]
     uint32_t ph = 0;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      {   // pull the tile after next's residual rows / next tile's rows into L2 ahead of their use
+      {   // pull the next tile's residual rows / c1 rows into L2 ahead of their use
         const int nt = tile + gridDim.x;
         if (nt < p.n_tiles) {
           const char* hn = reinterpret_cast<const char*>(p.h + (size_t)nt * (TILE * 256));
@@ -251,6 +256,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
       tmem_wait_st(); tc_fence_before();
     };
 
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // the previous launch's h / c1 are complete and visible
     if (p.has_back && (int)blockIdx.x < p.n_tiles) { load_a1(blockIdx.x); warp_arrive(&bar_a1); }
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TILE;
@@ -312,8 +318,9 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
         float v[32];
         if (p.has_back) {
           mbar_wait(&bar_d2[cc >> 1], ph); tc_fence_after();
-          if (i == 0) DXI_STAMP(4);
+          if (i == 0) DXI_STAMP(4); else DXI_STAMP(13);
           tmem_ld32(lane_addr + COL_D2 + 32 * cc, v); tmem_wait_ld();
+          if (i == 0) DXI_STAMP(10); else DXI_STAMP(14);
           // packed fp32x2 arithmetic (FADD2 / FFMA2): v = inv2 * acc + (nim * colsum + (h + b3))
           const float4* b3 = reinterpret_cast<const float4*>(sAux + OFF_B3 + 32 * cc);
           const float4* cs = reinterpret_cast<const float4*>(sAux + OFF_CS3 + 32 * cc);
@@ -353,6 +360,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
+        if (i == 0) DXI_STAMP(11);
         if (p.has_front) {
           uint32_t hi[16], lo[16];
 #pragma unroll
@@ -366,6 +374,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
           if (SPLIT) tmem_st16(lane_addr + COL_D2 + 32 * cc + 16, lo);
           tmem_wait_st(); warp_arrive(&bar_a3[cc]);
         }
+        if (i == 0) DXI_STAMP(12);
       }
       DXI_STAMP(5);
       float mu3 = 0.0f, inv3 = 0.0f;
@@ -470,6 +479,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) stem_umma_kernel(const StemA
   __syncthreads();
   tc_fence_after();
   if (tmem_slot != 0) __trap();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == EPI_WARPS) {
     if (elect_one()) {
       mbar_arrive_expect_tx(&bar_w, STEM_IMG_BYTES);
@@ -480,6 +490,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) stem_umma_kernel(const StemA
     }
     __syncwarp();
     mbar_wait(&bar_w, 0);
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // everything the previous launch wrote is visible
     const uint32_t w_hi = smem_u32(sW), w_lo = w_hi + STEM_PART;
     constexpr uint32_t id128 = make_idesc_f16(TILE, 128);
     uint32_t ph = 0;
@@ -500,6 +511,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) stem_umma_kernel(const StemA
     }
   } else {
     mbar_wait(&bar_w, 0);
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // everything the previous launch wrote is visible
     const int qd = warp >> 2, row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ph = 0;
@@ -586,6 +598,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) head_umma_kernel(const HeadA
   __syncthreads();
   tc_fence_after();
   if (tmem_slot != 0) __trap();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == EPI_WARPS) {
     if (elect_one()) {
       mbar_arrive_expect_tx(&bar_w, HEAD_IMG_BYTES);
@@ -596,6 +609,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) head_umma_kernel(const HeadA
     }
     __syncwarp();
     mbar_wait(&bar_w, 0);
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // everything the previous launch wrote is visible
     const uint32_t w_hi = smem_u32(sW);
     constexpr uint32_t id128 = make_idesc_f16(TILE, 128);
     uint32_t ph = 0;
@@ -624,6 +638,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) head_umma_kernel(const HeadA
     }
   } else {
     mbar_wait(&bar_w, 0);
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // everything the previous launch wrote is visible
     const int qd = warp >> 2, row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ph = 0;
@@ -708,6 +723,23 @@ static void pack_b_sw128(unsigned char* hi, unsigned char* lo, int N, int K, con
 }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Launch with programmatic stream serialization: the kernel may be scheduled while its predecessor in the stream
+// drains; it calls griddepcontrol.wait before touching anything the predecessor wrote.
+template <typename Args>
+static cudaError_t launch_pdl(void (*kern)(const Args), int grid, int block, size_t smem, cudaStream_t st, const Args& a) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, a);
+}
 
 static int n_dilations(int max_d_rate) { int n = 0; for (int m = max_d_rate; m > 0; m >>= 1) ++n; return n; }
 
@@ -815,7 +847,7 @@ int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, floa
     ProfScope prof("tcn_stem", st, 2);
     for (int half = 0; half < 2; ++half) {
       StemArgs a{images + net.umma_stage_offset[half], mag, h, stem_stats, T, tiles, n_tiles, half, c.n_feat};
-      stem_umma_kernel<<<grid, STAGE_THREADS, smem_stem, st>>>(a);
+      DXI_CUDA(launch_pdl(stem_umma_kernel, grid, STAGE_THREADS, smem_stem, st, a));
       DXI_LAUNCHED("stem_umma_kernel");
     }
   }
@@ -842,8 +874,8 @@ int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, floa
     const int d = s >= 1 ? 1 << ((s - 1) % nd) : 1;
     if (c.padding == DXI_PAD_CAUSAL) { a.shift0 = 2 * d; a.shift1 = d; a.shift2 = 0; }       // tap j reads t-(2-j)d
     else                             { a.shift0 = d;     a.shift1 = 0; a.shift2 = -d; }      // tap j reads t+(j-1)d
-    if (split) tcn_stage_kernel<true><<<grid, STAGE_THREADS, smem, st>>>(a);
-    else       tcn_stage_kernel<false><<<grid, STAGE_THREADS, smem, st>>>(a);
+    if (split) DXI_CUDA(launch_pdl(tcn_stage_kernel<true>, grid, STAGE_THREADS, smem, st, a));
+    else       DXI_CUDA(launch_pdl(tcn_stage_kernel<false>, grid, STAGE_THREADS, smem, st, a));
     DXI_LAUNCHED("tcn_stage_kernel");
   }
   }
@@ -853,7 +885,7 @@ int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, floa
     DXI_CUDA(cudaFuncSetAttribute(head_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head));
     HeadArgs a{images + net.umma_stage_offset[2], h, xbar, T, tiles, n_tiles, c.n_outp};
     ProfScope prof("tcn_head", st, 1);
-    head_umma_kernel<<<grid, STAGE_THREADS, smem_head, st>>>(a);
+    DXI_CUDA(launch_pdl(head_umma_kernel, grid, STAGE_THREADS, smem_head, st, a));
     DXI_LAUNCHED("head_umma_kernel");
   }
   return DXI_OK;

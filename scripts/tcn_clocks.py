@@ -17,7 +17,8 @@ lib = _lib.load()
 lib.dxi_debug_tcn_clocks(_lib.ptr(buf), stage | (flags << 8))
 net(x); torch.cuda.synchronize()
 lib.dxi_debug_tcn_clocks(None, -1)
-c = buf.cpu().numpy().reshape(n_tiles, 16)[:, :10]
+call = buf.cpu().numpy().reshape(n_tiles, 16)
+c = call[:, :10]
 d = np.diff(c, axis=1)
 names = ['wait GEMM1', 'P1 (A2)', 'merge2', 'wait GEMM2 g0', 'P2 (h, A3)', 'merge3', 'A1 next', 'wait GEMM3', 'P3 (c1 out)']
 print('flags', flags, 'tiles', n_tiles, 'stage', stage, ' total per tile: median %.0f cycles' % np.median(c[:, 9] - c[:, 0]))
@@ -27,3 +28,21 @@ for i, n in enumerate(names):
 g = 148
 gaps = [c[t + g, 0] - c[t, 9] for t in range(0, n_tiles - g)]
 print('inter-tile gap median %.0f' % np.median(gaps))
+
+# finer stamps inside P2 (thread 0: chunks cc = 0 then 4): 3 -> [h loads issued, wait d2] 4 -> [tmem ld] 10 -> [math, STG] 11
+# -> [split, tmem st, arrive] 12 -> [h loads, wait d2] 13 -> [tmem ld] 14 -> [rest of chunk 1] 5
+seq = [3, 4, 10, 11, 12, 13, 14, 5]
+lab = ['i0 ldg issue + wait d2', 'i0 tmem ld', 'i0 math + STG', 'i0 split + tmem st + arrive', 'i1 ldg issue + wait d2', 'i1 tmem ld', 'i1 math..arrive']
+for k in range(len(seq) - 1):
+    dd = call[:, seq[k + 1]] - call[:, seq[k]]
+    print('  P2 %-28s median %7.0f  mean %7.0f  p90 %7.0f' % (lab[k], np.median(dd), dd.mean(), np.percentile(dd, 90)))
+# per-CTA busy span (first stamp of its first tile -> last stamp of its last tile; one SM clock) and per-round tile time
+spans = []
+for cta in range(min(g, n_tiles)):
+    ts = list(range(cta, n_tiles, g))
+    spans.append(c[ts[-1], 9] - c[ts[0], 0])
+spans = np.array(spans)
+print('per-CTA busy span: median %.0f  max %.0f  min %.0f cycles (%.1f us at 1.965 GHz max)' % (np.median(spans), spans.max(), spans.min(), spans.max() / 1965.0))
+for r in range((n_tiles + g - 1) // g):
+    ts = np.arange(r * g, min((r + 1) * g, n_tiles))
+    print('  round %d: tiles %4d  median tile %6.0f  mean %6.0f' % (r, len(ts), np.median(c[ts, 9] - c[ts, 0]), (c[ts, 9] - c[ts, 0]).mean()))
