@@ -24,9 +24,15 @@ names = ['wait GEMM1', 'P1 (A2)', 'merge2', 'wait GEMM2 g0', 'P2 (h, A3)', 'merg
 print('flags', flags, 'tiles', n_tiles, 'stage', stage, ' total per tile: median %.0f cycles' % np.median(c[:, 9] - c[:, 0]))
 for i, n in enumerate(names):
     print('%-16s median %7.0f  mean %7.0f  p90 %7.0f' % (n, np.median(d[:, i]), d[:, i].mean(), np.percentile(d[:, i], 90)))
-# gap between consecutive tiles of the same CTA
+# tile ownership: chained kernel -> CTA c owns tiles [c m, (c+1) m); per-stage launches -> c, c + 148, ...
+chain = os.environ.get('DXI_TCN_CHAIN', '1') != '0'
 g = 148
-gaps = [c[t + g, 0] - c[t, 9] for t in range(0, n_tiles - g)]
+if chain:
+    m = -(-n_tiles // g)
+    owned = [list(range(cta * m, min((cta + 1) * m, n_tiles))) for cta in range(-(-n_tiles // m))]
+else:
+    owned = [list(range(cta, n_tiles, g)) for cta in range(min(g, n_tiles))]
+gaps = [c[ts[i + 1], 0] - c[ts[i], 9] for ts in owned for i in range(len(ts) - 1)]
 print('inter-tile gap median %.0f' % np.median(gaps))
 
 # finer stamps inside P2 (thread 0: chunks cc = 0 then 4): 3 -> [h loads issued, wait d2] 4 -> [tmem ld] 10 -> [math, STG] 11
@@ -37,12 +43,8 @@ for k in range(len(seq) - 1):
     dd = call[:, seq[k + 1]] - call[:, seq[k]]
     print('  P2 %-28s median %7.0f  mean %7.0f  p90 %7.0f' % (lab[k], np.median(dd), dd.mean(), np.percentile(dd, 90)))
 # per-CTA busy span (first stamp of its first tile -> last stamp of its last tile; one SM clock) and per-round tile time
-spans = []
-for cta in range(min(g, n_tiles)):
-    ts = list(range(cta, n_tiles, g))
-    spans.append(c[ts[-1], 9] - c[ts[0], 0])
-spans = np.array(spans)
+spans = np.array([c[ts[-1], 9] - c[ts[0], 0] for ts in owned])
 print('per-CTA busy span: median %.0f  max %.0f  min %.0f cycles (%.1f us at 1.965 GHz max)' % (np.median(spans), spans.max(), spans.min(), spans.max() / 1965.0))
-for r in range((n_tiles + g - 1) // g):
-    ts = np.arange(r * g, min((r + 1) * g, n_tiles))
+for r in range(max(len(ts) for ts in owned)):
+    ts = np.array([o[r] for o in owned if len(o) > r])
     print('  round %d: tiles %4d  median tile %6.0f  mean %6.0f' % (r, len(ts), np.median(c[ts, 9] - c[ts, 0]), (c[ts, 9] - c[ts, 0]).mean()))
