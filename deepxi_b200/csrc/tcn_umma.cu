@@ -29,7 +29,6 @@
 // LayerNorm statistics merged with Chan's formula through shared memory).  Warp 16: weight load (bulk async
 // copy), L2 prefetch of the next tile, warp-convergent MMA issue.  GEMM2 is committed in four column groups and
 // GEMM3 is issued in eight K-chunks as the epilogue produces them.
-#include <cstdlib>
 #include <vector>
 #include "net.cuh"
 #include "umma.cuh"
@@ -55,21 +54,17 @@ constexpr uint32_t COL_D3 = 256;                          // 64 fp32 (A2 is dead
 constexpr uint32_t COL_A1_HI = 320, COL_A1_LO = 416;      // 3 taps x 32 columns each
 
 struct StageArgs {
-  const unsigned char* img;      // packed weights of stage 0; stage s lives at img + s * IMG_BYTES
+  const unsigned char* img;      // packed weights of this stage
   float* h;                      // residual stream, tiled: [tile][c/4][row][4] fp32
-  __half* c1[2];                 // [B][2 planes][8 units][Ts][8] fp16 (hi plane, lo plane); stage s reads c1[(s+1)&1], writes c1[s&1]
+  const __half* c1_in;           // [B][2 planes][8 units][Ts][8] fp16 (hi plane, lo plane)
+  __half* c1_out;
   int T, tiles_per_utt, n_tiles, Ts;
-  int s_begin, s_end;            // stages [s_begin, s_end) run inside this launch
-  int n_blocks, nd, causal;      // stage 0 has no back half, stage n_blocks no front half; dilation of stage s >= 1 is 2^((s-1) % nd)
-  int chain_m;                   // 0: CTA c owns tiles c, c + grid, ... (one stage per launch)
-                                 // m > 0 ("chain"): CTA c owns tiles [c m, (c+1) m) through every stage of the launch; the grid must be
-                                 // co-resident (cooperative launch) because CTAs wait for their neighbours' tiles through `flags`
-  int* flags;                    // chain mode: flags[tile] = number of front halves of the tile that are published (zeroed by the host)
-  const float2* stem_stats;      // stage 0: per-row partial statistics of the stem pre-activation (8 parts of 32 channels);
-                                 // the row is then LayerNorm(gamma) + ReLU'd on load (tcn.py:176-179), gamma in the b3 slot
-  int dbg_flags;                 // tuning experiments only: 1 = skip residual loads, 2 = skip residual stores, 4 = skip c1 tap loads
-  int dbg_stage;                 // stage whose epilogue writes clock stamps
-  long long* dbg;                // optional: clock64 stamps of the epilogue phases (16 per tile), see dxi_debug_tcn_clocks
+  int shift0, shift1, shift2;    // frame offsets of the three taps: tap j reads frame t - shift_j
+  int has_back, has_front;
+  const float2* stem_stats;     // stage 0 only: per-row partial statistics of the stem pre-activation (8 parts of 32 channels);
+                                // the row is then LayerNorm(gamma) + ReLU'd on load (tcn.py:176-179), gamma in the b3 slot
+  int dbg_flags;                // tuning experiments only: 1 = skip residual loads, 2 = skip residual stores, 4 = skip c1 tap loads
+  long long* dbg;               // optional: clock64 stamps of the epilogue phases (16 per tile), see dxi_debug_tcn_clocks
 };
 
 __device__ __forceinline__ float relu(float x) { return fmaxf(x, 0.0f); }
@@ -78,7 +73,6 @@ constexpr int NSPLIT = 4;                         // threads per frame
 constexpr int EPI_WARPS = 4 * NSPLIT;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int STAGE_THREADS = EPI_THREADS + 32;   // + 1 warp: weight load, L2 prefetch, MMA issue
-constexpr int STAGE_SMEM = 1024 + IMG_BIAS + 2 * N_AUX * 4;      // weights (1024-aligned) + double-buffered biases / column sums
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 // The NSPLIT threads that share a frame sit in the NSPLIT warps with the same lane quarter q = warp & 3: statistics
@@ -86,14 +80,6 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" :
 __device__ __forceinline__ void quarter_barrier(int q) { asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(NSPLIT * 32) : "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
-  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // LayerNorm statistics of one row split between NSPLIT threads (n values each): every thread contributes
@@ -116,15 +102,14 @@ __device__ __forceinline__ void ln_merge(float2* red, int row, int qd, float n, 
   inv = rsqrtf(m2 / (n * NSPLIT) + 1e-6f);
 }
 
-// Both roles walk the same sequence of (stage, tile) pairs: for s in [s_begin, s_end): for k in [0, n_k): tile = first + k * stride.
 template <bool SPLIT>
 __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const StageArgs p) {
   extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, bar_a1, bar_a2, bar_a3[8], bar_d1, bar_d2[4], bar_d3, bar_pub, bar_dep;
+  __shared__ __align__(8) uint64_t bar_w, bar_a1, bar_a2, bar_a3[8], bar_d1, bar_d2[4], bar_d3;
   __shared__ uint32_t tmem_slot;
   __shared__ float2 red[3][NSPLIT * TILE];
   unsigned char* sW = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* sAuxBuf = reinterpret_cast<float*>(sW + IMG_BIAS);       // [2][N_AUX], indexed by stage parity
+  const float* sAux = reinterpret_cast<const float*>(sW + IMG_BIAS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == EPI_WARPS) tmem_alloc(&tmem_slot, 512);
@@ -137,8 +122,6 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
     mbar_init(&bar_d1, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&bar_d2[i], 1);
     mbar_init(&bar_d3, 1);
-    mbar_init(&bar_pub, EPI_WARPS);      // chain mode: a tile's c1 rows are written (epilogue -> MMA warp, which publishes them)
-    mbar_init(&bar_dep, 1);              // chain mode: the tiles the next c1 tap load depends on are published (MMA warp -> epilogue)
     fence_mbar_init();
   }
   tc_fence_before();
@@ -147,88 +130,46 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
   // The CTA owns the SM's whole tensor memory (512 columns, one CTA per SM), so the allocation starts at
   // lane 0 / column 0: TMEM addresses below are compile-time constants.
   if (tmem_slot != 0) __trap();
-  // Programmatic dependent launch: the next launch's CTAs may be scheduled as SMs drain (their prologue -- barrier
+  // Programmatic dependent launch: the next stage's CTAs may be scheduled as SMs drain (their prologue -- barrier
   // init, TMEM allocation, weight load -- overlaps this launch's tail); nothing written by the PREVIOUS launch is
   // touched before griddepcontrol.wait below.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  const int first = p.chain_m ? (int)blockIdx.x * p.chain_m : (int)blockIdx.x;
-  const int stride = p.chain_m ? 1 : (int)gridDim.x;
-  int n_k = p.chain_m ? min(p.chain_m, p.n_tiles - first) : (p.n_tiles - first + stride - 1) / stride;
-  if (n_k < 0) n_k = 0;
-  const int n_it = (p.s_end - p.s_begin) * n_k;
-
   if (warp == EPI_WARPS) {
     // ================= weight load, L2 prefetch of the next tile, MMA issue =================
     // The whole warp runs this code convergently; single-thread operations elect a lane inside the asm.
-    auto load_weights = [&](int s) {
-      if (elect_one()) {
-        const unsigned char* src = p.img + (size_t)s * IMG_BYTES;
-        mbar_arrive_expect_tx(&bar_w, IMG_BYTES);
-        for (int off = 0; off < IMG_BIAS; off += 16384) bulk_g2s(sW + off, src + off, 16384, &bar_w);
-        bulk_g2s(sAuxBuf + (s & 1) * N_AUX, src + IMG_BIAS, N_AUX * 4, &bar_w);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&bar_w, IMG_BYTES);
+      for (int off = 0; off < IMG_BYTES; off += 16384) {
+        const int n = IMG_BYTES - off < 16384 ? IMG_BYTES - off : 16384;
+        bulk_g2s(sW + off, p.img + off, n, &bar_w);
       }
-      __syncwarp();
-    };
-    static_assert(IMG_BIAS % 16384 == 0, "weight image is copied in 16 KB pieces");
-    if (n_it > 0) load_weights(p.s_begin);
+    }
+    __syncwarp();
+    mbar_wait(&bar_w, 0);
     const uint32_t w_hi = smem_u32(sW), w_lo = w_hi + IMG_PART;
     constexpr uint32_t id64 = make_idesc_f16(TILE, 64);
     constexpr int NPART = SPLIT ? 3 : 1;          // (a_hi, w_hi) [+ (a_lo, w_hi) + (a_hi, w_lo)]
-    uint32_t phb = 0, phf = 0, pw = 0, ppub = 0;
-    // Chain mode: this warp is also the CTA's synchronisation agent, so that the epilogue never pays a gpu-scope fence or a
-    // flag round trip.  publish(t): wait until all epilogue warps have written tile t's c1 rows (bar_pub), then release them
-    // at gpu scope by bumping flags[t].  await(t, s_): tile t's c1 taps for stage s_ may be loaded once stage s_-1 of t and of
-    // its neighbours inside the utterance is published (left / self: producers of the rows read; right: done READING the plane
-    // stage s_ overwrites, and a producer when the padding is 'same'); then bar_dep tells the epilogue.
-    auto publish = [&](int t) {
-      mbar_wait(&bar_pub, ppub); ppub ^= 1;
-      if (elect_one()) { __threadfence(); red_release_gpu_add(p.flags + t, 1); }
-      __syncwarp();
-    };
-    auto await = [&](int t, int s_) {
-      const int j = t % p.tiles_per_utt, dj = lane - 1;      // lanes 0..2 poll tiles t-1, t, t+1
-      if (lane < 3 && j + dj >= 0 && j + dj < p.tiles_per_utt) {
-        const int* f = p.flags + t + dj;
-        while (ld_acquire_gpu(f) < s_) {}
-      }
-      __syncwarp();
-      if (elect_one()) mbar_arrive(&bar_dep);
-      __syncwarp();
-    };
-    const bool chain = p.flags != nullptr;
+    uint32_t ph = 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    int s = p.s_begin, k = 0;
-    for (int it = 0; it < n_it; ++it) {
-      const bool has_back = s >= 1, has_front = s < p.n_blocks;
-      const int tile = first + k * stride;
-      if (k == 0) {
-        if (it > 0) {   // the previous stage's last GEMM3 (and everything before it) has read its weights: reuse the buffer
-          mbar_wait(&bar_d3, phf ^ 1);
-          load_weights(s);
-          if (chain) { publish(first + (n_k - 1) * stride); await(tile, s); }
-        }
-        mbar_wait(&bar_w, pw); pw ^= 1;
-      } else if (chain && !has_back && has_front) {
-        publish(tile - stride);
-      }
-      if (!p.chain_m) {   // pull the next tile's residual rows / c1 rows into L2 ahead of their use (chain mode works out of L2 anyway)
-        const int nt = tile + stride;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      {   // pull the next tile's residual rows / c1 rows into L2 ahead of their use
+        const int nt = tile + gridDim.x;
         if (nt < p.n_tiles) {
           const char* hn = reinterpret_cast<const char*>(p.h + (size_t)nt * (TILE * 256));
           if (lane < 8) prefetch_l2(hn + lane * 16384, 16384);
-          if (has_back && lane >= 16 && lane < (SPLIT ? 32 : 24)) {
-            const int d = 1 << ((s - 1) % p.nd);
-            const int back = p.causal ? 2 * d : d, fwd = p.causal ? 0 : d;
+          if (p.has_back && lane >= 16 && lane < (SPLIT ? 32 : 24)) {
             const int b = nt / p.tiles_per_utt, t0 = (nt - b * p.tiles_per_utt) * TILE;
-            const __half* cb = p.c1[(s + 1) & 1] + (size_t)b * 2 * 8 * p.Ts * 8;
-            prefetch_l2(cb + ((size_t)(lane - 16) * p.Ts + (t0 - back + C1_PAD)) * 8, (TILE + back + fwd) * 16);
+            const int lo_row = t0 - (p.shift0 > 0 ? p.shift0 : 0) + C1_PAD;
+            const int n_rows = TILE + (p.shift0 > 0 ? p.shift0 : 0) - (p.shift2 < 0 ? p.shift2 : 0);
+            const __half* cb = p.c1_in + (size_t)b * 2 * 8 * p.Ts * 8;
+            prefetch_l2(cb + ((size_t)(lane - 16) * p.Ts + lo_row) * 8, n_rows * 16);
           }
         }
         __syncwarp();
       }
-      if (has_back) {
-        mbar_wait(&bar_a1, phb); tc_fence_after();
+      if (p.has_back) {
+        mbar_wait(&bar_a1, ph); tc_fence_after();
         {   // c2 = W2 (*) [c1(t-s0) | c1(t-s1) | c1(t-s2)] : K = 192, N = 64
           uint32_t acc = 0;
 #pragma unroll
@@ -242,8 +183,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
           }
         }
         mma_commit_elect(&bar_d1);
-        if (chain && k > 0 && has_front) publish(tile - stride);      // the previous tile of this stage
-        mbar_wait(&bar_a2, phb); tc_fence_after();
+        mbar_wait(&bar_a2, ph); tc_fence_after();
 #pragma unroll
         for (int g = 0; g < 4; ++g) {   // W3 ReLU(c2): K = 64, N = 256 in four column groups, each committed on its own
           uint32_t acc = 0;
@@ -258,14 +198,12 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
           }
           mma_commit_elect(&bar_d2[g]);
         }
-        phb ^= 1;
-        if (chain && k + 1 < n_k) await(tile + stride, s);      // next tile of this stage: its taps are loaded after P2
       }
-      if (has_front) {
+      if (p.has_front) {
         uint32_t acc = 0;
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {   // W1' ReLU(h): K = 256 in eight 32-channel chunks, issued as the epilogue produces them
-          mbar_wait(&bar_a3[cc], phf); tc_fence_after();
+          mbar_wait(&bar_a3[cc], ph); tc_fence_after();
 #pragma unroll
           for (int part = 0; part < NPART; ++part) {
             const uint32_t a0 = COL_D2 + 32 * cc + (part == 1 ? 16 : 0), w0 = (part == 2 ? w_lo : w_hi) + IMG_W1;
@@ -278,93 +216,64 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
           }
         }
         mma_commit_elect(&bar_d3);
-        phf ^= 1;
       }
-      if (++k == n_k) { k = 0; ++s; }
+      ph ^= 1;
     }
   } else {
     // ================= epilogue: warps (q, qd): TMEM lane quarter q = warp & 3, column quarter qd = warp >> 2 =================
+    mbar_wait(&bar_w, 0);        // biases / column sums live in the weight image
     const int qd = warp >> 2, row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    uint32_t phb = 0, phf = 0, pw = 0, pdep = 0;
+    uint32_t ph = 0;
     // one arrival per warp: tcgen05.wait is warp-wide, so once it returns every lane's TMEM traffic is done
     auto warp_arrive = [&](uint64_t* bar) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar); };
+    const bool stamp = p.dbg != nullptr && tid == 0;
+#define DXI_STAMP(k) do { if (stamp) p.dbg[(size_t)tile * 16 + (k)] = clock64(); } while (0)
 
-    // c1 taps of tile tile_ for stage s_ (>= 1) -> TMEM [320,512): this thread moves units 2qd, 2qd+1 of every (tap, plane).
-    auto load_a1 = [&](int tile_, int s_) {
-      if (p.flags) { mbar_wait(&bar_dep, pdep); pdep ^= 1; }      // the MMA warp saw the tiles these rows depend on published
-      const int b = tile_ / p.tiles_per_utt, j = tile_ - b * p.tiles_per_utt;
-      const int t = j * TILE + row;
-      const int d = 1 << ((s_ - 1) % p.nd);
-      const int sh0 = p.causal ? 2 * d : d, sh1 = p.causal ? d : 0, sh2 = p.causal ? 0 : -d;     // tap jj reads frame t - shift_jj
-      const __half* cb = p.c1[(s_ + 1) & 1] + (size_t)b * 2 * 8 * p.Ts * 8;
+    // c1 taps of a tile -> TMEM [320,512): this thread moves units 2qd, 2qd+1 of every (tap, plane)
+    auto load_a1 = [&](int tile_) {
+      const int b = tile_ / p.tiles_per_utt, t = (tile_ - b * p.tiles_per_utt) * TILE + row;
+      const __half* cb = p.c1_in + (size_t)b * 2 * 8 * p.Ts * 8;
       uint4 qv[3][SPLIT ? 2 : 1][2];
 #pragma unroll
-      for (int jj = 0; jj < 3; ++jj) {
-        const int shift = jj == 0 ? sh0 : (jj == 1 ? sh1 : sh2);
+      for (int j = 0; j < 3; ++j) {
+        const int shift = j == 0 ? p.shift0 : (j == 1 ? p.shift1 : p.shift2);
         const size_t r_in = (size_t)(t - shift + C1_PAD);
 #pragma unroll
         for (int plane = 0; plane < (SPLIT ? 2 : 1); ++plane)
 #pragma unroll
           for (int u = 0; u < 2; ++u)
-            qv[jj][plane][u] = (p.dbg_flags & 4) ? make_uint4(0, 0, 0, 0) : __ldcg(reinterpret_cast<const uint4*>(cb + ((size_t)(plane * 8 + 2 * qd + u) * p.Ts + r_in) * 8));
+            qv[j][plane][u] = (p.dbg_flags & 4) ? make_uint4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uint4*>(cb + ((size_t)(plane * 8 + 2 * qd + u) * p.Ts + r_in) * 8));
       }
 #pragma unroll
-      for (int jj = 0; jj < 3; ++jj)
+      for (int j = 0; j < 3; ++j)
 #pragma unroll
         for (int plane = 0; plane < (SPLIT ? 2 : 1); ++plane) {
-          const uint32_t r[8] = {qv[jj][plane][0].x, qv[jj][plane][0].y, qv[jj][plane][0].z, qv[jj][plane][0].w,
-                                 qv[jj][plane][1].x, qv[jj][plane][1].y, qv[jj][plane][1].z, qv[jj][plane][1].w};
-          tmem_st8(lane_addr + (plane ? COL_A1_LO : COL_A1_HI) + 32 * jj + 8 * qd, r);
+          const uint32_t r[8] = {qv[j][plane][0].x, qv[j][plane][0].y, qv[j][plane][0].z, qv[j][plane][0].w,
+                                 qv[j][plane][1].x, qv[j][plane][1].y, qv[j][plane][1].z, qv[j][plane][1].w};
+          tmem_st8(lane_addr + (plane ? COL_A1_LO : COL_A1_HI) + 32 * j + 8 * qd, r);
         }
-      tmem_wait_st();
+      tmem_wait_st(); tc_fence_before();
     };
 
     asm volatile("griddepcontrol.wait;" ::: "memory");      // the previous launch's h / c1 are complete and visible
-    if (n_it > 0 && p.s_begin >= 1) { load_a1(first, p.s_begin); warp_arrive(&bar_a1); }
-    int s = p.s_begin, k = 0;
-    const float* sAux = sAuxBuf;
-    for (int it = 0; it < n_it; ++it) {
-      const bool has_back = s >= 1, has_front = s < p.n_blocks, stem = s == 0 && p.stem_stats != nullptr;
-      const int tile = first + k * stride;
-      if (k == 0) {       // a new stage: its biases / column sums arrive with its weights
-        mbar_wait(&bar_w, pw); pw ^= 1;
-        sAux = sAuxBuf + (s & 1) * N_AUX;
-      }
-      // the next (stage, tile) of this CTA.  Its c1 taps are loaded after P2 -- unless (chain mode) it belongs to the next stage:
-      // then this tile's own output must be published first (the next tile or a neighbour CTA may be waiting for it) and the taps
-      // are loaded at the very end.
-      int ns = s, nk = k + 1;
-      if (nk == n_k) { nk = 0; ++ns; }
-      const int next = first + nk * stride;
-      const bool has_next = it + 1 < n_it && ns >= 1;
-      const bool a1_early = has_next && !(p.flags != nullptr && ns != s);
-      const bool stamp = p.dbg != nullptr && tid == 0 && s == p.dbg_stage;
-#define DXI_STAMP(k_) do { if (stamp) p.dbg[(size_t)tile * 16 + (k_)] = clock64(); } while (0)
+    if (p.has_back && (int)blockIdx.x < p.n_tiles) { load_a1(blockIdx.x); warp_arrive(&bar_a1); }
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TILE;
       const int t = t0 + row;
       const bool valid = t < p.T;
       float* hrow = p.h + (size_t)tile * (TILE * 256) + row * 4;          // + c4 * 512
       DXI_STAMP(0);
-      // residual rows of a 32-channel chunk (8 float4 per thread): the first chunk's are requested now and consumed after P1, the
-      // second chunk's while the first chunk's operand goes to TMEM
-      auto h_load = [&](int cc, float4 (&dst)[8]) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          dst[q] = (p.dbg_flags & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(reinterpret_cast<const float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4)));
-      };
-      float4 hv[8];
-      h_load(qd, hv);
       float mu2 = 0.0f, inv2 = 0.0f;
-      if (has_back) {
+      if (p.has_back) {
         // ---- P1: r2 = ReLU(acc1 + b2) -> A2 at once (un-normalised); statistics merged while GEMM2 runs
-        mbar_wait(&bar_d1, phb); tc_fence_after();
+        mbar_wait(&bar_d1, ph); tc_fence_after();
         DXI_STAMP(1);
         float a[16];
         tmem_ld16(lane_addr + COL_D1 + 16 * qd, a); tmem_wait_ld();
-        float sm = 0.0f;
+        float s = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { a[j] = relu(a[j] + sAux[OFF_B2 + 16 * qd + j]); sm += a[j]; }
+        for (int j = 0; j < 16; ++j) { a[j] = relu(a[j] + sAux[OFF_B2 + 16 * qd + j]); s += a[j]; }
         {
           uint32_t hi[8], lo[8];
 #pragma unroll
@@ -374,7 +283,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
         }
         tmem_wait_st(); warp_arrive(&bar_a2);
         DXI_STAMP(2);
-        const float mean_i = sm * (1.0f / 16.0f);
+        const float mean_i = s * (1.0f / 16.0f);
         float q2 = 0.0f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) { const float d = a[j] - mean_i; q2 = fmaf(d, d, q2); }
@@ -383,7 +292,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
       DXI_STAMP(3);
       // ---- P2: h_new = h + b3 + inv2 (acc2 - mu2 colsum(W3)); r3 = ReLU(h_new) -> A3 in place, chunk by chunk
       float mean0 = 0.0f, inv0 = 0.0f;
-      if (stem) {     // merge the 8 partial statistics (32 channels each) the stem kernels left for this row
+      if (p.stem_stats) {     // merge the 8 partial statistics (32 channels each) the stem kernels left for this row
         const float2* sp = p.stem_stats + ((size_t)tile * TILE + row) * 8;
         float2 pt[8];
 #pragma unroll
@@ -403,9 +312,12 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int cc = qd + 4 * i;
+        float4 hv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) hv[q] = (p.dbg_flags & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4));
         float v[32];
-        if (has_back) {
-          mbar_wait(&bar_d2[cc >> 1], phb); tc_fence_after();
+        if (p.has_back) {
+          mbar_wait(&bar_d2[cc >> 1], ph); tc_fence_after();
           if (i == 0) DXI_STAMP(4); else DXI_STAMP(13);
           tmem_ld32(lane_addr + COL_D2 + 32 * cc, v); tmem_wait_ld();
           if (i == 0) DXI_STAMP(10); else DXI_STAMP(14);
@@ -416,15 +328,15 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const float4 bq = b3[q], cq = cs[q];
-            float2 t0_ = __fadd2_rn(make_float2(hv[q].x, hv[q].y), make_float2(bq.x, bq.y));
-            float2 t1_ = __fadd2_rn(make_float2(hv[q].z, hv[q].w), make_float2(bq.z, bq.w));
-            t0_ = __ffma2_rn(nimv, make_float2(cq.x, cq.y), t0_);
-            t1_ = __ffma2_rn(nimv, make_float2(cq.z, cq.w), t1_);
-            t0_ = __ffma2_rn(inv2v, make_float2(v[4 * q], v[4 * q + 1]), t0_);
-            t1_ = __ffma2_rn(inv2v, make_float2(v[4 * q + 2], v[4 * q + 3]), t1_);
-            v[4 * q] = t0_.x; v[4 * q + 1] = t0_.y; v[4 * q + 2] = t1_.x; v[4 * q + 3] = t1_.y;
+            float2 t0 = __fadd2_rn(make_float2(hv[q].x, hv[q].y), make_float2(bq.x, bq.y));
+            float2 t1 = __fadd2_rn(make_float2(hv[q].z, hv[q].w), make_float2(bq.z, bq.w));
+            t0 = __ffma2_rn(nimv, make_float2(cq.x, cq.y), t0);
+            t1 = __ffma2_rn(nimv, make_float2(cq.z, cq.w), t1);
+            t0 = __ffma2_rn(inv2v, make_float2(v[4 * q], v[4 * q + 1]), t0);
+            t1 = __ffma2_rn(inv2v, make_float2(v[4 * q + 2], v[4 * q + 3]), t1);
+            v[4 * q] = t0.x; v[4 * q + 1] = t0.y; v[4 * q + 2] = t1.x; v[4 * q + 3] = t1.y;
           }
-        } else if (stem) {
+        } else if (p.stem_stats) {
           // stage 0: the loaded row is the stem pre-activation z; h0 = ReLU(z * inv0 * gamma - mean0 * inv0 * gamma)
           const float* gm = sAux + OFF_B3 + 32 * cc;
 #pragma unroll
@@ -443,14 +355,13 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.0f;
         }
-        if ((has_back || stem) && !(p.dbg_flags & 2)) {
+        if ((p.has_back || p.stem_stats) && !(p.dbg_flags & 2)) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            __stcg(reinterpret_cast<float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4)), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+            *reinterpret_cast<float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
         if (i == 0) DXI_STAMP(11);
-        if (has_front) {
-          // A operand of GEMM3, in place: the chunk's 32 fp32 columns become 16 columns of fp16 hi pairs + 16 of lo pairs
+        if (p.has_front) {
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -459,49 +370,46 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
             s2v = __ffma2_rn(r, r, s2v);
             to_h2<SPLIT>(r.x, r.y, hi[j], lo[j]);
           }
-          if (i == 0) h_load(qd + 4, hv);
           tmem_st16(lane_addr + COL_D2 + 32 * cc, hi);
           if (SPLIT) tmem_st16(lane_addr + COL_D2 + 32 * cc + 16, lo);
           tmem_wait_st(); warp_arrive(&bar_a3[cc]);
-        } else if (i == 0) {
-          h_load(qd + 4, hv);
         }
         if (i == 0) DXI_STAMP(12);
       }
       DXI_STAMP(5);
       float mu3 = 0.0f, inv3 = 0.0f;
-      if (has_front) {
+      if (p.has_front) {
         const float s1 = s1v.x + s1v.y, s2 = s2v.x + s2v.y, m1 = s1 * (1.0f / 64.0f);
         ln_merge(red[1], row, qd, 64.0f, m1, fmaxf(s2 - s1 * m1, 0.0f), mu3, inv3);
       }
       DXI_STAMP(6);
+      // ---- the next tile's c1 taps travel to TMEM while this tile's GEMM3 drains
+      const int next = tile + gridDim.x;
+      const bool has_next = p.has_back && next < p.n_tiles;
+      if (has_next) load_a1(next);
       DXI_STAMP(7);
-      // The next tile's taps travel to TMEM while this tile's GEMM3 drains.  Its GEMM1 is released at once: it is issued behind
-      // this tile's GEMM3 (in-order tensor pipe) and runs while P3 reads D3; the next tile's A2 overwrites the D3 columns only
-      // after this thread's quarter has passed P3's merge barrier (program order).
-      if (a1_early) { load_a1(next, ns); if (!(p.dbg_flags & 16)) warp_arrive(&bar_a1); }
-      if (has_front) {
+      if (p.has_front) {
         // ---- P3: c1' = LN(ReLU(inv3 (acc3 - mu3 colsum(W1')) + b1')) -> fp16 hi | lo planes in HBM (zeros beyond T)
-        mbar_wait(&bar_d3, phf); tc_fence_after();
+        mbar_wait(&bar_d3, ph); tc_fence_after();
         DXI_STAMP(8);
         float a[16];
         tmem_ld16(lane_addr + COL_D3 + 16 * qd, a); tmem_wait_ld();
-        if (a1_early && (p.dbg_flags & 16)) warp_arrive(&bar_a1);
+        if (has_next) warp_arrive(&bar_a1);      // every D3 read is done: GEMM1 / A2 of the next tile may reuse the columns
         const float nim3 = -inv3 * mu3;
-        float sm = 0.0f;
+        float s = 0.0f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           a[j] = relu(fmaf(inv3, a[j], fmaf(nim3, sAux[OFF_CS1 + 16 * qd + j], sAux[OFF_B1 + 16 * qd + j])));
-          sm += a[j];
+          s += a[j];
         }
-        const float mean_i = sm * (1.0f / 16.0f);
+        const float mean_i = s * (1.0f / 16.0f);
         float q2 = 0.0f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) { const float d = a[j] - mean_i; q2 = fmaf(d, d, q2); }
         float mean, inv;
         ln_merge(red[2], row, qd, 16.0f, mean_i, q2, mean, inv);
         const float off = -mean * inv;
-        __half* ob = p.c1[s & 1] + (size_t)b * 2 * 8 * p.Ts * 8;
+        __half* ob = p.c1_out + (size_t)b * 2 * 8 * p.Ts * 8;
         const size_t r_out = (size_t)(t + C1_PAD);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -511,18 +419,14 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
             const float x0 = valid ? fmaf(a[8 * u + 2 * j], inv, off) : 0.0f, x1 = valid ? fmaf(a[8 * u + 2 * j + 1], inv, off) : 0.0f;
             to_h2<SPLIT>(x0, x1, hi[j], lo[j]);
           }
-          __stcg(reinterpret_cast<uint4*>(ob + ((size_t)(2 * qd + u) * p.Ts + r_out) * 8), make_uint4(hi[0], hi[1], hi[2], hi[3]));
-          if (SPLIT) __stcg(reinterpret_cast<uint4*>(ob + ((size_t)(8 + 2 * qd + u) * p.Ts + r_out) * 8), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+          *reinterpret_cast<uint4*>(ob + ((size_t)(2 * qd + u) * p.Ts + r_out) * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (SPLIT) *reinterpret_cast<uint4*>(ob + ((size_t)(8 + 2 * qd + u) * p.Ts + r_out) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-        if (p.flags) { __syncwarp(); if (lane == 0) mbar_arrive(&bar_pub); }      // this warp's share of the tile's c1 rows is written
-      } else if (a1_early && (p.dbg_flags & 16)) {
+      } else if (has_next) {
         warp_arrive(&bar_a1);
       }
-      if (has_next && !a1_early) { load_a1(next, ns); warp_arrive(&bar_a1); }
       DXI_STAMP(9);
-      if (has_back) phb ^= 1;
-      if (has_front) phf ^= 1;
-      s = ns; k = nk;
+      ph ^= 1;
     }
 #undef DXI_STAMP
   }
@@ -907,56 +811,33 @@ int resnet_umma_prepare(dxi_net& net, cudaStream_t st) {
 static thread_local long long* g_dbg_clocks = nullptr;
 static thread_local int g_dbg_stage = -1, g_dbg_flags = 0, g_dbg_stop_after = -1;
 
-// Tuning knobs (read once): DXI_TCN_CHAIN=0 falls back to one launch per stage; DXI_TCN_L2_MB is the working-set budget
-// (residual stream + both c1 planes of one chunk) that the chained kernel tries to keep inside the 126 MB L2.
-static int env_int(const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; }
-static int chain_enabled() { static const int v = env_int("DXI_TCN_CHAIN", 1); return v; }
-static int chain_l2_mb() { static const int v = env_int("DXI_TCN_L2_MB", 88); return v; }
-
 int64_t resnet_umma_workspace_bytes(const dxi_net& net, int B, int T) {
   const int tiles = (T + TILE - 1) / TILE;
   const size_t Ts = (size_t)tiles * TILE + 2 * C1_PAD;
   const size_t h_bytes = (size_t)B * tiles * TILE * 256 * 4;
   const size_t c1_bytes = align_up((size_t)B * 2 * 8 * Ts * 16, 256);
-  const size_t flag_bytes = align_up((size_t)B * tiles * sizeof(int), 256);
   const size_t stats_bytes = (size_t)B * tiles * TILE * 8 * sizeof(float2);
-  return (int64_t)(256 + h_bytes + 2 * c1_bytes + flag_bytes + stats_bytes);
+  return (int64_t)(256 + h_bytes + 2 * c1_bytes + stats_bytes);
 }
 
-template <typename Args>
-static cudaError_t launch_cooperative(void (*kern)(const Args), int grid, int block, size_t smem, cudaStream_t st, const Args& a) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(block);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: they wait for each other's tiles
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, a);
-}
-
-// One group of whole utterances through stem -> 41 stages -> output layer.  The workspace region is the same for every
-// group (same addresses: what the previous group left in L2 is overwritten in place, not written back and re-fetched).
-static int resnet_umma_group(const dxi_net& net, const float* mag, int B, int T, float* xbar, unsigned char* base, int m_chain,
-                             int n_sm, bool dbg, cudaStream_t st) {
+int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, float* xbar, void* ws, size_t ws_bytes,
+                        cudaStream_t st) {
   const dxi_net_cfg& c = net.cfg;
+  if ((int64_t)ws_bytes < resnet_umma_workspace_bytes(net, B, T)) { set_error("workspace too small"); return DXI_E_NOMEM; }
   const int tiles = (T + TILE - 1) / TILE;
   const int Ts = tiles * TILE + 2 * C1_PAD;
   const size_t h_bytes = (size_t)B * tiles * TILE * 256 * 4;
   const size_t c1_bytes = align_up((size_t)B * 2 * 8 * Ts * 16, 256);
-  const size_t flag_bytes = align_up((size_t)B * tiles * sizeof(int), 256);
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   float* h = reinterpret_cast<float*>(base);
-  __half* c1a = reinterpret_cast<__half*>(base + h_bytes);
-  __half* c1b = reinterpret_cast<__half*>(base + h_bytes + c1_bytes);
-  int* flags = reinterpret_cast<int*>(base + h_bytes + 2 * c1_bytes);
-  float2* stem_stats = reinterpret_cast<float2*>(base + h_bytes + 2 * c1_bytes + flag_bytes);
-  // zero padding rows of the c1 planes (and everything else in them) and the tile progress counters
-  DXI_CUDA(cudaMemsetAsync(c1a, 0, 2 * c1_bytes + flag_bytes, st));
+  __half* c1[2] = {reinterpret_cast<__half*>(base + h_bytes), reinterpret_cast<__half*>(base + h_bytes + c1_bytes)};
+  float2* stem_stats = reinterpret_cast<float2*>(base + h_bytes + 2 * c1_bytes);
+  // zero padding rows of the c1 planes (and everything else in them)
+  DXI_CUDA(cudaMemsetAsync(c1[0], 0, 2 * c1_bytes, st));
 
   const int n_tiles = B * tiles;
+  int n_sm = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
   const unsigned char* images = reinterpret_cast<const unsigned char*>(net.d_umma);
   // ---- stem (tcgen05, two 128-column halves) -> pre-activation z in the tiled buffer + partial row statistics
@@ -970,76 +851,42 @@ static int resnet_umma_group(const dxi_net& net, const float* mag, int B, int T,
       DXI_LAUNCHED("stem_umma_kernel");
     }
   }
-  // ---- 41 tensor-core stages: one persistent launch (chain) or one launch per stage
+  // ---- 41 tensor-core stages
   const bool split = c.precision == DXI_PREC_F16X3;
-  DXI_CUDA(cudaFuncSetAttribute(tcn_stage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_SMEM));
-  DXI_CUDA(cudaFuncSetAttribute(tcn_stage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGE_SMEM));
-  StageArgs a{};
-  a.img = images;
-  a.h = h;
-  a.c1[0] = c1a; a.c1[1] = c1b;
-  a.T = T; a.tiles_per_utt = tiles; a.n_tiles = n_tiles; a.Ts = Ts;
-  a.n_blocks = c.n_blocks; a.nd = n_dilations(c.max_d_rate); a.causal = c.padding == DXI_PAD_CAUSAL;
-  a.stem_stats = stem_stats;
-  a.dbg = dbg ? g_dbg_clocks : nullptr;
-  a.dbg_stage = g_dbg_stage;
-  a.dbg_flags = g_dbg_flags | env_int("DXI_TCN_DBGFLAGS", 0);
-  const int s_last = g_dbg_stop_after >= 0 && g_dbg_stop_after < c.n_blocks ? g_dbg_stop_after : c.n_blocks;
-  if (m_chain > 0) {
-    ProfScope prof_stages("tcn_stage", st, 1);
-    a.s_begin = 0; a.s_end = s_last + 1;
-    a.chain_m = m_chain;
-    a.flags = flags;
-    const int g = (n_tiles + m_chain - 1) / m_chain;
-    if (split) DXI_CUDA(launch_cooperative(tcn_stage_kernel<true>, g, STAGE_THREADS, STAGE_SMEM, st, a));
-    else       DXI_CUDA(launch_cooperative(tcn_stage_kernel<false>, g, STAGE_THREADS, STAGE_SMEM, st, a));
+  const size_t smem = IMG_BYTES + 1024;
+  DXI_CUDA(cudaFuncSetAttribute(tcn_stage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DXI_CUDA(cudaFuncSetAttribute(tcn_stage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nd = n_dilations(c.max_d_rate);
+  {
+  ProfScope prof_stages("tcn_stage", st, c.n_blocks + 1);
+  for (int s = 0; s <= c.n_blocks; ++s) {
+    if (g_dbg_stop_after >= 0 && s > g_dbg_stop_after) break;
+    StageArgs a{};
+    a.img = images + (size_t)s * IMG_BYTES;
+    a.stem_stats = s == 0 ? stem_stats : nullptr;
+    a.h = h;
+    a.c1_in = c1[(s + 1) & 1];
+    a.c1_out = c1[s & 1];
+    a.T = T; a.tiles_per_utt = tiles; a.n_tiles = n_tiles; a.Ts = Ts;
+    a.has_back = s >= 1; a.has_front = s < c.n_blocks;
+    a.dbg = (s == g_dbg_stage) ? g_dbg_clocks : nullptr;
+    a.dbg_flags = g_dbg_flags;
+    const int d = s >= 1 ? 1 << ((s - 1) % nd) : 1;
+    if (c.padding == DXI_PAD_CAUSAL) { a.shift0 = 2 * d; a.shift1 = d; a.shift2 = 0; }       // tap j reads t-(2-j)d
+    else                             { a.shift0 = d;     a.shift1 = 0; a.shift2 = -d; }      // tap j reads t+(j-1)d
+    if (split) DXI_CUDA(launch_pdl(tcn_stage_kernel<true>, grid, STAGE_THREADS, smem, st, a));
+    else       DXI_CUDA(launch_pdl(tcn_stage_kernel<false>, grid, STAGE_THREADS, smem, st, a));
     DXI_LAUNCHED("tcn_stage_kernel");
-  } else {
-    ProfScope prof_stages("tcn_stage", st, s_last + 1);
-    for (int s = 0; s <= s_last; ++s) {
-      a.s_begin = s; a.s_end = s + 1;
-      if (split) DXI_CUDA(launch_pdl(tcn_stage_kernel<true>, grid, STAGE_THREADS, STAGE_SMEM, st, a));
-      else       DXI_CUDA(launch_pdl(tcn_stage_kernel<false>, grid, STAGE_THREADS, STAGE_SMEM, st, a));
-      DXI_LAUNCHED("tcn_stage_kernel");
-    }
+  }
   }
   // ---- output layer (tcgen05 + one fp32 column): tiled h -> sigmoid(W h + b), row-major x_bar
   {
     const size_t smem_head = HEAD_W_PAD + (size_t)NSPLIT * TILE * HEAD_STAGE_LD * sizeof(float) + 1024;
     DXI_CUDA(cudaFuncSetAttribute(head_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head));
-    HeadArgs ha{images + net.umma_stage_offset[2], h, xbar, T, tiles, n_tiles, c.n_outp};
+    HeadArgs a{images + net.umma_stage_offset[2], h, xbar, T, tiles, n_tiles, c.n_outp};
     ProfScope prof("tcn_head", st, 1);
-    DXI_CUDA(launch_pdl(head_umma_kernel, grid, STAGE_THREADS, smem_head, st, ha));
+    DXI_CUDA(launch_pdl(head_umma_kernel, grid, STAGE_THREADS, smem_head, st, a));
     DXI_LAUNCHED("head_umma_kernel");
-  }
-  return DXI_OK;
-}
-
-int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, float* xbar, void* ws, size_t ws_bytes,
-                        cudaStream_t st) {
-  const dxi_net_cfg& c = net.cfg;
-  if ((int64_t)ws_bytes < resnet_umma_workspace_bytes(net, B, T)) { set_error("workspace too small"); return DXI_E_NOMEM; }
-  if (B <= 0 || T <= 0) return DXI_OK;
-  const int tiles = (T + TILE - 1) / TILE;
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-  int n_sm = 148;
-  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
-  // Chain mode: groups of whole utterances whose residual stream + c1 planes (192 KB per tile) fit the L2 budget; every CTA
-  // keeps the same m consecutive tiles through all stages.  An utterance longer than a group falls back to per-stage launches.
-  const size_t tile_bytes = (size_t)TILE * 256 * 4 + 2 * 2 * (size_t)TILE * 64 * 2;
-  const int budget_tiles = (int)(((size_t)chain_l2_mb() << 20) / tile_bytes);
-  int m_max = budget_tiles / n_sm;
-  if (m_max < 1) m_max = 1;
-  const int utt_per_group_max = (n_sm * m_max) / tiles;
-  if (!chain_enabled() || utt_per_group_max < 1) return resnet_umma_group(net, mag, B, T, xbar, base, 0, n_sm, true, st);
-  const int n_groups = (B + utt_per_group_max - 1) / utt_per_group_max;
-  const int upg = (B + n_groups - 1) / n_groups;
-  for (int b0 = 0; b0 < B; b0 += upg) {
-    const int Bg = B - b0 < upg ? B - b0 : upg;
-    const int m = (Bg * tiles + n_sm - 1) / n_sm;
-    const int rc = resnet_umma_group(net, mag + (size_t)b0 * T * c.n_feat, Bg, T, xbar + (size_t)b0 * T * c.n_outp, base, m, n_sm,
-                                     b0 == 0, st);
-    if (rc != DXI_OK) return rc;
   }
   return DXI_OK;
 }

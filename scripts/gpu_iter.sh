@@ -4,7 +4,7 @@ set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 timeout -k 5 ${TEST_TIMEOUT:-300} python -m pytest tests/test_gpu_network.py tests/test_gpu_signal.py -q -x --durations=5 ${1:+-k "$1"} > gpurun_out/tests.log 2>&1 ; echo "tests rc=$?" ; tail -${TEST_TAIL:-12} gpurun_out/tests.log
-for f in ${CLOCK_FLAGS:-0}; do timeout -k 5 120 python scripts/tcn_clocks.py ${CLOCK_B:-86} 20 $f 2>&1 | grep -v "^$"; done > gpurun_out/clocks.txt 2>&1; cat gpurun_out/clocks.txt
+for f in ${CLOCK_FLAGS:-0}; do timeout -k 5 120 python scripts/tcn_clocks.py ${CLOCK_B:-256} 20 $f 2>&1 | grep -v "^$"; done > gpurun_out/clocks.txt 2>&1; cat gpurun_out/clocks.txt
 timeout -k 5 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_iter.json 2> gpurun_out/bench_iter.err ; echo "bench rc=$?"
 python - <<'PY'
 import json
