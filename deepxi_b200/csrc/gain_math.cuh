@@ -115,4 +115,93 @@ __device__ __forceinline__ float xbar_from_xi(float xi, float mu, float sigma) {
   return __fmul_rn(0.5f, __fadd_rn(1.0f, v3));
 }
 
+// ---- fast path of the fused enhancement kernel: x_bar -> G_LSA(xi_hat, xi_hat + 1) ---------------------------------
+// MUFU-based (ex2 / lg2 / rcp approximations, ~2^-22 relative) restatement of xi_from_xbar + gain_mmse_lsa for the one
+// combination the reference's default inference uses (inp_tgt.py:198-214 with gtype 'mmse-lsa': gamma_hat = xi_hat + 1, so
+// nu = xi_hat and G depends on xi_hat alone).  Relative error of G against the float64 chain < 1e-5 (dominated by the
+// float32 erfinv amplified by sigma), i.e. > 100 dB on the waveform; the exact-order functions above stay the ones behind
+// dxi_map_gain / dxi_gfunc and every other gain type.
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#else
+static inline float fast_ex2(float x) { return exp2f(x); }
+static inline float fast_lg2(float x) { return log2f(x); }
+static inline float fast_rcp(float x) { return 1.0f / x; }
+static inline float fast_sqrt(float x) { return sqrtf(x); }
+#endif
+
+// erfinv(x), |x| < 1 (M. Giles, "Approximating the erfinv function", single-precision polynomials in w = -ln(1 - x^2))
+__device__ __forceinline__ float erfinv_fast(float x) {
+  float w = -0.69314718f * fast_lg2(fmaf(-x, x, 1.0f));
+  float p;
+  if (w < 5.0f) {
+    w -= 2.5f;
+    p = 2.81022636e-08f;
+    p = fmaf(p, w, 3.43273939e-07f);
+    p = fmaf(p, w, -3.5233877e-06f);
+    p = fmaf(p, w, -4.39150654e-06f);
+    p = fmaf(p, w, 0.00021858087f);
+    p = fmaf(p, w, -0.00125372503f);
+    p = fmaf(p, w, -0.00417768164f);
+    p = fmaf(p, w, 0.246640727f);
+    p = fmaf(p, w, 1.50140941f);
+  } else {
+    w = fast_sqrt(w) - 3.0f;
+    p = -0.000200214257f;
+    p = fmaf(p, w, 0.000100950558f);
+    p = fmaf(p, w, 0.00134934322f);
+    p = fmaf(p, w, -0.00367342844f);
+    p = fmaf(p, w, 0.00573950773f);
+    p = fmaf(p, w, -0.0076224613f);
+    p = fmaf(p, w, 0.00943887047f);
+    p = fmaf(p, w, 1.00167406f);
+    p = fmaf(p, w, 2.83297682f);
+  }
+  return p * x;
+}
+
+// E1(x), x >= 1e-12: power series (9 terms) up to 1, Abramowitz & Stegun 5.1.56 (|eps| < 2e-8 on x e^x E1) above
+__device__ __forceinline__ float expint_e1_fast(float x) {
+  if (x <= 1.0f) {
+    float p = 3.0619244e-7f;                   // k=9
+    p = fmaf(p, x, -3.1001984e-6f);
+    p = fmaf(p, x, 2.8344671e-5f);
+    p = fmaf(p, x, -2.3148148e-4f);
+    p = fmaf(p, x, 1.6666667e-3f);
+    p = fmaf(p, x, -1.0416667e-2f);
+    p = fmaf(p, x, 5.5555556e-2f);
+    p = fmaf(p, x, -0.25f);
+    p = fmaf(p, x, 1.0f);
+    return fmaf(p, x, fmaf(-0.69314718f, fast_lg2(x), -0.57721566f));
+  }
+  const float r = fast_rcp(x);
+  float n = 0.2677737343f;
+  n = fmaf(n, r, 8.6347608925f);
+  n = fmaf(n, r, 18.0590169730f);
+  n = fmaf(n, r, 8.5733287401f);
+  n = fmaf(n, r, 1.0f);
+  float d = 3.9584969228f;
+  d = fmaf(d, r, 21.0996530827f);
+  d = fmaf(d, r, 25.6329561486f);
+  d = fmaf(d, r, 9.5733223454f);
+  d = fmaf(d, r, 1.0f);
+  return fast_ex2(-1.44269504f * x) * r * n * fast_rcp(d);
+}
+
+// s2 = sigma * f32(sqrt(2)).  Arguments on or outside the open interval (erfinv = +-inf, NaN) take the exact-order path.
+__device__ __forceinline__ float lsa_gain_from_xbar_fast(float xbar, float mu, float s2, float sigma) {
+  const float arg = fmaf(2.0f, xbar, -1.0f);
+  if (!(fabsf(arg) < 1.0f)) {
+    const float xi = xi_from_xbar(xbar, mu, sigma);
+    return gain_mmse_lsa(xi, __fadd_rn(xi, 1.0f));
+  }
+  const float xdb = fminf(fmaf(s2, erfinv_fast(arg), mu), 300.0f);
+  const float xi = fmaxf(fast_ex2(0.33219281f * xdb), 1e-12f);
+  const float wf = xi * fast_rcp(1.0f + xi);
+  return wf * fast_ex2(0.72134752f * expint_e1_fast(xi));
+}
+
 }  // namespace dxi

@@ -10,6 +10,7 @@
 // Each sample is read from HBM once (the 50 % frame overlap is served from shared memory) and every
 // output element is written once.
 #include <math.h>
+#include <stdlib.h>
 #include <mutex>
 #include "fft.cuh"
 #include "gain_math.cuh"
@@ -171,9 +172,10 @@ struct IstftSmem {
   float2 tw512[NBINS + 1];
 };
 
-// MODE 0: gain tensor (nullable); MODE 1: fused inverse map + gain from xbar (inp_tgt.py:198-214)
+// MODE 0: gain tensor (nullable); MODE 1: fused inverse map + gain from xbar (inp_tgt.py:198-214), exact-order math, any gain
+// type; MODE 2: the same for MMSE-LSA through the MUFU-based path of gain_math.cuh (lsa_gain_from_xbar_fast)
 template <int MODE>
-__global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ mag, const float* __restrict__ gain_or_xbar,
+__global__ void __launch_bounds__(256, 3) istft_kernel(const float* __restrict__ mag, const float* __restrict__ gain_or_xbar,
                                                     const float* __restrict__ phase, const float* __restrict__ mu,
                                                     const float* __restrict__ sigma, int gtype,
                                                     const int32_t* __restrict__ n_frames, int B, int Tmax,
@@ -200,27 +202,51 @@ __global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ ma
     // frames hs-1 .. he-1 in passes of FR; the first frame of the strip only provides its tail
     for (int f0 = hs - 1; f0 < he; f0 += FR) {
       const int nf = min(FR, he - f0);
-      // ---- spectrum of every frame: Y = (|X| G) e^{j phase}
-      int fi = 0, k = tid;
-      for (int i = tid; i < nf * NBINS; i += 256, k += 256) {
-        if (k >= NBINS) { k -= NBINS; ++fi; }
-        const int t = f0 + fi;
-        float2 Y = make_float2(0.0f, 0.0f);
-        if (t >= 0 && t < T) {
-          const int64_t gi = in0 + (int64_t)t * NBINS + k;
-          float m = __ldcs(mag + gi);
-          float p = __ldcs(phase + gi);
-          if (MODE == 0) {
-            if (gain_or_xbar) m *= __ldcs(gain_or_xbar + gi);
-          } else {
-            float xi = xi_from_xbar(__ldcs(gain_or_xbar + gi), __ldg(mu + k), __ldg(sigma + k));
-            m = __fmul_rn(m, gfunc_eval(gtype, xi, __fadd_rn(xi, 1.0f)));
+      // ---- spectrum of every frame: Y = (|X| G) e^{j phase}.  Flat element i = 256 it + tid = 257 it + (tid - it): bin
+      // k = tid - it of frame it (or k + 257 of frame it - 1); two elements per iteration so that six loads are in flight.
+      const int n_el = nf * NBINS;
+      for (int it = 0; it * 256 < n_el; it += 2) {
+        float mv[2], pv[2], gv[2];
+        int kk[2], ff[2];
+        bool inb[2], ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          int k = tid - (it + u), fi = it + u;
+          if (k < 0) { k += NBINS; --fi; }
+          kk[u] = k; ff[u] = fi;
+          inb[u] = (it + u) * 256 + tid < n_el;
+          const int t = f0 + fi;
+          ok[u] = inb[u] && t >= 0 && t < T;
+          mv[u] = pv[u] = gv[u] = 0.0f;
+          if (ok[u]) {
+            const int64_t gi = in0 + (int64_t)t * NBINS + k;
+            mv[u] = __ldcs(mag + gi);
+            pv[u] = __ldcs(phase + gi);
+            if (MODE != 0 || gain_or_xbar) gv[u] = __ldcs(gain_or_xbar + gi);
           }
-          float sn, cs;
-          __sincosf(p, &sn, &cs);                                        // |p| <= pi: abs error < 5e-7
-          Y = make_float2(m * cs, (k == 0 || k == 256) ? 0.0f : m * sn);   // c2r ignores Im of DC / Nyquist
         }
-        sm.buf[fi * FFT_FRAME_SLOTS + k] = Y;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (!inb[u]) continue;
+          const int k = kk[u];
+          float2 Y = make_float2(0.0f, 0.0f);
+          if (ok[u]) {
+            float m = mv[u];
+            if (MODE == 0) {
+              if (gain_or_xbar) m *= gv[u];
+            } else if (MODE == 1) {
+              float xi = xi_from_xbar(gv[u], __ldg(mu + k), __ldg(sigma + k));
+              m = __fmul_rn(m, gfunc_eval(gtype, xi, __fadd_rn(xi, 1.0f)));
+            } else {
+              const float sg = __ldg(sigma + k);      // (the 2 KB of statistics stay in L1; shared memory is what bounds occupancy here)
+              m *= lsa_gain_from_xbar_fast(gv[u], __ldg(mu + k), __fmul_rn(sg, 1.41421354f), sg);
+            }
+            float sn, cs;
+            __sincosf(pv[u], &sn, &cs);                                      // |p| <= pi: abs error < 5e-7
+            Y = make_float2(m * cs, (k == 0 || k == 256) ? 0.0f : m * sn);   // c2r ignores Im of DC / Nyquist
+          }
+          sm.buf[ff[u] * FFT_FRAME_SLOTS + k] = Y;
+        }
       }
       __syncthreads();
       // ---- merge step + 256-point inverse FFT
@@ -265,6 +291,9 @@ __global__ void __launch_bounds__(256) istft_kernel(const float* __restrict__ ma
   }
 }
 
+// DXI_ENHANCE_EXACT=1 keeps the exact-order math for MMSE-LSA too (A/B against the MUFU-based path).
+static bool exact_enhance() { static const bool v = [] { const char* e = getenv("DXI_ENHANCE_EXACT"); return e && *e && *e != '0'; }(); return v; }
+
 static int istft_launch(int mode, const float* mag, const float* g_or_xbar, const float* phase, const float* mu,
                         const float* sigma, int gtype, const int32_t* n_frames, int B, int Tmax, float* wav_f32,
                         int16_t* wav_i16, int64_t out_stride, cudaStream_t st) {
@@ -277,6 +306,10 @@ static int istft_launch(int mode, const float* mag, const float* g_or_xbar, cons
   if (mode == 0) {
     DXI_CUDA(cudaFuncSetAttribute(istft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     istft_kernel<0><<<grid, 256, smem, st>>>(mag, g_or_xbar, phase, mu, sigma, gtype, n_frames, B, Tmax, strips,
+                                             wav_f32, wav_i16, out_stride);
+  } else if (gtype == DXI_G_MMSE_LSA && !exact_enhance()) {
+    DXI_CUDA(cudaFuncSetAttribute(istft_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    istft_kernel<2><<<grid, 256, smem, st>>>(mag, g_or_xbar, phase, mu, sigma, gtype, n_frames, B, Tmax, strips,
                                              wav_f32, wav_i16, out_stride);
   } else {
     DXI_CUDA(cudaFuncSetAttribute(istft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -115,4 +115,11 @@ void host_gfunc(const float* xi, const float* gamma, int n, int gtype, float* G)
 }
 
 float host_e1(float x) { return expint_e1(x); }
+float host_e1_fast(float x) { return expint_e1_fast(x); }
+float host_erfinv_fast(float x) { return erfinv_fast(x); }
+void host_lsa_from_xbar_fast(const float* xbar, const float* mu, const float* sigma, int rows, int bins, float* G) {
+  for (int r = 0; r < rows; ++r)
+    for (int k = 0; k < bins; ++k)
+      G[r * bins + k] = lsa_gain_from_xbar_fast(xbar[r * bins + k], mu[k], __fmul_rn(sigma[k], 1.41421354f), sigma[k]);
+}
 }

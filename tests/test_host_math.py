@@ -107,3 +107,32 @@ def test_inverse_map_chain_and_ibm_exactness(hostlib, xi_stats):
     back = np.zeros_like(xb)
     hostlib.host_xbar_from_xi(P(ref), P(mu), P(sg), xb.shape[0], 257, P(back))
     assert np.abs(back - cdfmap.normal_cdf_map(ref, mu, sg)).max() < 3e-7
+
+
+def test_fast_lsa_path_math(hostlib, xi_stats):
+    """The MUFU-style restatement behind the fused enhancement kernel (gain_math.cuh: erfinv_fast, expint_e1_fast,
+    lsa_gain_from_xbar_fast) against scipy and the oracle chain x_bar -> xi_hat -> G_LSA(xi_hat, xi_hat + 1)."""
+    hostlib.host_e1_fast.restype = ctypes.c_float
+    hostlib.host_e1_fast.argtypes = [ctypes.c_float]
+    hostlib.host_erfinv_fast.restype = ctypes.c_float
+    hostlib.host_erfinv_fast.argtypes = [ctypes.c_float]
+    x = (10.0 ** np.linspace(-12, 3, 4000)).astype(np.float32)
+    e = np.array([hostlib.host_e1_fast(float(v)) for v in x], dtype=np.float64)
+    ref = spsp.exp1(x.astype(np.float64))
+    sel = (x > 1e-3) & (x < 10)      # beyond 10, E1 < 5e-6: only the absolute error matters for exp(E1 / 2)
+    assert np.abs(e - ref).max() < 3e-6 and (np.abs(e - ref) <= 1e-6 * ref)[sel].all()
+    a = np.concatenate([np.linspace(-1, 1, 20001)[1:-1], 1 - 2.0 ** -np.arange(2, 25), -1 + 2.0 ** -np.arange(2, 25)]).astype(np.float32)
+    u = np.array([hostlib.host_erfinv_fast(float(v)) for v in a], dtype=np.float64)
+    uref = spsp.erfinv(a.astype(np.float64))
+    assert np.abs(u - uref).max() < 3e-6
+    mu, sg = xi_stats['resnet-1.1c/mu'], xi_stats['resnet-1.1c/sigma']
+    rng = np.random.default_rng(5)
+    xb = np.vstack([rng.uniform(1e-6, 1 - 1e-6, (300, 257)), rng.beta(0.3, 0.3, (300, 257)),
+                    np.full((1, 257), 2.0 ** -24), np.full((1, 257), 1 - 2.0 ** -24), np.zeros((1, 257))]).astype(np.float32)
+    G = np.zeros_like(xb)
+    hostlib.host_lsa_from_xbar_fast(P(xb), P(mu), P(sg), xb.shape[0], 257, P(G))
+    xi = cdfmap.normal_cdf_inverse(xb, mu, sg)
+    Gref = gain.gfunc(xi, (xi + np.float32(1.0)).astype(np.float32), 'mmse-lsa')
+    ok = np.isfinite(Gref)
+    assert ok.mean() > 0.99
+    assert np.allclose(G[ok], Gref[ok], rtol=2e-5, atol=1e-30)      # > 90 dB on the waveform
