@@ -36,6 +36,8 @@ UTTS_PER_GPU = 256
 FLOP_PER_FRAME_STAGES = 40 * 2 * (256 * 64 + 3 * 64 * 64 + 64 * 256)     # the 40 residual blocks (tensor cores)
 FLOP_PER_FRAME_TOTAL = 3867648                                           # whole ResNetV2
 STFT_BYTES_PER_FRAME = 512 + 2 * 257 * 4                                 # int16 in, mag + phase out
+TCN_STAGE_BYTES_PER_FRAME = 2 * 1024 + 256 + 256                         # per stage: h read + write (fp32), c1 write, c1 read (once)
+NCU_TCN_STAGE_TRAFFIC = 235.93e6 + 158.85e6                              # dram bytes read + written by one launch (ncu, profiles/)
 RES_KW = dict(d_model=256, n_blocks=40, d_f=64, k=3, max_d_rate=16, unit_type='ReLU->LN->W+b', outp_act='Sigmoid')
 
 
@@ -254,6 +256,12 @@ def run_ours(args, rank, world, local_rank):
     st_per_step = st_n / max(args.steps, 1)          # 41 (one launch per stage) or the number of utterance groups (chained kernel)
     flops_per_launch = frames * FLOP_PER_FRAME_STAGES / max(st_per_step, 1)
     achieved_tf = flops_per_launch / (st_ms_per_launch * 1e-3) / 1e12 if st_n else None
+    # the same launches seen from the memory side: per frame and stage the residual stream is read and written (2 x 1 KB fp32) and
+    # c1 is written once (fp16 hi + lo, 256 B) and fetched from HBM once (256 B; its other two taps are L2 hits)
+    st_bytes_per_launch = frames * TCN_STAGE_BYTES_PER_FRAME * 41.0 / max(st_per_step, 1)
+    st_gbs = st_bytes_per_launch / (st_ms_per_launch * 1e-3) / 1e9 if st_n else None
+    # dram__bytes_read + dram__bytes_write of one launch from the committed ncu --set full capture (C2 shape, one launch per stage)
+    traffic = NCU_TCN_STAGE_TRAFFIC if (frames == 160000 and abs(st_per_step - 41) < 0.5 and args.precision == 'f16x3') else None
     stft_ms, stft_n = prof['stft']
     stft_gbs = frames * STFT_BYTES_PER_FRAME / (stft_ms / max(stft_n, 1) * 1e-3) / 1e9 if stft_n else None
     enh_ms, enh_n = prof['enhance']
@@ -279,7 +287,12 @@ def run_ours(args, rank, world, local_rank):
         'gpu_launches': launches,
         'roofline': {'kernel': 'tcn_stage_kernel (tcgen05 / TMEM, %g launches per step)' % st_per_step, 'bound': 'tensor',
                      'achieved': achieved_tf, 'peak': tf_peak, 'unit': 'TFLOP/s',
-                     'frac': (achieved_tf / tf_peak) if achieved_tf else None, 'traffic': None,
+                     'frac': (achieved_tf / tf_peak) if achieved_tf else None, 'traffic': traffic,
+                     'traffic_source': 'profiles/r01_prof_tcn_stage_final.csv (bytes per launch; algorithmic %.0f)' % st_bytes_per_launch,
+                     'hbm_view': {'bound': 'hbm', 'achieved': st_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+                                  'frac': (st_gbs / hbm_peak) if st_gbs else None, 'bytes_per_frame_and_stage': TCN_STAGE_BYTES_PER_FRAME,
+                                  'note': 'as launched (one stage per launch) the kernel streams the fp32 residual through HBM: '
+                                          'this is the bound that binds today, the tensor figure is the target'},
                      'peak_source': peak_src + ' bf16 sustained (MEASURED_PEAKS.json)',
                      'algorithmic_flop_per_launch': flops_per_launch, 'ms_per_launch': st_ms_per_launch,
                      'share_of_step': st_ms / ms if ms else None,

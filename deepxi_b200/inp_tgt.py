@@ -80,6 +80,53 @@ class MagXi(MagTgt):
         self.xi_map.set_stats(mu, sigma)
         return self
 
+    # -- training-target side ------------------------------------------------------
+    def example(self, s, d, s_len, d_len, snr, offsets=None):
+        """Observation and target of a training batch (inp_tgt.py:173-196): noisy-speech magnitude spectrum x_STMS
+        and mapped a priori SNR xi_bar, both [B, Tmax, 257] (rows beyond an utterance's frame count are the
+        transform of silence), and the frame counts."""
+        so, do, xo, nfr = self.mix(s, d, s_len, d_len, snr, offsets)
+        lens = torch.tensor([int(v) for v in s_len], dtype=torch.int32).to(so.device, non_blocking=True)
+        S, _ = self._stft(so, lens)
+        D, _ = self._stft(do, lens)
+        X, _ = self._stft(xo, lens)
+        mu, sigma = self.xi_map._stats_dev(S.device)
+        xi_bar = torch.empty_like(S)
+        if S.numel():
+            _lib.check(_lib.load().dxi_xi_map(_lib.ptr(S), _lib.ptr(D), _lib.ptr(mu), _lib.ptr(sigma), S.numel() // self.n_feat,
+                                              self.n_feat, None, _lib.ptr(xi_bar), _lib.stream_ptr(S.device)))
+        return X, xi_bar, nfr
+
+    def xi_db_moments(self, s_sample, d_sample, wav_len):
+        """Per-bin (count, sum, sum of squares) of 10 log10 max(xi, 1e-12) over every frame of the sample, float64
+        [3, 257] on the device: the mergeable form of transfrom_stats + xi + NormalCDF.stats (inp_tgt.py:114-139,
+        :160-171; map.py:392-402).  s_sample / d_sample: float32 [N, L] clean speech and scaled noise."""
+        s, _ = to_dev(s_sample, torch.float32)
+        d, _ = to_dev(d_sample, torch.float32)
+        if s.shape != d.shape or s.dim() != 2:
+            raise ValueError('s_sample and d_sample must both be [N, L]')
+        lens_host = [int(v) for v in wav_len]
+        lens = torch.tensor(lens_host, dtype=torch.int32).to(s.device, non_blocking=True)
+        acc = torch.zeros((3, self.n_feat), dtype=torch.float64, device=s.device)
+        if s.shape[0]:
+            S, _ = self._stft(s, lens)
+            D, _ = self._stft(d, lens)
+            nfr = torch.tensor([self.n_frames(n) for n in lens_host], dtype=torch.int32).to(s.device, non_blocking=True)
+            _lib.check(_lib.load().dxi_xi_db_moments(_lib.ptr(S), _lib.ptr(D), _lib.ptr(nfr), S.shape[0], S.shape[1], self.n_feat,
+                                                     _lib.ptr(acc), _lib.stream_ptr(s.device)))
+        return acc
+
+    def stats(self, s_sample, d_sample, x_sample, wav_len, group=None):
+        """Statistics of the a priori SNR in dB for the CDF map (inp_tgt.py:160-171).  When torch.distributed is
+        initialised every rank passes ITS shard of the sample and the moments are summed over the ranks (NCCL
+        all-reduce of 3 x 257 float64 on the GPU, or gloo through the host): all ranks end with the statistics of
+        the whole sample -- the only collective anywhere on a Deep Xi path."""
+        from .stats import allreduce_moments, stats_from_moments
+        acc = allreduce_moments(self.xi_db_moments(s_sample, d_sample, wav_len), group)
+        mu, sigma = stats_from_moments(acc.cpu().numpy())
+        self.set_stats(mu, sigma)
+        return mu, sigma
+
     def xi_hat(self, xi_bar_hat):
         """A priori SNR estimate (inp_tgt.py:216-227)."""
         return self.xi_map.inverse(xi_bar_hat)

@@ -88,3 +88,59 @@ class InputTarget(AnalysisSynthesis):
     def n_frames(self, N):
         """ceil(N / N_s) (sig.py:201-212)."""
         return int(math.ceil(float(N) / float(self.N_s)))
+
+    # -- training-target side (SURVEY 8f row N1) ------------------------------------------------------
+    def xi(self, S, D):
+        """Instantaneous a priori SNR S^2 / max(D^2, 1e-12) (sig.py:110-121)."""
+        S, was_np = to_dev(S, torch.float32)
+        D, _ = to_dev(D, torch.float32)
+        if S.shape != D.shape:
+            raise ValueError('S and D must have the same shape')
+        out = torch.empty_like(S)
+        if S.numel():
+            nb = S.shape[-1]
+            _lib.check(_lib.load().dxi_xi_map(_lib.ptr(S), _lib.ptr(D), None, None, S.numel() // nb, nb, _lib.ptr(out), None,
+                                              _lib.stream_ptr(S.device)))
+        return ret(out, was_np)
+
+    def gamma(self, X, D):
+        """Instantaneous a posteriori SNR X^2 / max(D^2, 1e-12) (sig.py:123-134)."""
+        return self.xi(X, D)
+
+    def mix(self, s, d, s_len, d_len, snr, offsets=None):
+        """Mixes clean speech and noise at the given SNR levels (sig.py:162-187; add_noise_batch / add_noise_pad /
+        add_noise :214-284).  s [B, Ls], d [B, Ld] int16 (padded), s_len / d_len / snr per utterance.
+
+        The reference draws the start of the noise section with tf.random.uniform (sig.py:277); `offsets` passes the
+        draw in (None: numpy's default generator draws it the same way).  Returns s, d, x as float32 CUDA tensors
+        [B, max(s_len)] (zero from s_len on) and the list of frame counts."""
+        s, _ = to_dev(s, torch.int16)
+        d, _ = to_dev(d, torch.int16)
+        if s.dim() != 2 or d.dim() != 2 or s.shape[0] != d.shape[0]:
+            raise ValueError('Waveforms are of incorrect rank.')
+        B = s.shape[0]
+        s_len = [int(v) for v in s_len]
+        d_len = [int(v) for v in d_len]
+        if len(s_len) != B or len(d_len) != B or len(snr) != B:
+            raise ValueError('one s_len, d_len and snr per utterance')
+        if any(dl < sl for sl, dl in zip(s_len, d_len)):
+            raise ValueError('every noise recording must be at least as long as its clean-speech utterance')
+        if offsets is None:
+            import numpy as np
+            rng = np.random.default_rng()
+            offsets = [int(rng.integers(0, 1 + dl - sl)) for sl, dl in zip(s_len, d_len)]
+        if any(o < 0 or o + sl > dl for o, sl, dl in zip(offsets, s_len, d_len)):
+            raise ValueError('noise offset outside [0, d_len - s_len]')
+        dev = s.device
+        L = max(s_len) if B else 0
+        i32 = lambda v: torch.tensor([int(u) for u in v], dtype=torch.int32).to(dev, non_blocking=True)
+        snr_t = torch.tensor([float(u) for u in snr], dtype=torch.float32).to(dev, non_blocking=True)
+        so, do, xo = (torch.empty((B, L), dtype=torch.float32, device=dev) for _ in range(3))
+        if B and L:
+            lib = _lib.load()
+            ws = torch.empty(int(lib.dxi_mix_workspace_bytes(B)), dtype=torch.uint8, device=dev)
+            sl_t, dl_t, of_t = i32(s_len), i32(d_len), i32(offsets)      # named: they must outlive the launch
+            _lib.check(lib.dxi_mix(_lib.ptr(s), _lib.ptr(d), _lib.ptr(sl_t), _lib.ptr(dl_t), _lib.ptr(snr_t),
+                                   _lib.ptr(of_t), B, s.shape[1], d.shape[1], _lib.ptr(so), _lib.ptr(do), _lib.ptr(xo),
+                                   L, _lib.ptr(ws), _lib.stream_ptr(dev)))
+        return so, do, xo, [self.n_frames(n) for n in s_len]

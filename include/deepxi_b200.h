@@ -114,6 +114,35 @@ DXI_API int dxi_gfunc(const float* xi, const float* gamma, int64_t n, int gtype,
 DXI_API int dxi_cdf_map(const float* xi, const float* mu, const float* sigma, int64_t n_rows, int n_bins,
                 float* xbar, void* stream);
 
+/* ---- training-target pipeline ------------------------------------------------------------ */
+
+/*
+ * InputTarget.mix for a padded int16 batch (deepxi/sig.py:162-187, add_noise_pad :231-254, add_noise :256-284):
+ * s / 32768; the noise section d[offset : offset + s_len] / 32768 scaled so that the SNR over the s_len samples is
+ * snr_db; x = s + d.  Outputs are float32 [B, out_stride], zero from s_len on; any of them may be NULL.  The
+ * reference draws `offset` with tf.random.uniform([1], 0, 1 + d_len - s_len) (sig.py:277): here the caller draws it.
+ * workspace: dxi_mix_workspace_bytes(B) bytes of device memory.
+ */
+DXI_API int64_t dxi_mix_workspace_bytes(int B);
+DXI_API int dxi_mix(const int16_t* s, const int16_t* d, const int32_t* s_len, const int32_t* d_len, const float* snr_db,
+            const int32_t* offsets, int B, int64_t s_stride, int64_t d_stride, float* s_out, float* d_out,
+            float* x_out, int64_t out_stride, void* workspace, void* stream);
+
+/* InputTarget.xi (deepxi/sig.py:110-121) = S^2 / max(D^2, 1e-12), optionally fused with NormalCDF.map
+ * (deepxi/map.py:356-371): the tail of MagXi.example (deepxi/inp_tgt.py:192-195).  xi or xi_bar may be NULL. */
+DXI_API int dxi_xi_map(const float* S, const float* D, const float* mu, const float* sigma, int64_t n_rows, int n_bins,
+               float* xi, float* xi_bar, void* stream);
+
+/*
+ * MagXi.stats / NormalCDF.stats (deepxi/inp_tgt.py:160-171, deepxi/map.py:392-402) as mergeable moments:
+ * acc[0][k] += number of frames, acc[1][k] += sum, acc[2][k] += sum of squares of 10 log10 max(xi, 1e-12) over the
+ * first n_frames[b] frames of every utterance (n_frames NULL: all Tmax).  acc: float64 [3][n_bins] on the device,
+ * zeroed by the caller; mu = acc[1] / acc[0], sigma = sqrt(acc[2] / acc[0] - mu^2) (population std).  Shards held by
+ * different GPUs are combined by summing acc (one all-reduce of 3 x n_bins doubles).
+ */
+DXI_API int dxi_xi_db_moments(const float* S, const float* D, const int32_t* n_frames, int B, int Tmax, int n_bins,
+                      double* acc, void* stream);
+
 /*
  * Fused enhancement back end: MagXi.enhanced_speech (deepxi/inp_tgt.py:198-214) =
  * inverse map -> gamma_hat = xi_hat + 1 -> gfunc -> |Y| = |X| G -> polar_synthesis.

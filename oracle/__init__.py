@@ -16,4 +16,4 @@ Parity pinning (see tests/test_oracle_kat.py and DESIGN.md):
     reference artefact that pins them numerically ("parity unpinned" for those; they are
     cross-checked against independent implementations: scipy.special, torch.nn.functional).
 """
-from . import sig, cdfmap, gain, tcn, attention, wavio, pipeline  # noqa: F401
+from . import sig, cdfmap, gain, tcn, attention, wavio, pipeline, train_tgt  # noqa: F401
