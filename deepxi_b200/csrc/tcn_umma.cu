@@ -29,6 +29,7 @@
 // LayerNorm statistics merged with Chan's formula through shared memory).  Warp 16: weight load (bulk async
 // copy), L2 prefetch of the next tile, warp-convergent MMA issue.  GEMM2 is committed in four column groups and
 // GEMM3 is issued in eight K-chunks as the epilogue produces them.
+#include <cstdlib>
 #include <vector>
 #include "net.cuh"
 #include "umma.cuh"
@@ -61,6 +62,7 @@ struct StageArgs {
   int T, tiles_per_utt, n_tiles, Ts;
   int shift0, shift1, shift2;    // frame offsets of the three taps: tap j reads frame t - shift_j
   int has_back, has_front;
+  int reverse;                   // walk this CTA's tiles last-to-first: consecutive stages alternate, so each starts on what the previous one left in L2
   const float2* stem_stats;     // stage 0 only: per-row partial statistics of the stem pre-activation (8 parts of 32 channels);
                                 // the row is then LayerNorm(gamma) + ReLU'd on load (tcn.py:176-179), gamma in the b3 slot
   int dbg_flags;                // tuning experiments only: 1 = skip residual loads, 2 = skip residual stores, 4 = skip c1 tap loads
@@ -135,6 +137,11 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
   // touched before griddepcontrol.wait below.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
+  // this CTA's tiles: blockIdx.x, blockIdx.x + grid, ... in ascending or (p.reverse) descending order
+  const int n_r = (int)blockIdx.x < p.n_tiles ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int tile_step = p.reverse ? -(int)gridDim.x : (int)gridDim.x;
+  const int tile_first = p.reverse ? (int)blockIdx.x + (n_r - 1) * (int)gridDim.x : (int)blockIdx.x;
+
   if (warp == EPI_WARPS) {
     // ================= weight load, L2 prefetch of the next tile, MMA issue =================
     // The whole warp runs this code convergently; single-thread operations elect a lane inside the asm.
@@ -152,10 +159,10 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
     constexpr int NPART = SPLIT ? 3 : 1;          // (a_hi, w_hi) [+ (a_lo, w_hi) + (a_hi, w_lo)]
     uint32_t ph = 0;
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    for (int r = 0, tile = tile_first; r < n_r; ++r, tile += tile_step) {
       {   // pull the next tile's residual rows / c1 rows into L2 ahead of their use
-        const int nt = tile + gridDim.x;
-        if (nt < p.n_tiles) {
+        const int nt = tile + tile_step;
+        if (r + 1 < n_r) {
           const char* hn = reinterpret_cast<const char*>(p.h + (size_t)nt * (TILE * 256));
           if (lane < 8) prefetch_l2(hn + lane * 16384, 16384);
           if (p.has_back && lane >= 16 && lane < (SPLIT ? 32 : 24)) {
@@ -257,8 +264,8 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
     };
 
     asm volatile("griddepcontrol.wait;" ::: "memory");      // the previous launch's h / c1 are complete and visible
-    if (p.has_back && (int)blockIdx.x < p.n_tiles) { load_a1(blockIdx.x); warp_arrive(&bar_a1); }
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    if (p.has_back && n_r > 0) { load_a1(tile_first); warp_arrive(&bar_a1); }
+    for (int r = 0, tile = tile_first; r < n_r; ++r, tile += tile_step) {
       const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TILE;
       const int t = t0 + row;
       const bool valid = t < p.T;
@@ -384,8 +391,8 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
       }
       DXI_STAMP(6);
       // ---- the next tile's c1 taps travel to TMEM while this tile's GEMM3 drains
-      const int next = tile + gridDim.x;
-      const bool has_next = p.has_back && next < p.n_tiles;
+      const int next = tile + tile_step;
+      const bool has_next = p.has_back && r + 1 < n_r;
       if (has_next) load_a1(next);
       DXI_STAMP(7);
       if (p.has_front) {
@@ -808,6 +815,7 @@ int resnet_umma_prepare(dxi_net& net, cudaStream_t st) {
   return DXI_OK;
 }
 
+static bool env_flag(const char* name) { const char* v = getenv(name); return v && *v && *v != '0'; }
 static thread_local long long* g_dbg_clocks = nullptr;
 static thread_local int g_dbg_stage = -1, g_dbg_flags = 0, g_dbg_stop_after = -1;
 
@@ -869,6 +877,7 @@ int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, floa
     a.c1_out = c1[s & 1];
     a.T = T; a.tiles_per_utt = tiles; a.n_tiles = n_tiles; a.Ts = Ts;
     a.has_back = s >= 1; a.has_front = s < c.n_blocks;
+    a.reverse = (s & 1) == 0 && !env_flag("DXI_TCN_NO_REVERSE");      // the stem leaves the last tiles in L2, the output layer starts on the first
     a.dbg = (s == g_dbg_stage) ? g_dbg_clocks : nullptr;
     a.dbg_flags = g_dbg_flags;
     const int d = s >= 1 ? 1 << ((s - 1) % nd) : 1;

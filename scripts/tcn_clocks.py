@@ -25,7 +25,7 @@ print('flags', flags, 'tiles', n_tiles, 'stage', stage, ' total per tile: median
 for i, n in enumerate(names):
     print('%-16s median %7.0f  mean %7.0f  p90 %7.0f' % (n, np.median(d[:, i]), d[:, i].mean(), np.percentile(d[:, i], 90)))
 # tile ownership: chained kernel -> CTA c owns tiles [c m, (c+1) m); per-stage launches -> c, c + 148, ...
-chain = os.environ.get('DXI_TCN_CHAIN', '0') != '0'      # (the chained-kernel experiment is in git history only)
+chain = False      # (the chained-kernel experiment is in git history only; note: odd stages now walk tiles in reverse)
 g = 148
 if chain:
     m = -(-n_tiles // g)
