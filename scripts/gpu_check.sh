@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 echo "== selftest" ; timeout -k 5 300 python -m pytest tests/test_gpu_network.py -q -k umma_selftest --maxfail=50 > gpurun_out/selftest.log 2>&1 ; echo "rc=$?" | tee -a gpurun_out/selftest.log ; tail -15 gpurun_out/selftest.log
-echo "== signal" ; timeout -k 5 600 python -m pytest tests/test_gpu_signal.py -q --maxfail=50 > gpurun_out/signal.log 2>&1 ; echo "rc=$?" | tee -a gpurun_out/signal.log ; tail -30 gpurun_out/signal.log
+echo "== signal" ; timeout -k 5 600 python -m pytest tests/test_gpu_signal.py tests/test_train_tgt.py -m gpu -q --maxfail=50 > gpurun_out/signal.log 2>&1 ; echo "rc=$?" | tee -a gpurun_out/signal.log ; tail -30 gpurun_out/signal.log
 echo "== network" ; timeout -k 5 900 python -m pytest tests/test_gpu_network.py -q -k "not umma_selftest" --maxfail=50 > gpurun_out/network.log 2>&1 ; echo "rc=$?" | tee -a gpurun_out/network.log ; tail -40 gpurun_out/network.log
 echo "== smoke" ; timeout -k 5 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1 ; echo "rc=$?" | tee -a gpurun_out/smoke.log ; tail -5 gpurun_out/smoke.log
 for prec in f16x3 f16 f32; do
