@@ -1,0 +1,295 @@
+// MHANetV3 linear layers on the 5th-generation tensor cores (tcgen05 + TMEM): the four GEMMs of every block
+// (fused QKV projection, output projection + residual + LayerNorm, feed-forward in / out; attention.py:327-353, :88-101)
+// in DXI_PREC_F16X3: both operands split into fp16 hi + lo, three MMAs per product, fp32 accumulate in tensor memory.
+//
+//   out[M, N] = epilogue( A[M, K] (fp32, row-major) x W[K, N] )        K in {256, 1024}, N in {256, 768, 1024}
+//
+// One persistent CTA per SM walks (row tile of 128) x (column tile of 256) output tiles, n fastest, so that the column
+// tiles of one row tile run on neighbouring SMs at the same time and share A through L2.  Warp roles:
+//   warps 0-3  producers: a [128 x 64] chunk of A per step: coalesced float4 loads, hi/lo split, stores into the
+//              128-byte-swizzled K-major shared-memory operand (the layout umma_selftest checks); lane 0 of warp 0 also
+//              starts the bulk copy of the matching pre-packed weight chunk (hi | lo, 64 KB);
+//   warp  8    issues the 12 MMAs of a chunk (M 128 x N 256 x K 16, (a_hi, w_hi) + (a_lo, w_hi) + (a_hi, w_lo)) as soon as
+//              both operands have landed, releases the ring slot with tcgen05.commit;
+//   warps 4-7  epilogue: thread = output row, 256 fp32 columns from TMEM in chunks of 32: bias / ReLU, or
+//              residual + LayerNorm (row statistics by Chan's merge over the 8 chunks, normalised in a second pass
+//              over the tile kept in TMEM); two accumulator buffers, so the epilogue of a tile overlaps the next tile's MMAs.
+// Shared memory: 2 ring slots x (A hi|lo 32 KB + W hi|lo 64 KB) = 192 KB + bias / gamma / beta of the column tile.
+#include <vector>
+#include "net.cuh"
+#include "umma.cuh"
+
+namespace dxi {
+using namespace umma;
+
+constexpr int LM = 128, LNT = 256, LK = 64;
+constexpr int LA_PART = LM * 128;                     // one precision part of an A chunk: [128 rows x 128 B]
+constexpr int LW_PART = LNT * 128;                    // one precision part of a W chunk: [256 rows x 128 B]
+constexpr int L_SLOT = 2 * LA_PART + 2 * LW_PART;     // 96 KB
+constexpr int L_WCHUNK = 2 * LW_PART;                 // packed weight chunk in global memory: hi | lo
+constexpr int L_THREADS = 9 * 32;
+constexpr int L_SMEM = 1024 + 2 * L_SLOT + 3 * LNT * 4;
+enum { LEPI_PLAIN = 0, LEPI_BIAS_RELU = 1, LEPI_RES_LN = 2 };
+
+struct LinArgs {
+  const float* A; int lda;
+  const unsigned char* W;      // packed: [column tile][K chunk][hi 32 KB | lo 32 KB]
+  const float* bias;           // [N] or null
+  const float* res;            // [M][N] (LEPI_RES_LN; N == 256)
+  const float* gamma; const float* beta;
+  float* out; int ldo;
+  int M, N, K, epi;
+};
+
+__global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_a[2], full_w[2], empty[2], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_slot;
+  unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* sVec = reinterpret_cast<float*>(ring + 2 * L_SLOT);      // bias[256], gamma[256], beta[256] of the column tile
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 8) tmem_alloc(&tmem_slot, 512);
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full_a[i], 4); mbar_init(&full_w[i], 1); mbar_init(&empty[i], 1);
+      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tmem_slot != 0) __trap();
+
+  const int n_nt = g.N / LNT, n_mt = (g.M + LM - 1) / LM, n_kc = g.K / LK;
+  const int n_tiles = n_mt * n_nt;
+
+  if (warp < 4) {
+    // ================= producers =================
+    int gch = 0;                                                  // chunk counter of this CTA: ring slot = gch & 1
+    const int c4 = tid & 15, r0 = tid >> 4;                       // float4 column, first row; rows r0 + 8 j
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int mt = t / n_nt, nt = t - mt * n_nt, m0 = mt * LM;
+      for (int kc = 0; kc < n_kc; ++kc, ++gch) {
+        const int slot = gch & 1, use = gch >> 1;
+        if (use >= 1) mbar_wait(&empty[slot], (use - 1) & 1);     // the MMAs that read this slot have completed
+        unsigned char* sA = ring + slot * L_SLOT;
+        if (tid == 0) {
+          mbar_arrive_expect_tx(&full_w[slot], L_WCHUNK);
+          const unsigned char* src = g.W + ((size_t)nt * n_kc + kc) * L_WCHUNK;
+          for (int off = 0; off < L_WCHUNK; off += 16384) bulk_g2s(sA + 2 * LA_PART + off, src + off, 16384, &full_w[slot]);
+        }
+        const float* ap = g.A + (size_t)m0 * g.lda + kc * LK + 4 * c4;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float4 v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r = r0 + 8 * (8 * half + j);
+            v[j] = (m0 + r < g.M) ? __ldg(reinterpret_cast<const float4*>(ap + (size_t)r * g.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int r = r0 + 8 * (8 * half + j);
+            uint32_t h0, l0, h1, l1;
+            split_h2(v[j].x, v[j].y, h0, l0);
+            split_h2(v[j].z, v[j].w, h1, l1);
+            const uint32_t off = (uint32_t)(r >> 3) * 1024 + (r & 7) * 128 + ((((uint32_t)c4 >> 1) ^ (r & 7)) << 4) + (c4 & 1) * 8;
+            *reinterpret_cast<uint2*>(sA + off) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(sA + LA_PART + off) = make_uint2(l0, l1);
+          }
+        }
+        fence_proxy_async();                                       // generic-proxy stores -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_a[slot]);
+      }
+    }
+  } else if (warp == 8) {
+    // ================= MMA issue =================
+    constexpr uint32_t idesc = make_idesc_f16(LM, LNT);
+    int gch = 0, lt = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+      const int buf = lt & 1, u = lt >> 1;
+      if (u >= 1) { mbar_wait(&acc_empty[buf], (u - 1) & 1); tc_fence_after(); }      // the epilogue has drained this accumulator
+      const uint32_t d_col = 256u * buf;
+      for (int kc = 0; kc < n_kc; ++kc, ++gch) {
+        const int slot = gch & 1, use = gch >> 1;
+        mbar_wait(&full_a[slot], use & 1);
+        mbar_wait(&full_w[slot], use & 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(ring + slot * L_SLOT), a_lo = a_hi + LA_PART, w_hi = a_hi + 2 * LA_PART, w_lo = w_hi + LW_PART;
+#pragma unroll
+        for (int part = 0; part < 3; ++part) {
+          const uint32_t a0 = part == 1 ? a_lo : a_hi, w0 = part == 2 ? w_lo : w_hi;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            mma_ss_elect(d_col, make_smem_desc_sw128(a0 + ks * 32), make_smem_desc_sw128(w0 + ks * 32), idesc,
+                         (kc > 0 || part > 0 || ks > 0) ? 1u : 0u);
+        }
+        mma_commit_elect(&empty[slot]);
+      }
+      mma_commit_elect(&acc_full[buf]);
+    }
+  } else {
+    // ================= epilogue (warps 4-7: TMEM lane quarter = warp & 3) =================
+    const int ew = warp & 3, row = ew * 32 + lane, et = tid - 128;      // et: 0..127
+    const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
+    auto epi_sync = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+    int lt = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+      const int mt = t / n_nt, nt = t - mt * n_nt, m = mt * LM + row, n0 = nt * LNT;
+      const int buf = lt & 1, u = lt >> 1;
+      const bool valid = m < g.M;
+      epi_sync();                                                  // previous tile's readers of sVec are done
+      for (int i = et; i < LNT; i += 128) {
+        sVec[i] = g.bias ? __ldg(g.bias + n0 + i) : 0.0f;
+        if (g.epi == LEPI_RES_LN) { sVec[LNT + i] = __ldg(g.gamma + i); sVec[2 * LNT + i] = __ldg(g.beta + i); }
+      }
+      epi_sync();
+      mbar_wait(&acc_full[buf], u & 1); tc_fence_after();
+      const uint32_t d_addr = lane_addr + 256u * buf;
+      float* orow = g.out + (size_t)m * g.ldo + n0;
+      if (g.epi != LEPI_RES_LN) {
+#pragma unroll 1
+        for (int c8 = 0; c8 < 8; ++c8) {
+          float v[32];
+          tmem_ld32(d_addr + 32 * c8, v); tmem_wait_ld();
+          if (valid) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float4 o;
+              o.x = v[4 * q] + sVec[32 * c8 + 4 * q];         o.y = v[4 * q + 1] + sVec[32 * c8 + 4 * q + 1];
+              o.z = v[4 * q + 2] + sVec[32 * c8 + 4 * q + 2]; o.w = v[4 * q + 3] + sVec[32 * c8 + 4 * q + 3];
+              if (g.epi == LEPI_BIAS_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              *reinterpret_cast<float4*>(orow + 32 * c8 + 4 * q) = o;
+            }
+          }
+        }
+      } else {
+        // y = acc + bias + residual, kept in TMEM; LayerNorm(y) * gamma + beta (Keras non-fused order, eps 1e-6)
+        const float* rrow = g.res + (size_t)m * g.N;
+        float mean = 0.0f, m2 = 0.0f;
+#pragma unroll 1
+        for (int c8 = 0; c8 < 8; ++c8) {
+          float v[32];
+          tmem_ld32(d_addr + 32 * c8, v); tmem_wait_ld();
+          float s = 0.0f;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 r4 = valid ? __ldg(reinterpret_cast<const float4*>(rrow + 32 * c8 + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * q] += sVec[32 * c8 + 4 * q] + r4.x;         v[4 * q + 1] += sVec[32 * c8 + 4 * q + 1] + r4.y;
+            v[4 * q + 2] += sVec[32 * c8 + 4 * q + 2] + r4.z; v[4 * q + 3] += sVec[32 * c8 + 4 * q + 3] + r4.w;
+            s += (v[4 * q] + v[4 * q + 1]) + (v[4 * q + 2] + v[4 * q + 3]);
+          }
+          const float mc = s * (1.0f / 32.0f);
+          float qc = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { const float d = v[j] - mc; qc = fmaf(d, d, qc); }
+          // Chan: merge (32 c8 values, mean, m2) with (32 values, mc, qc)
+          const float na = 32.0f * c8, nb = 32.0f, dlt = mc - mean, nn = na + nb;
+          mean += dlt * (nb / nn);
+          m2 += qc + dlt * dlt * (na * nb / nn);
+          tmem_st32(d_addr + 32 * c8, reinterpret_cast<const uint32_t(&)[32]>(v));
+        }
+        tmem_wait_st();
+        const float rstd = rsqrtf(m2 * (1.0f / LNT) + 1e-6f);
+#pragma unroll 1
+        for (int c8 = 0; c8 < 8; ++c8) {
+          float v[32];
+          tmem_ld32(d_addr + 32 * c8, v); tmem_wait_ld();
+          if (valid) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = 32 * c8 + 4 * q + e;
+                const float inv = rstd * sVec[LNT + c];
+                o[e] = fmaf(v[4 * q + e], inv, sVec[2 * LNT + c] - mean * inv);
+              }
+              *reinterpret_cast<float4*>(orow + 32 * c8 + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(0, 512);
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+// W [K][N] fp32 row-major -> [N / 256][K / 64][hi | lo] chunks, each part [256 rows (n) x 128 B (64 k as fp16)], 128-byte swizzle
+static void pack_lin(std::vector<unsigned char>& img, size_t base, const float* W, int K, int N) {
+  const int n_nt = N / LNT, n_kc = K / LK;
+  for (int nt = 0; nt < n_nt; ++nt)
+    for (int kc = 0; kc < n_kc; ++kc) {
+      unsigned char* hi = img.data() + base + ((size_t)nt * n_kc + kc) * L_WCHUNK;
+      unsigned char* lo = hi + LW_PART;
+      for (int n = 0; n < LNT; ++n)
+        for (int kk = 0; kk < LK; ++kk) {
+          const float w = W[(size_t)(kc * LK + kk) * N + nt * LNT + n];
+          const __half h = __float2half_rn(w);
+          const __half l = __float2half_rn(w - __half2float(h));
+          const size_t off = (size_t)(n >> 3) * 1024 + (n & 7) * 128 + (((kk >> 3) ^ (n & 7)) * 16) + (kk & 7) * 2;
+          memcpy(hi + off, &h, 2);
+          memcpy(lo + off, &l, 2);
+        }
+    }
+}
+
+// Packs the 4 x n_blocks weight matrices; net.umma_stage_offset[4 blk + {0: qkv, 1: projection, 2: ffn in, 3: ffn out}]
+int mhanet_umma_prepare(dxi_net& net, cudaStream_t st) {
+  const dxi_net_cfg& c = net.cfg;
+  const int d = c.d_model;
+  if (d != 256) { set_error("tcgen05 MHANetV3 path is built for d_model = 256"); return DXI_E_INVALID; }
+  const size_t sz[4] = {(size_t)d * 3 * d * 4, (size_t)d * d * 4, (size_t)d * 4 * d * 4, (size_t)4 * d * d * 4};   // hi + lo = 4 B per weight
+  std::vector<size_t> offs;
+  size_t total = 0;
+  for (int blk = 0; blk < c.n_blocks; ++blk)
+    for (int i = 0; i < 4; ++i) { offs.push_back(total); total += sz[i]; }
+  std::vector<unsigned char> img(total, 0);
+  for (int blk = 0; blk < c.n_blocks; ++blk) {
+    const int li = 3 + 5 * blk;
+    char nm[64];
+    snprintf(nm, sizeof(nm), "packed-%d/qkv", li);
+    auto it = net.host.find(nm);
+    if (it == net.host.end()) { set_error("packed QKV weights missing"); return DXI_E_STATE; }
+    pack_lin(img, offs[4 * blk + 0], it->second.data(), d, 3 * d);
+    pack_lin(img, offs[4 * blk + 1], net.host_tensor(li, "projection_kernel")->data(), d, d);
+    pack_lin(img, offs[4 * blk + 2], net.host_tensor(li + 2, "kernel")->data(), d, 4 * d);
+    pack_lin(img, offs[4 * blk + 3], net.host_tensor(li + 3, "kernel")->data(), 4 * d, d);
+  }
+  net.umma_stage_offset = offs;
+  if (net.d_umma) { cudaFree(net.d_umma); net.d_umma = nullptr; }
+  DXI_CUDA(cudaMalloc(&net.d_umma, img.size()));
+  DXI_CUDA(cudaMemcpyAsync(net.d_umma, img.data(), img.size(), cudaMemcpyHostToDevice, st));
+  DXI_CUDA(cudaStreamSynchronize(st));      // img is a local
+  net.umma_bytes = img.size();
+  return DXI_OK;
+}
+
+// which: 0 qkv, 1 projection (+ residual + LN), 2 ffn in (bias + ReLU), 3 ffn out (bias + residual + LN)
+int mhanet_umma_linear(const dxi_net& net, int blk, int which, const float* A, int lda, const float* bias, const float* res,
+                       const float* gamma, const float* beta, float* out, int ldo, int M, int N, int K, cudaStream_t st) {
+  if (!net.d_umma || (size_t)(4 * blk + which) >= net.umma_stage_offset.size()) { set_error("tcgen05 weight images missing"); return DXI_E_STATE; }
+  if (N % LNT || K % LK || (lda & 3) || (ldo & 3)) { set_error("lin_umma: unsupported shape"); return DXI_E_INVALID; }
+  LinArgs g{A, lda, reinterpret_cast<const unsigned char*>(net.d_umma) + net.umma_stage_offset[4 * blk + which], bias, res, gamma, beta,
+            out, ldo, M, N, K, (which == 1 || which == 3) ? LEPI_RES_LN : (which == 2 ? LEPI_BIAS_RELU : LEPI_PLAIN)};
+  if (g.epi == LEPI_RES_LN && N != LNT) { set_error("lin_umma: LayerNorm epilogue needs N = 256"); return DXI_E_INVALID; }
+  static bool attr_set = false;
+  if (!attr_set) { DXI_CUDA(cudaFuncSetAttribute(lin_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM)); attr_set = true; }
+  int n_sm = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+  const int tiles = ((M + LM - 1) / LM) * (N / LNT);
+  ProfScope prof("mha_gemm", st, 1);
+  lin_umma_kernel<<<tiles < n_sm ? tiles : n_sm, L_THREADS, L_SMEM, st>>>(g);
+  DXI_LAUNCHED("lin_umma_kernel");
+  return DXI_OK;
+}
+
+}  // namespace dxi

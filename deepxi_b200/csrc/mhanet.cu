@@ -250,7 +250,8 @@ int64_t mhanet_workspace_bytes(const dxi_net& net, int B, int T) {
 int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xbar, void* ws, size_t ws_bytes, cudaStream_t st) {
   const dxi_net_cfg& c = net.cfg;
   if (c.d_model != GN || c.d_model / c.n_heads != HD) { set_error("MHANetV3 path is built for d_model=256, head size 32"); return DXI_E_INVALID; }
-  if (c.precision != DXI_PREC_F32) { set_error("MHANetV3: only precision f32 is built in this round"); return DXI_E_INVALID; }
+  if (c.precision != DXI_PREC_F32 && c.precision != DXI_PREC_F16X3) { set_error("MHANetV3: precisions f32 and f16x3 are built"); return DXI_E_INVALID; }
+  const bool tc = c.precision == DXI_PREC_F16X3;      // the four GEMMs of every block on tcgen05 (mha_umma.cu); first / last layer and attention on the fp32 pipes
   if (T > c.max_len) { set_error("MHANetV3: %d frames exceed the %d rows of the positional embedding (attention.py:432)", T, c.max_len); return DXI_E_INVALID; }
   if ((int64_t)ws_bytes < mhanet_workspace_bytes(net, B, T)) { set_error("workspace too small"); return DXI_E_NOMEM; }
   const int rows = B * T, d = c.d_model;
@@ -275,8 +276,12 @@ int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xb
     snprintf(nm, sizeof(nm), "packed-%d/qkv", li);
     auto it = net.d_offset.find(nm);
     if (it == net.d_offset.end()) { set_error("packed QKV weights missing"); return DXI_E_STATE; }
-    g = GemmArgs{x, d, net.d_arena + it->second, nullptr, nullptr, nullptr, nullptr, nullptr, qkv, 3 * d, rows, 3 * d, d, T, EPI_BIAS};
-    if (int rc = launch_gemm(g, st, "mha_gemm")) return rc;
+    if (tc) {
+      if (int rc = mhanet_umma_linear(net, blk, 0, x, d, nullptr, nullptr, nullptr, nullptr, qkv, 3 * d, rows, 3 * d, d, st)) return rc;
+    } else {
+      g = GemmArgs{x, d, net.d_arena + it->second, nullptr, nullptr, nullptr, nullptr, nullptr, qkv, 3 * d, rows, 3 * d, d, T, EPI_BIAS};
+      if (int rc = launch_gemm(g, st, "mha_gemm")) return rc;
+    }
     {
       dim3 grid((T + AQ - 1) / AQ, c.n_heads, B);
       ProfScope prof("mha_attn", st, 1);
@@ -285,6 +290,11 @@ int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xb
       DXI_LAUNCHED("attn_f32_kernel");
     }
     // a = LN(x + att Wp)      (projection_kernel [8,32,256] is [256][256] row-major as stored)
+    if (tc) {
+      if (int rc = mhanet_umma_linear(net, blk, 1, att, d, nullptr, x, Wt(li + 1, "gamma"), Wt(li + 1, "beta"), a, d, rows, d, d, st)) return rc;
+      if (int rc = mhanet_umma_linear(net, blk, 2, a, d, Wt(li + 2, "bias"), nullptr, nullptr, nullptr, f, 4 * d, rows, 4 * d, d, st)) return rc;      // f = ReLU(a W1 + b1)
+      if (int rc = mhanet_umma_linear(net, blk, 3, f, 4 * d, Wt(li + 3, "bias"), a, Wt(li + 4, "gamma"), Wt(li + 4, "beta"), x, d, rows, d, 4 * d, st)) return rc;      // x = LN(a + f W2 + b2)
+    } else {
     g = GemmArgs{att, d, Wt(li, "projection_kernel"), nullptr, x, Wt(li + 1, "gamma"), Wt(li + 1, "beta"), nullptr, a, d, rows, d, d, T, EPI_RES_LN};
     if (int rc = launch_gemm(g, st, "mha_gemm")) return rc;
     // f = ReLU(a W1 + b1)
@@ -293,6 +303,7 @@ int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xb
     // x = LN(a + f W2 + b2)
     g = GemmArgs{f, 4 * d, Wt(li + 3, "kernel"), Wt(li + 3, "bias"), a, Wt(li + 4, "gamma"), Wt(li + 4, "beta"), nullptr, x, d, rows, d, 4 * d, T, EPI_RES_LN};
     if (int rc = launch_gemm(g, st, "mha_gemm")) return rc;
+    }
     li += 5;
   }
   g = GemmArgs{x, d, Wt(li, "kernel"), Wt(li, "bias"), nullptr, nullptr, nullptr, nullptr, xbar, c.n_outp, rows, c.n_outp, d, T, EPI_SIGMOID};

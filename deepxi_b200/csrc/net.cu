@@ -122,6 +122,9 @@ extern "C" DXI_API int dxi_net_finalize(dxi_net_t* h, void* stream) {
   if (h->kind == DXI_NET_RESNETV2 && h->cfg.precision != DXI_PREC_F32) {
     if (int rc = resnet_umma_prepare(*h, st)) return rc;
   }
+  if (h->kind == DXI_NET_MHANETV3 && h->cfg.precision != DXI_PREC_F32) {
+    if (int rc = mhanet_umma_prepare(*h, st)) return rc;
+  }
   DXI_CUDA(cudaStreamSynchronize(st));
   h->finalized = true;
   return DXI_OK;

@@ -7,7 +7,8 @@ from deepxi_b200.network.selector import network_selector
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 1875
 kw = dict(d_model=256, n_blocks=5, n_heads=8, warmup_steps=40000, max_len=2048, causal=1, outp_act='Sigmoid')
-net = network_selector('MHANetV3', None, 257, **kw).load_weights(weights.synthetic_mhanetv3(0))
+prec = sys.argv[3] if len(sys.argv) > 3 else 'f32'
+net = network_selector('MHANetV3', None, 257, precision=prec, **kw).load_weights(weights.synthetic_mhanetv3(0))
 x = torch.rand(B, T, 257, device='cuda')
 for _ in range(2):
     y = net(x)
@@ -21,5 +22,13 @@ for _ in range(n):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
 flop = B * T * 17.73e6
-print('MHANetV3 %d x %d frames: %.2f ms / forward, %.1f TFLOP/s (17.73 MFLOP/frame unmasked), %.0f audio-s/s, %d launches / forward'
+print(prec, 'MHANetV3 %d x %d frames: %.2f ms / forward, %.1f TFLOP/s (17.73 MFLOP/frame unmasked), %.0f audio-s/s, %d launches / forward'
       % (B, T, ms, flop / ms / 1e9, B * T * 0.016 / (ms / 1e3), _lib.launch_count() // n))
+_lib.profile_enable(True)
+for k in ('mha_gemm', 'mha_attn'):
+    _lib.profile_read(k)
+y = net(x); torch.cuda.synchronize()
+for k in ('mha_gemm', 'mha_attn'):
+    ms_k, n_k = _lib.profile_read(k)
+    print('  %-9s %.2f ms in %d launches' % (k, ms_k, n_k))
+_lib.profile_enable(False)
