@@ -13,6 +13,7 @@
 // attention.py:355-385 (causal AND both frames non-zero) the way tfa applies one (logits += -1e10 (1 - mask)).
 // This is the correctness-first path of round 1; the GEMMs move to tcgen05 next.
 #include <math.h>
+#include <stdlib.h>
 #include "net.cuh"
 
 namespace dxi {
@@ -282,7 +283,9 @@ int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xb
       g = GemmArgs{x, d, net.d_arena + it->second, nullptr, nullptr, nullptr, nullptr, nullptr, qkv, 3 * d, rows, 3 * d, d, T, EPI_BIAS};
       if (int rc = launch_gemm(g, st, "mha_gemm")) return rc;
     }
-    {
+    if (tc && !getenv("DXI_MHA_ATTN_F32")) {
+      if (int rc = mhanet_umma_attention(net, qkv, valid, B, T, att, st)) return rc;
+    } else {
       dim3 grid((T + AQ - 1) / AQ, c.n_heads, B);
       ProfScope prof("mha_attn", st, 1);
       if (c.mask_mode == DXI_MASK_CAUSAL_PAD) attn_f32_kernel<1><<<grid, 256, 0, st>>>(qkv, valid, T, d, att);
