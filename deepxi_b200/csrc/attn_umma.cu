@@ -15,6 +15,7 @@
 #include <math.h>
 #include "net.cuh"
 #include "umma.cuh"
+#include "gain_math.cuh"
 
 namespace dxi {
 using namespace umma;
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_umma_kernel(const AttnArgs 
     // ================= softmax / Q / O : thread = query row =================
     const int row = warp * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    const float scale = rsqrtf((float)AHD);
+    const float scale = rsqrtf((float)AHD) * 1.44269504f;      // q / sqrt(depth), times log2(e): the softmax below works in base 2
     int kt = 0, it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int qt = item % n_qt, bh = item / n_qt, h = bh % g.n_heads, b = bh / g.n_heads;
@@ -98,16 +99,23 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_umma_kernel(const AttnArgs 
           if (MASK && !(kj <= qi && qvalid && vk[c])) return -1e10f;      // logits += -1e10 (1 - mask) absorbs s in fp32
           return s;
         };
+        // interior tiles of the unmasked mode need no per-element tests (every key exists, nothing is masked)
+        const bool plain = !MASK && k0 + AT <= g.T;
         float mx = -INFINITY;
 #pragma unroll 1
         for (int c4 = 0; c4 < 4; ++c4) {
           float s[32];
           tmem_ld32(s_addr + 32 * c4, s); tmem_wait_ld();
+          if (plain) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) mx = fmaxf(mx, logit(s[e], 32 * c4 + e));
+            for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(s[e], s[e + 1]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) mx = fmaxf(mx, logit(s[e], 32 * c4 + e));
+          }
         }
         const float m_new = fmaxf(m_run, mx);
-        const float alpha = (m_run == -INFINITY) ? 0.0f : __expf(m_run - m_new);
+        const float alpha = (m_run == -INFINITY) ? 0.0f : fast_ex2(m_run - m_new);
         if (kt > 0) { mbar_wait(&pv_done, (kt - 1) & 1); tc_fence_after(); }      // P and O are free again
         float psum = 0.0f;
 #pragma unroll 1
@@ -115,12 +123,21 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_umma_kernel(const AttnArgs 
           float s[32];
           tmem_ld32(s_addr + 32 * c4, s); tmem_wait_ld();
           uint32_t hi[16], lo[16];
+          if (plain) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float l0 = logit(s[2 * e], 32 * c4 + 2 * e), l1 = logit(s[2 * e + 1], 32 * c4 + 2 * e + 1);
-            const float p0 = (l0 == -INFINITY) ? 0.0f : __expf(l0 - m_new), p1 = (l1 == -INFINITY) ? 0.0f : __expf(l1 - m_new);
-            psum += p0 + p1;
-            split_h2(p0, p1, hi[e], lo[e]);
+            for (int e = 0; e < 16; ++e) {
+              const float2 pp = make_float2(fast_ex2(s[2 * e] - m_new), fast_ex2(s[2 * e + 1] - m_new));
+              psum += pp.x + pp.y;
+              split_h2x(pp, hi[e], lo[e]);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float l0 = logit(s[2 * e], 32 * c4 + 2 * e), l1 = logit(s[2 * e + 1], 32 * c4 + 2 * e + 1);
+              const float2 pp = make_float2((l0 == -INFINITY) ? 0.0f : fast_ex2(l0 - m_new), (l1 == -INFINITY) ? 0.0f : fast_ex2(l1 - m_new));
+              psum += pp.x + pp.y;
+              split_h2x(pp, hi[e], lo[e]);
+            }
           }
           tmem_st16(lane_addr + AC_PHI + 16 * c4, hi);
           tmem_st16(lane_addr + AC_PLO + 16 * c4, lo);

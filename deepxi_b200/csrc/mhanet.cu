@@ -283,7 +283,7 @@ int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xb
       g = GemmArgs{x, d, net.d_arena + it->second, nullptr, nullptr, nullptr, nullptr, nullptr, qkv, 3 * d, rows, 3 * d, d, T, EPI_BIAS};
       if (int rc = launch_gemm(g, st, "mha_gemm")) return rc;
     }
-    if (tc && !getenv("DXI_MHA_ATTN_F32")) {
+    if (tc && !(getenv("DXI_MHA_ATTN_F32") && atoi(getenv("DXI_MHA_ATTN_F32")))) {
       if (int rc = mhanet_umma_attention(net, qkv, valid, B, T, att, st)) return rc;
     } else {
       dim3 grid((T + AQ - 1) / AQ, c.n_heads, B);

@@ -9,7 +9,7 @@ class MHANetV3(DeviceNetwork):
     kind = 'MHANetV3'
 
     def __init__(self, inp=None, n_outp=257, d_model=256, n_blocks=5, n_heads=8, warmup_steps=40000, max_len=2048,
-                 causal=True, outp_act='Sigmoid', n_feat=257, mask_mode='none', precision='f32'):
+                 causal=True, outp_act='Sigmoid', n_feat=257, mask_mode='none', precision='f16x3'):
         if outp_act != 'Sigmoid':
             if outp_act in ('ReLU', 'Linear'):
                 raise NotImplementedError('only the Sigmoid output activation of the committed models is built')

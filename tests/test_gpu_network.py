@@ -170,6 +170,29 @@ def test_mhanetv3_forward_vs_oracle(xi_stats, mask_mode, precision, tol):
         assert err.max() < tol, (mask_mode, precision, i, err.max())
 
 
+@pytest.mark.parametrize('mask_mode', ['none', 'causal+pad'])
+def test_mhanetv3_tensor_core_path_many_tiles(xi_stats, mask_mode):
+    """f16x3 (tcgen05 GEMMs + attention) against the float64 oracle at a length that needs several query / key tiles,
+    ragged utterances, more work items than one wave: exercises the operand rings, the running-softmax rescale and the
+    causal tile skipping of attn_umma_kernel."""
+    from oracle import attention as oatt
+    mu, sg = xi_stats['mhanet-1.1c/mu'], xi_stats['mhanet-1.1c/sigma']
+    w = weights.synthetic_mhanetv3(2)
+    lens = [150000, 90000, 33333]                                  # 586 / 352 / 131 frames: 5 tiles of 128
+    x = synth.noisy_speech(3, 150000, seed=63)
+    inp, _, nfr = osig.observation_batch(x, lens)
+    ref = oatt.mhanetv3_forward(inp, w, mask_mode=mask_mode, dtype=torch.float64)
+    net = network_selector('MHANetV3', None, 257, mask_mode=mask_mode, precision='f16x3', **MHA_KW).load_weights(w)
+    xbar = net(inp)
+    assert xbar.shape == ref.shape == (3, 586, 257)
+    for i, n in enumerate(nfr):
+        rows = slice(0, n) if mask_mode == 'causal+pad' else slice(0, 586)
+        err = _db_err(xbar[i, rows], ref[i, rows], mu, sg)
+        assert err.max() < 5e-3, (mask_mode, i, err.max())
+    again = net(inp)
+    assert np.array_equal(np.asarray(xbar), np.asarray(again))     # no order-dependent arithmetic anywhere
+
+
 def test_mhanetv3_infer_and_limits(xi_stats):
     w = weights.synthetic_mhanetv3(1)
     dx = DeepXi(512, 256, 512, 16000, 'MagXi', 'MHANetV3', ver='mhanet-1.1c', map_type='DBNormalCDF', map_params=None,
