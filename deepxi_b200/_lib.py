@@ -24,7 +24,7 @@ SYMBOLS = ['dxi_last_error', 'dxi_version', 'dxi_device_check', 'dxi_stft', 'dxi
            'dxi_cdf_map', 'dxi_enhance', 'dxi_net_create', 'dxi_net_load', 'dxi_net_finalize',
            'dxi_net_workspace_bytes', 'dxi_net_forward', 'dxi_net_destroy', 'dxi_launch_count',
            'dxi_launch_count_reset', 'dxi_selftest_umma', 'dxi_profile_enable', 'dxi_profile_read', 'dxi_debug_tcn_clocks', 'dxi_debug_tmem_bw', 'dxi_debug_tcn_stop_after',
-           'dxi_mix_workspace_bytes', 'dxi_mix', 'dxi_xi_map', 'dxi_xi_db_moments']
+           'dxi_mix_workspace_bytes', 'dxi_mix', 'dxi_xi_map', 'dxi_xi_db_moments', 'dxi_subband_ibm']
 
 
 class DxiError(RuntimeError):
@@ -84,7 +84,8 @@ def load():
     lib.dxi_mix.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, i64, vp, vp, vp, i64, vp, vp]
     lib.dxi_xi_map.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp, vp]
     lib.dxi_xi_db_moments.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
-    for name in ('dxi_mix', 'dxi_xi_map', 'dxi_xi_db_moments'):
+    lib.dxi_subband_ibm.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp]
+    for name in ('dxi_mix', 'dxi_xi_map', 'dxi_xi_db_moments', 'dxi_subband_ibm'):
         getattr(lib, name).restype = i32
     for name in ('dxi_stft', 'dxi_istft', 'dxi_map_gain', 'dxi_gfunc', 'dxi_cdf_map', 'dxi_enhance', 'dxi_net_create',
                  'dxi_net_load', 'dxi_net_finalize', 'dxi_net_forward', 'dxi_net_destroy', 'dxi_selftest_umma'):

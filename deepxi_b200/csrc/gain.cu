@@ -105,3 +105,44 @@ extern "C" DXI_API int dxi_cdf_map(const float* xi, const float* mu, const float
   DXI_LAUNCHED("cdf_map_kernel");
   return DXI_OK;
 }
+
+
+// ---- subband IBM: xi_hat [rows, n_bins] x mel filter bank H [M, n_bins]^T -> subband a priori SNR and its
+// mask (deepxi/model.py:323-328, deepxi/sig.py:301-346).  One warp per row: the row is read once (coalesced), every lane keeps
+// ceil(n_bins / 32) values in registers and the M dot products are warp reductions; H (M x n_bins floats, 41 KB for 40 x 257)
+// is read through L1.  HBM-bound: n_bins * 4 B in + M (+ 4 M) B out per row.
+namespace dxi {
+__global__ void __launch_bounds__(256) subband_kernel(const float* __restrict__ xi, const float* __restrict__ H, int64_t n_rows,
+                                                      int n_bins, int M, float* __restrict__ xi_sub, uint8_t* __restrict__ ibm) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); row < n_rows; row += (int64_t)gridDim.x * 8) {
+    float x[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { const int k = lane + 32 * i; x[i] = k < n_bins ? __ldcs(xi + row * n_bins + k) : 0.0f; }
+    for (int m = 0; m < M; ++m) {
+      float a = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) { const int k = lane + 32 * i; if (k < n_bins) a = fmaf(x[i], __ldg(H + (size_t)m * n_bins + k), a); }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) {
+        if (xi_sub) xi_sub[row * M + m] = a;
+        if (ibm) ibm[row * M + m] = a > 1.0f ? 1 : 0;
+      }
+    }
+  }
+}
+}  // namespace dxi
+
+extern "C" DXI_API int dxi_subband_ibm(const float* xi, const float* H, int64_t n_rows, int n_bins, int M, float* xi_sub,
+                               uint8_t* ibm, void* stream) {
+  if (int rc = check_device()) return rc;
+  DXI_REQUIRE(xi && H && (xi_sub || ibm), "dxi_subband_ibm: null argument");
+  DXI_REQUIRE(n_rows >= 0 && n_bins > 0 && n_bins <= 288 && M > 0, "dxi_subband_ibm: bad shape (n_bins <= 288)");
+  if (n_rows == 0) return DXI_OK;
+  const int64_t blocks = (n_rows + 7) / 8;
+  ProfScope prof("subband", as_stream(stream), 1);
+  dxi::subband_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, as_stream(stream)>>>(xi, H, n_rows, n_bins, M, xi_sub, ibm);
+  DXI_LAUNCHED("subband_kernel");
+  return DXI_OK;
+}

@@ -20,8 +20,8 @@ from .inp_tgt import inp_tgt_selector
 from .network.selector import network_selector
 from .utils import save_mat, save_wav, read_mat
 
-_OUT_TYPES = ('y', 'xi_hat', 'gamma_hat', 'gain', 'ibm_hat', 'deepmmse')
-_OTHER_OUT_TYPES = ('mag_hat', 'subband_ibm_hat', 'cd_hat')
+_OUT_TYPES = ('y', 'xi_hat', 'gamma_hat', 'gain', 'ibm_hat', 'deepmmse', 'subband_ibm_hat')
+_OTHER_OUT_TYPES = ('mag_hat', 'cd_hat')
 
 
 class DeepXi:
@@ -72,7 +72,7 @@ class DeepXi:
         return self.inp_tgt.observation_batch(x_batch, x_batch_len)
 
     # ------------------------------------------------------------------------------------------
-    def infer_batch(self, test_x, test_x_len, out_type='y', gain='mmse-lsa', int16=False):
+    def infer_batch(self, test_x, test_x_len, out_type='y', gain='mmse-lsa', int16=False, n_filters=40):
         """One batch through the hot path; returns (output device tensor [B, ...], n_frames list).
 
         'y' -> [B, (Tmax+1)*256] waveform (float32, or int16 with the save_wav rule); the others
@@ -94,6 +94,8 @@ class DeepXi:
             out = it.gain_hat(xbar, gain)
         elif out_type == 'ibm_hat':
             out = it.ibm_hat(xbar)
+        elif out_type == 'subband_ibm_hat':      # (xi_hat H^T) > 1 with the mel filter bank (model.py:255-258, :323-328)
+            out = it.subband(it.xi_hat(xbar), n_filters)[1]
         else:  # deepmmse: |X|^2 * G_deepmmse(xi_hat, xi_hat + 1)   (model.py:314-318)
             out = inp * inp * it.gain_hat(xbar, 'deepmmse')
         return out, n_frames
@@ -113,6 +115,7 @@ class DeepXi:
                 elif out_type == 'y': out_path = out_path + '/y/' + g
                 elif out_type == 'deepmmse': out_path = out_path + '/deepmmse'
                 elif out_type == 'ibm_hat': out_path = out_path + '/ibm_hat'
+                elif out_type == 'subband_ibm_hat': out_path = out_path + '/subband_ibm_hat'
                 elif out_type == 'gain': out_path = out_path + '/gain/' + g
                 elif out_type in _OTHER_OUT_TYPES:
                     raise NotImplementedError('out_type %r belongs to targets without committed models' % out_type)
@@ -120,10 +123,10 @@ class DeepXi:
                 if not os.path.exists(out_path): os.makedirs(out_path)
                 if self._weights_epoch != 'explicit' and self._weights_epoch != (model_path, e - 1):
                     self.load_weights(model_path, e - 1)
-                out, n_frames = self.infer_batch(test_x, test_x_len, out_type, g, int16=(out_type == 'y'))
+                out, n_frames = self.infer_batch(test_x, test_x_len, out_type, g, int16=(out_type == 'y'), n_filters=n_filters)
                 out = out.cpu().numpy()
                 key = {'xi_hat': 'xi_hat', 'gamma_hat': 'gamma_hat', 'gain': 'gain', 'ibm_hat': 'ibm_hat',
-                       'deepmmse': 'd_psd_hat'}.get(out_type)
+                       'deepmmse': 'd_psd_hat', 'subband_ibm_hat': 'subband_ibm_hat'}.get(out_type)
                 for i, base_name in enumerate(test_x_base_names):
                     if out_type == 'y':
                         # polar_synthesis length (T-1)*N_s + N_d of the un-padded utterance (inp_tgt.py:198-214)

@@ -89,6 +89,53 @@ class InputTarget(AnalysisSynthesis):
         """ceil(N / N_s) (sig.py:201-212)."""
         return int(math.ceil(float(N) / float(self.N_s)))
 
+    # -- mel filter bank for the subband IBM output (SURVEY 8f row N4) ---------------------------------
+    def hz_to_mel(self, f):
+        """sig.py:348-358."""
+        import numpy as np
+        return 2595 * np.log10(1 + (f / 700))
+
+    def mel_to_hz(self, m):
+        """sig.py:360-370."""
+        return 700 * ((10 ** (m / 2595)) - 1)
+
+    def bpoint(self, m, M, f_l, f_h):
+        """Frequency-bin boundary point of filter m (sig.py:332-346)."""
+        K = self.K // 2 + 1
+        return ((2 * K) / self.f_s) * self.mel_to_hz(self.hz_to_mel(f_l) + m * ((self.hz_to_mel(f_h) - self.hz_to_mel(f_l)) / (M + 1)))
+
+    def mel_filter_bank(self, M):
+        """Triangular mel filter bank [M, K/2+1] whose filters sum to unity (sig.py:301-330); host-side, built once."""
+        import numpy as np
+        f_l, f_h = 0, self.f_s / 2
+        K = self.K // 2 + 1
+        H = np.zeros([M, K], dtype=np.float32)
+        for m in range(1, M + 1):
+            bl, c, bh = self.bpoint(m - 1, M, f_l, f_h), self.bpoint(m, M, f_l, f_h), self.bpoint(m + 1, M, f_l, f_h)
+            for k in range(K):
+                if k >= bl and k <= c:
+                    H[m - 1, k] = (2 * (k - bl)) / ((bh - bl) * (c - bl))
+                if k >= c and k <= bh:
+                    H[m - 1, k] = (2 * (bh - k)) / ((bh - bl) * (bh - c))
+        return H
+
+    def subband(self, xi, n_filters=40, want_mask=True):
+        """xi [..., 257] -> subband a priori SNR xi H^T [..., n_filters] (and its mask > 1): model.py:323-328."""
+        import numpy as np
+        xi, was_np = to_dev(xi, torch.float32)
+        cache = self.__dict__.setdefault('_mel_cache', {})
+        key = (n_filters, str(xi.device))
+        if key not in cache:
+            cache[key] = torch.from_numpy(np.ascontiguousarray(self.mel_filter_bank(n_filters))).to(xi.device)
+        H = cache[key]
+        rows = xi.numel() // self.n_bins
+        sub = torch.empty(xi.shape[:-1] + (n_filters,), dtype=torch.float32, device=xi.device)
+        ibm = torch.empty(sub.shape, dtype=torch.uint8, device=xi.device) if want_mask else None
+        if rows:
+            _lib.check(_lib.load().dxi_subband_ibm(_lib.ptr(xi), _lib.ptr(H), rows, self.n_bins, n_filters, _lib.ptr(sub),
+                                                   _lib.ptr(ibm, allow_none=True), _lib.stream_ptr(xi.device)))
+        return ret(sub, was_np), (ret(ibm.bool(), was_np) if want_mask else None)
+
     # -- training-target side (SURVEY 8f row N1) ------------------------------------------------------
     def xi(self, S, D):
         """Instantaneous a priori SNR S^2 / max(D^2, 1e-12) (sig.py:110-121)."""

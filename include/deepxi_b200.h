@@ -114,6 +114,11 @@ DXI_API int dxi_gfunc(const float* xi, const float* gamma, int64_t n, int gtype,
 DXI_API int dxi_cdf_map(const float* xi, const float* mu, const float* sigma, int64_t n_rows, int n_bins,
                 float* xbar, void* stream);
 
+/* Subband a priori SNR and its ideal binary mask (deepxi/model.py:323-328 with the mel filter bank of deepxi/sig.py:301-346):
+ * xi_sub[r][m] = sum_k xi[r][k] H[m][k], ibm = xi_sub > 1.  H: float32 [M][n_bins] on the device; xi_sub or ibm may be NULL. */
+DXI_API int dxi_subband_ibm(const float* xi, const float* H, int64_t n_rows, int n_bins, int M, float* xi_sub,
+                    uint8_t* ibm, void* stream);
+
 /* ---- training-target pipeline ------------------------------------------------------------ */
 
 /*

@@ -99,3 +99,28 @@ def observation_batch(x_batch, x_batch_len, N_d=512, N_s=256, K=512):
         inp[i, :nfr[i]] = m
         sup[i, :nfr[i]] = p
     return inp, sup, nfr
+
+
+def mel_filter_bank(M, K=512, f_s=16000):
+    """InputTarget.mel_filter_bank / bpoint / hz_to_mel / mel_to_hz (deepxi/sig.py:301-370): triangular filters that sum to
+    unity, [M, K/2+1] float32."""
+    hz_to_mel = lambda f: 2595 * np.log10(1 + (f / 700))
+    mel_to_hz = lambda m: 700 * ((10 ** (m / 2595)) - 1)
+    nb = K // 2 + 1
+    f_l, f_h = 0, f_s / 2
+    bpoint = lambda m: ((2 * nb) / f_s) * mel_to_hz(hz_to_mel(f_l) + m * ((hz_to_mel(f_h) - hz_to_mel(f_l)) / (M + 1)))
+    H = np.zeros([M, nb], dtype=np.float32)
+    for m in range(1, M + 1):
+        bl, c, bh = bpoint(m - 1), bpoint(m), bpoint(m + 1)
+        for k in range(nb):
+            if bl <= k <= c:
+                H[m - 1, k] = (2 * (k - bl)) / ((bh - bl) * (c - bl))
+            if c <= k <= bh:
+                H[m - 1, k] = (2 * (bh - k)) / ((bh - bl) * (bh - c))
+    return H
+
+
+def subband_ibm(xi_hat, M=40, K=512, f_s=16000):
+    """(xi_hat H^T, its mask > 1): deepxi/model.py:323-328."""
+    sub = np.matmul(np.asarray(xi_hat, np.float32), mel_filter_bank(M, K, f_s).transpose())
+    return sub, np.greater(sub, 1.0)

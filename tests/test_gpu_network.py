@@ -100,6 +100,11 @@ def test_infer_out_types_vs_oracle(xi_stats, tmp_path):
     g, _ = dx.infer_batch(x, lens, 'gain', 'mmse-lsa')
     ref_g = pipeline.infer(x, lens, w, mu, sg, out_type='gain', gtype='mmse-lsa')
     assert np.allclose(g.cpu().numpy()[0, :nfr[0]], ref_g[0], rtol=2e-2)
+    sb, _ = dx.infer_batch(x, lens, 'subband_ibm_hat', n_filters=40)          # model.py:323-328 on the mel filter bank
+    sb = sb.cpu().numpy()
+    ref_sub, ref_sb = osig.subband_ibm(xi[0, :nfr[0]], 40)
+    sure = np.abs(ref_sub - 1.0) > 1e-4
+    assert sb.shape == (2, nfr[0], 40) and np.array_equal(sb[0, :nfr[0]][sure], ref_sb[sure])
     with pytest.raises(ValueError, match='Invalid output type.'):
         dx.infer_batch(x, lens, 'bogus')
     # file outputs with the reference's directory layout (model.py:264-276)

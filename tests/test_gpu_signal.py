@@ -172,3 +172,18 @@ def test_enhanced_speech_fused_vs_oracle(xi_stats, gtype):
         assert not y[i, (n + 1) * 256:].any()           # beyond the utterance: silence
         di = np.abs(yi[i, :(n + 1) * 256].astype(np.int32) - wavio.float_to_int16(ref).astype(np.int32))
         assert di.max() <= 1
+
+
+def test_subband_ibm_matches_oracle(xi_stats):
+    """xi_hat -> mel-subband a priori SNR -> mask (deepxi/model.py:323-328, sig.py:301-346)."""
+    it = inp_tgt_selector('MagXi', 512, 256, 512, 16000, map_type='DBNormalCDF', map_params=None)
+    rng = np.random.default_rng(11)
+    xi = (10.0 ** rng.uniform(-3, 3, (3, 77, 257))).astype(np.float32)
+    sub, ibm = it.subband(xi, 40)
+    r_sub, r_ibm = osig.subband_ibm(xi, 40)
+    assert sub.shape == r_sub.shape == (3, 77, 40) and ibm.dtype == np.bool_
+    assert np.allclose(sub, r_sub, rtol=2e-6)                     # different summation order of the 257-term dot products
+    sure = np.abs(r_sub - 1.0) > 1e-5                              # the mask can only differ where the sum sits on the threshold
+    assert np.array_equal(ibm[sure], r_ibm[sure])
+    sub24, _ = it.subband(xi[0], 24, want_mask=False)
+    assert np.allclose(sub24, osig.subband_ibm(xi[0], 24)[0], rtol=2e-6)

@@ -144,3 +144,15 @@ def test_synthetic_inputs_are_seeded():
     a = synth.noisy_speech(2, 4000, seed=7)
     b = synth.noisy_speech(2, 4000, seed=7)
     assert a.dtype == np.int16 and np.array_equal(a, b) and np.abs(a).max() > 1000
+
+
+def test_mel_filter_bank_mirror_equals_oracle():
+    """Host-side mirror of InputTarget.mel_filter_bank (sig.py:301-346) against the oracle's restatement."""
+    from deepxi_b200.sig import InputTarget
+    from oracle import sig as osig
+    it = InputTarget(512, 256, 512, 16000)
+    for M in (24, 40):
+        H = it.mel_filter_bank(M)
+        assert H.shape == (M, 257) and H.dtype == np.float32
+        assert np.array_equal(H, osig.mel_filter_bank(M))
+        assert (H >= 0).all() and np.all(np.diff(H.argmax(axis=1)) > 0)      # triangular, centres increase
