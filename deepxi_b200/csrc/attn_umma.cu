@@ -10,8 +10,11 @@
 //   O += P V    : M 128 x N 32 x K 128, V^T tile (hi | lo) in shared memory.
 // Warps 0-3: softmax (TMEM lane quarter = warp).  Warps 4-7: load K / V tiles (fp32 from the fused QKV activations), split
 // and lay them out as K-major UMMA operands (8 x 16-byte core matrices, no swizzle; V goes through a transposing stage).
-// Warp 8: MMA issue; S of tile j+1 is issued before P V of tile j so the tensor core works while the softmax runs.
-// TMEM columns: S0 [0,128) S1 [128,256) P hi [256,320) lo [320,384) O [384,416) Q hi [416,432) lo [432,448).
+// Warp 8: MMA issue.  A CTA needs only 192 TMEM columns (it allocates 256) and 83 KB of shared memory, so TWO CTAs share an
+// SM: while one waits for its 4 softmax warps the tensor core serves the other (the single-CTA version with two S buffers
+// took 4.8 k cycles per key tile against 0.8 k of tensor work).
+// TMEM columns (relative to the allocation): S [0,128), overwritten IN PLACE by P (chunk of 32 fp32 columns -> 16 columns of
+// fp16 hi pairs + 16 of lo pairs); O [128,160); Q hi [160,176) lo [176,192).
 #include <math.h>
 #include "net.cuh"
 #include "umma.cuh"
@@ -21,7 +24,7 @@ namespace dxi {
 using namespace umma;
 
 constexpr int AT = 128, AHD = 32;
-constexpr uint32_t AC_S = 0, AC_PHI = 256, AC_PLO = 320, AC_O = 384, AC_QHI = 416, AC_QLO = 432;
+constexpr uint32_t AC_S = 0, AC_O = 128, AC_QHI = 160, AC_QLO = 176, A_TMEM_COLS = 256;
 constexpr int AK_PART = AT * AHD * 2;                  // 8 KB: one precision part of a K tile / of a V^T tile
 constexpr int A_SLOT = 4 * AK_PART;                    // K hi | K lo | V^T hi | V^T lo
 constexpr int A_STAGE_LD = AHD + 1;
@@ -36,24 +39,24 @@ struct AttnArgs {
 };
 
 template <int MASK>
-__global__ void __launch_bounds__(A_THREADS, 1) attn_umma_kernel(const AttnArgs g) {
+__global__ void __launch_bounds__(A_THREADS, 2) attn_umma_kernel(const AttnArgs g) {
   extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t kv_full[2], kv_empty[2], s_full[2], q_full, p_ready, pv_done;
+  __shared__ __align__(8) uint64_t kv_full[2], kv_empty[2], s_full, q_full, p_ready, pv_done;
   __shared__ uint32_t tmem_slot;
   unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* vstage = reinterpret_cast<float*>(ring + 2 * A_SLOT);
   uint8_t* sValid = reinterpret_cast<uint8_t*>(vstage + AT * A_STAGE_LD);       // [2][128]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (warp == 8) tmem_alloc(&tmem_slot, 512);
+  if (warp == 8) tmem_alloc(&tmem_slot, A_TMEM_COLS);
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 4); mbar_init(&kv_empty[i], 1); mbar_init(&s_full[i], 1); }
-    mbar_init(&q_full, 4); mbar_init(&p_ready, 4); mbar_init(&pv_done, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 4); mbar_init(&kv_empty[i], 1); }
+    mbar_init(&s_full, 1); mbar_init(&q_full, 4); mbar_init(&p_ready, 4); mbar_init(&pv_done, 1);
     fence_mbar_init();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (tmem_slot != 0) __trap();
+  const uint32_t tbase = tmem_slot;      // two CTAs per SM: the allocation does not start at column 0
 
   const int n_qt = (g.T + AT - 1) / AT;
   const int n_items = g.B * g.n_heads * n_qt;
@@ -64,7 +67,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_umma_kernel(const AttnArgs 
   if (warp < 4) {
     // ================= softmax / Q / O : thread = query row =================
     const int row = warp * 32 + lane;
-    const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_addr = tbase + ((uint32_t)(warp * 32) << 16);
     const float scale = rsqrtf((float)AHD) * 1.44269504f;      // q / sqrt(depth), times log2(e): the softmax below works in base 2
     int kt = 0, it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -89,9 +92,9 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_umma_kernel(const AttnArgs 
       float m_run = -INFINITY, l_run = 0.0f;
       const int nk = n_ktiles(qt);
       for (int j = 0; j < nk; ++j, ++kt) {
-        const int buf = kt & 1, k0 = j * AT;
-        mbar_wait(&s_full[buf], (kt >> 1) & 1); tc_fence_after();
-        const uint32_t s_addr = lane_addr + AC_S + 128u * buf;
+        const int k0 = j * AT;
+        mbar_wait(&s_full, kt & 1); tc_fence_after();
+        const uint32_t s_addr = lane_addr + AC_S;
         const uint8_t* vk = sValid + (kt & 1) * AT;
         auto logit = [&](float s, int c) -> float {          // c: key index inside the tile
           const int kj = k0 + c;
@@ -139,8 +142,8 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_umma_kernel(const AttnArgs 
               split_h2x(pp, hi[e], lo[e]);
             }
           }
-          tmem_st16(lane_addr + AC_PHI + 16 * c4, hi);
-          tmem_st16(lane_addr + AC_PLO + 16 * c4, lo);
+          tmem_st16(s_addr + 32 * c4, hi);             // in place: this chunk's logits are in registers
+          tmem_st16(s_addr + 32 * c4 + 16, lo);
         }
         l_run = l_run * alpha + psum;
         m_run = m_new;
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_umma_kernel(const AttnArgs 
   } else {
     // ================= MMA issue =================
     constexpr uint32_t id_s = make_idesc_f16(AT, AT), id_o = make_idesc_f16(AT, AHD);
-    auto issue_s = [&](int ktile) {      // S[ktile & 1] = Q K^T
+    auto issue_s = [&](int ktile) {      // S = Q K^T (issued behind the previous tile's P V: the tensor pipe runs in order)
       const int slot = ktile & 1;
       mbar_wait(&kv_full[slot], (ktile >> 1) & 1); tc_fence_after();
       const uint32_t k_hi = smem_u32(ring + slot * A_SLOT), k_lo = k_hi + AK_PART;
@@ -238,27 +241,27 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_umma_kernel(const AttnArgs 
         const uint32_t a0 = part == 1 ? AC_QLO : AC_QHI, b0 = part == 2 ? k_lo : k_hi;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
-          mma_ts_elect(AC_S + 128u * slot, a0 + 8 * ks, make_smem_desc_noswz(b0 + ks * 256, 128, 512), id_s, (part > 0 || ks > 0) ? 1u : 0u);
+          mma_ts_elect(tbase + AC_S, tbase + a0 + 8 * ks, make_smem_desc_noswz(b0 + ks * 256, 128, 512), id_s, (part > 0 || ks > 0) ? 1u : 0u);
       }
-      mma_commit_elect(&s_full[slot]);
+      mma_commit_elect(&s_full);
     };
     int kt = 0, it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int qt = item % n_qt;
       const int nk = n_ktiles(qt);
       mbar_wait(&q_full, it & 1); tc_fence_after();
-      issue_s(kt);
       for (int j = 0; j < nk; ++j, ++kt) {
-        if (j + 1 < nk) issue_s(kt + 1);
+        issue_s(kt);
         mbar_wait(&p_ready, kt & 1); tc_fence_after();
         const int slot = kt & 1;
         const uint32_t v_hi = smem_u32(ring + slot * A_SLOT) + 2 * AK_PART, v_lo = v_hi + AK_PART;
 #pragma unroll
         for (int part = 0; part < 3; ++part) {
-          const uint32_t a0 = part == 1 ? AC_PLO : AC_PHI, b0 = part == 2 ? v_lo : v_hi;
+          const uint32_t b0 = part == 2 ? v_lo : v_hi;
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            mma_ts_elect(AC_O, a0 + 8 * ks, make_smem_desc_noswz(b0 + ks * 256, 128, 2048), id_o, (j > 0 || part > 0 || ks > 0) ? 1u : 0u);
+          for (int ks = 0; ks < 8; ++ks)      // keys 16 ks ..: chunk ks >> 1, hi pairs at 32 c + 8 (ks & 1), lo pairs 16 columns further
+            mma_ts_elect(tbase + AC_O, tbase + AC_S + 32 * (ks >> 1) + 8 * (ks & 1) + (part == 1 ? 16 : 0),
+                         make_smem_desc_noswz(b0 + ks * 256, 128, 2048), id_o, (j > 0 || part > 0 || ks > 0) ? 1u : 0u);
         }
         mma_commit_elect(&kv_empty[slot]);
         mma_commit_elect(&pv_done);
@@ -267,7 +270,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_umma_kernel(const AttnArgs 
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(0, 512);
+  if (warp == 8) tmem_dealloc(tbase, A_TMEM_COLS);
 }
 
 int mhanet_umma_attention(const dxi_net& net, const float* qkv, const uint8_t* valid, int B, int T, float* att, cudaStream_t st) {
@@ -283,7 +286,7 @@ int mhanet_umma_attention(const dxi_net& net, const float* qkv, const uint8_t* v
   int n_sm = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   const int items = B * c.n_heads * ((T + AT - 1) / AT);
-  const int grid = items < n_sm ? items : n_sm;
+  const int grid = items < 2 * n_sm ? items : 2 * n_sm;      // two CTAs per SM
   ProfScope prof("mha_attn", st, 1);
   if (c.mask_mode == DXI_MASK_CAUSAL_PAD) attn_umma_kernel<1><<<grid, A_THREADS, A_SMEM, st>>>(a);
   else attn_umma_kernel<0><<<grid, A_THREADS, A_SMEM, st>>>(a);
