@@ -245,3 +245,24 @@ def test_resnetv2_repeatable_after_a_larger_batch():
             big = net(inp)
             assert torch.equal(net(small), ref)
             assert torch.equal(big[:3, :T], ref)
+
+
+def test_cli_main_writes_the_reference_layout(tmp_path):
+    """python -m deepxi_b200.main with run.sh's flags: out/<ver>/e<epoch>/y/<gain>/<name>.wav and .mat outputs."""
+    from deepxi_b200 import main as cli, utils
+    src = tmp_path / 'noisy'
+    src.mkdir()
+    x = synth.noisy_speech(2, 12000, seed=77)
+    for i, n in enumerate((12000, 7000)):
+        utils.save_wav(str(src / ('utt%d.wav' % i)), x[i, :n], 16000)
+    base = ('--ver resnet-1.1c --network_type ResNetV2 --d_model 256 --n_blocks 40 --d_f 64 --k 3 --max_d_rate 16 --causal 1 '
+            '--unit_type ReLU->LN->W+b --outp_act Sigmoid --test_epoch 200 --inp_tgt_type MagXi --map_type DBNormalCDF --f_s 16000 '
+            '--T_d 32 --T_s 16 --min_snr -10 --max_snr 20 --snr_inter 1 --infer 1 --synthetic_weights 0').split()
+    base += ['--test_x_path', str(src), '--out_path', str(tmp_path / 'out')]
+    assert cli.main(base + ['--out_type', 'y', '--gain', 'mmse-lsa,srwf']) == 0
+    for g in ('mmse-lsa', 'srwf'):
+        y, fs = utils.read_wav(str(tmp_path / 'out' / 'resnet-1.1c' / 'e200' / 'y' / g / 'utt1.wav'))
+        assert fs == 16000 and len(y) == (28 + 1) * 256 and np.abs(y.astype(np.int32)).max() > 0
+    assert cli.main(base + ['--out_type', 'subband_ibm_hat', '--gain', 'mmse-lsa', '--n_filters', '24']) == 0
+    m = utils.read_mat(str(tmp_path / 'out' / 'resnet-1.1c' / 'e200' / 'subband_ibm_hat' / 'utt0.mat'))['subband_ibm_hat']
+    assert m.shape == (47, 24)

@@ -156,3 +156,24 @@ def test_mel_filter_bank_mirror_equals_oracle():
         assert H.shape == (M, 257) and H.dtype == np.float32
         assert np.array_equal(H, osig.mel_filter_bank(M))
         assert (H >= 0).all() and np.all(np.diff(H.argmax(axis=1)) > 0)      # triangular, centres increase
+
+
+def test_cli_flags_mirror_run_sh():
+    """deepxi_b200.args parses the flag set run.sh passes for VER=resnet-1.1c INFER=1 (run.sh:98-140, main.py:12-60) the way
+    deepxi/args.py does (str_to_bool / str_to_list / read_dtype)."""
+    from deepxi_b200 import args as A, main as M
+    argv = ('--ver resnet-1.1c --network_type ResNetV2 --d_model 256 --n_blocks 40 --d_f 64 --k 3 --max_d_rate 16 --causal 1 '
+            '--unit_type ReLU->LN->W+b --loss_fnc BinaryCrossentropy --outp_act Sigmoid --max_epochs 200 --resume_epoch 0 '
+            '--test_epoch 200 --mbatch_size 8 --inp_tgt_type MagXi --map_type DBNormalCDF --sample_size 1000 --f_s 16000 --T_d 32 '
+            '--T_s 16 --min_snr -10 --max_snr 20 --snr_inter 1 --out_type y --gain mmse-lsa,mmse-stsa --infer 1 --gpu 0').split()
+    a = A.get_args(argv)
+    assert a.infer is True and a.train is False and a.causal is True and a.val_flag is True
+    assert a.test_epoch == 200 and a.gain == ['mmse-lsa', 'mmse-stsa'] and a.map_type == 'DBNormalCDF'
+    assert a.map_params == [None, None] and a.out_path == 'out' and a.test_x_path == 'set/test_noisy_speech'
+    assert A.str_to_list('1,2;3,4') == [[1, 2], [3, 4]] and A.str_to_list('neg_5,0.5') == [-5, 0.5] and A.read_dtype('pi') > 3.14
+    a.padding = 'causal'
+    kw = M.network_kwargs(a)
+    assert kw == dict(d_model=256, n_blocks=40, d_f=64, k=3, max_d_rate=16, padding='causal', unit_type='ReLU->LN->W+b',
+                      outp_act='Sigmoid', precision='f16x3')
+    with pytest.raises(NotImplementedError):
+        M.main(argv[:-4] + ['--train', '1'])
