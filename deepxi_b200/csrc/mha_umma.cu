@@ -28,8 +28,9 @@ constexpr int LW_PART = LNT * 128;                    // one precision part of a
 constexpr int L_SLOT = 2 * LA_PART + 2 * LW_PART;     // 96 KB
 constexpr int L_WCHUNK = 2 * LW_PART;                 // packed weight chunk in global memory: hi | lo
 constexpr int L_THREADS = 9 * 32;
-constexpr int L_SMEM = 1024 + 2 * L_SLOT + 3 * LNT * 4;
-enum { LEPI_PLAIN = 0, LEPI_BIAS_RELU = 1, LEPI_RES_LN = 2 };
+constexpr int L_STAGE_LD = 33;
+constexpr int L_SMEM = 1024 + 2 * L_SLOT + 3 * LNT * 4 + LM * L_STAGE_LD * 4;
+enum { LEPI_PLAIN = 0, LEPI_BIAS_RELU = 1, LEPI_RES_LN = 2, LEPI_SIGMOID = 3 };
 
 struct LinArgs {
   const float* A; int lda;
@@ -37,8 +38,10 @@ struct LinArgs {
   const float* bias;           // [N] or null
   const float* res;            // [M][N] (LEPI_RES_LN; N == 256)
   const float* gamma; const float* beta;
+  const float* pos; int T;     // LEPI_RES_LN without residual: ReLU, then + pos[m % T][:] (input layer, attention.py:428-433)
   float* out; int ldo;
-  int M, N, K, epi;
+  int M, N, K, epi;            // N, K: padded to multiples of 256 / 64 (the packed weights carry the zeros)
+  int Nr, Kr;                  // real sizes (Kr = 257 for the input layer, Nr = 257 for the output layer)
 };
 
 __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g) {
@@ -47,6 +50,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
   __shared__ uint32_t tmem_slot;
   unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* sVec = reinterpret_cast<float*>(ring + 2 * L_SLOT);      // bias[256], gamma[256], beta[256] of the column tile
+  float* sStage = sVec + 3 * LNT;                                 // [128][33]: row-major re-ordering of a 32-column chunk (unaligned outputs)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 8) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
@@ -80,13 +84,22 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
           for (int off = 0; off < L_WCHUNK; off += 16384) bulk_g2s(sA + 2 * LA_PART + off, src + off, 16384, &full_w[slot]);
         }
         const float* ap = g.A + (size_t)m0 * g.lda + kc * LK + 4 * c4;
+        const bool vec = (g.lda & 3) == 0 && (kc + 1) * LK <= g.Kr;      // else: rows not 16-byte aligned / ragged K (input layer)
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           float4 v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int r = r0 + 8 * (8 * half + j);
-            v[j] = (m0 + r < g.M) ? __ldg(reinterpret_cast<const float4*>(ap + (size_t)r * g.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (vec) {
+              v[j] = (m0 + r < g.M) ? __ldg(reinterpret_cast<const float4*>(ap + (size_t)r * g.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+              const float* q = ap + (size_t)r * g.lda;
+              const int k = kc * LK + 4 * c4;
+              const bool in = m0 + r < g.M;
+              v[j].x = (in && k < g.Kr) ? __ldg(q) : 0.f;         v[j].y = (in && k + 1 < g.Kr) ? __ldg(q + 1) : 0.f;
+              v[j].z = (in && k + 2 < g.Kr) ? __ldg(q + 2) : 0.f; v[j].w = (in && k + 3 < g.Kr) ? __ldg(q + 3) : 0.f;
+            }
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -142,14 +155,30 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
       const bool valid = m < g.M;
       epi_sync();                                                  // previous tile's readers of sVec are done
       for (int i = et; i < LNT; i += 128) {
-        sVec[i] = g.bias ? __ldg(g.bias + n0 + i) : 0.0f;
+        sVec[i] = (g.bias && n0 + i < g.Nr) ? __ldg(g.bias + n0 + i) : 0.0f;
         if (g.epi == LEPI_RES_LN) { sVec[LNT + i] = __ldg(g.gamma + i); sVec[2 * LNT + i] = __ldg(g.beta + i); }
       }
       epi_sync();
       mbar_wait(&acc_full[buf], u & 1); tc_fence_after();
       const uint32_t d_addr = lane_addr + 256u * buf;
       float* orow = g.out + (size_t)m * g.ldo + n0;
-      if (g.epi != LEPI_RES_LN) {
+      if (g.epi == LEPI_SIGMOID) {
+        // sigmoid(acc + bias) -> [M][Nr] with an unaligned row pitch: every 32-column chunk is re-ordered through shared memory
+        // so that a warp writes 32 consecutive floats of one row
+#pragma unroll 1
+        for (int c8 = 0; c8 < 8 && n0 + 32 * c8 < g.Nr; ++c8) {
+          float v[32];
+          tmem_ld32(d_addr + 32 * c8, v); tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) sStage[row * L_STAGE_LD + e] = 1.0f / (1.0f + __expf(-(v[e] + sVec[32 * c8 + e])));
+          epi_sync();
+          for (int i = et; i < LM * 32; i += 128) {
+            const int r = i >> 5, c = i & 31, mm = mt * LM + r, col = n0 + 32 * c8 + c;
+            if (mm < g.M && col < g.Nr) g.out[(size_t)mm * g.ldo + col] = sStage[r * L_STAGE_LD + c];
+          }
+          epi_sync();
+        }
+      } else if (g.epi != LEPI_RES_LN) {
 #pragma unroll 1
         for (int c8 = 0; c8 < 8; ++c8) {
           float v[32];
@@ -167,7 +196,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
         }
       } else {
         // y = acc + bias + residual, kept in TMEM; LayerNorm(y) * gamma + beta (Keras non-fused order, eps 1e-6)
-        const float* rrow = g.res + (size_t)m * g.N;
+        const float* rrow = g.res ? g.res + (size_t)m * g.N : nullptr;
+        const float* prow = g.pos ? g.pos + (size_t)(m % g.T) * LNT : nullptr;
         float mean = 0.0f, m2 = 0.0f;
 #pragma unroll 1
         for (int c8 = 0; c8 < 8; ++c8) {
@@ -176,7 +206,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
           float s = 0.0f;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 r4 = valid ? __ldg(reinterpret_cast<const float4*>(rrow + 32 * c8 + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 r4 = (valid && rrow) ? __ldg(reinterpret_cast<const float4*>(rrow + 32 * c8 + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
             v[4 * q] += sVec[32 * c8 + 4 * q] + r4.x;         v[4 * q + 1] += sVec[32 * c8 + 4 * q + 1] + r4.y;
             v[4 * q + 2] += sVec[32 * c8 + 4 * q + 2] + r4.z; v[4 * q + 3] += sVec[32 * c8 + 4 * q + 3] + r4.w;
             s += (v[4 * q] + v[4 * q + 1]) + (v[4 * q + 2] + v[4 * q + 3]);
@@ -206,6 +236,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
                 const int c = 32 * c8 + 4 * q + e;
                 const float inv = rstd * sVec[LNT + c];
                 o[e] = fmaf(v[4 * q + e], inv, sVec[2 * LNT + c] - mean * inv);
+                if (prow) o[e] = fmaxf(o[e], 0.0f) + __ldg(prow + c);
               }
               *reinterpret_cast<float4*>(orow + 32 * c8 + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
             }
@@ -224,7 +255,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
 
 // ---- host side ------------------------------------------------------------------------------------------------
 // W [K][N] fp32 row-major -> [N / 256][K / 64][hi | lo] chunks, each part [256 rows (n) x 128 B (64 k as fp16)], 128-byte swizzle
-static void pack_lin(std::vector<unsigned char>& img, size_t base, const float* W, int K, int N) {
+static void pack_lin(std::vector<unsigned char>& img, size_t base, const float* W, int Kr, int Nr) {
+  const int K = (Kr + LK - 1) / LK * LK, N = (Nr + LNT - 1) / LNT * LNT;      // padded with zero weights
   const int n_nt = N / LNT, n_kc = K / LK;
   for (int nt = 0; nt < n_nt; ++nt)
     for (int kc = 0; kc < n_kc; ++kc) {
@@ -232,7 +264,8 @@ static void pack_lin(std::vector<unsigned char>& img, size_t base, const float* 
       unsigned char* lo = hi + LW_PART;
       for (int n = 0; n < LNT; ++n)
         for (int kk = 0; kk < LK; ++kk) {
-          const float w = W[(size_t)(kc * LK + kk) * N + nt * LNT + n];
+          const int k = kc * LK + kk, nn = nt * LNT + n;
+          const float w = (k < Kr && nn < Nr) ? W[(size_t)k * Nr + nn] : 0.0f;
           const __half h = __float2half_rn(w);
           const __half l = __float2half_rn(w - __half2float(h));
           const size_t off = (size_t)(n >> 3) * 1024 + (n & 7) * 128 + (((kk >> 3) ^ (n & 7)) * 16) + (kk & 7) * 2;
@@ -252,7 +285,13 @@ int mhanet_umma_prepare(dxi_net& net, cudaStream_t st) {
   size_t total = 0;
   for (int blk = 0; blk < c.n_blocks; ++blk)
     for (int i = 0; i < 4; ++i) { offs.push_back(total); total += sz[i]; }
+  // input layer [n_feat -> d] (K padded to 320) and output layer [d -> n_outp] (N padded to 512)
+  const int Kin = (c.n_feat + LK - 1) / LK * LK, Nout = (c.n_outp + LNT - 1) / LNT * LNT;
+  offs.push_back(total); total += (size_t)Kin * d * 4;
+  offs.push_back(total); total += (size_t)d * Nout * 4;
   std::vector<unsigned char> img(total, 0);
+  pack_lin(img, offs[4 * c.n_blocks], net.host_tensor(0, "kernel")->data(), c.n_feat, d);
+  pack_lin(img, offs[4 * c.n_blocks + 1], net.host_tensor(3 + 5 * c.n_blocks, "kernel")->data(), d, c.n_outp);
   for (int blk = 0; blk < c.n_blocks; ++blk) {
     const int li = 3 + 5 * blk;
     char nm[64];
@@ -273,14 +312,16 @@ int mhanet_umma_prepare(dxi_net& net, cudaStream_t st) {
   return DXI_OK;
 }
 
-// which: 0 qkv, 1 projection (+ residual + LN), 2 ffn in (bias + ReLU), 3 ffn out (bias + residual + LN)
-int mhanet_umma_linear(const dxi_net& net, int blk, int which, const float* A, int lda, const float* bias, const float* res,
-                       const float* gamma, const float* beta, float* out, int ldo, int M, int N, int K, cudaStream_t st) {
-  if (!net.d_umma || (size_t)(4 * blk + which) >= net.umma_stage_offset.size()) { set_error("tcgen05 weight images missing"); return DXI_E_STATE; }
-  if (N % LNT || K % LK || (lda & 3) || (ldo & 3)) { set_error("lin_umma: unsupported shape"); return DXI_E_INVALID; }
-  LinArgs g{A, lda, reinterpret_cast<const unsigned char*>(net.d_umma) + net.umma_stage_offset[4 * blk + which], bias, res, gamma, beta,
-            out, ldo, M, N, K, (which == 1 || which == 3) ? LEPI_RES_LN : (which == 2 ? LEPI_BIAS_RELU : LEPI_PLAIN)};
-  if (g.epi == LEPI_RES_LN && N != LNT) { set_error("lin_umma: LayerNorm epilogue needs N = 256"); return DXI_E_INVALID; }
+// image: index into net.umma_stage_offset (4 blk + {0 qkv, 1 projection, 2 ffn in, 3 ffn out}; 4 n_blocks: input layer, + 1: output)
+int mhanet_umma_linear(const dxi_net& net, int image, int epi, const float* A, int lda, const float* bias, const float* res,
+                       const float* gamma, const float* beta, const float* pos, int T, float* out, int ldo, int M, int Nr, int Kr,
+                       cudaStream_t st) {
+  if (!net.d_umma || (size_t)image >= net.umma_stage_offset.size()) { set_error("tcgen05 weight images missing"); return DXI_E_STATE; }
+  const int N = (Nr + LNT - 1) / LNT * LNT, K = (Kr + LK - 1) / LK * LK;
+  LinArgs g{A, lda, reinterpret_cast<const unsigned char*>(net.d_umma) + net.umma_stage_offset[image], bias, res, gamma, beta, pos, T,
+            out, ldo, M, N, K, epi, Nr, Kr};
+  if (epi == LEPI_RES_LN && Nr != LNT) { set_error("lin_umma: LayerNorm epilogue needs N = 256"); return DXI_E_INVALID; }
+  if (epi != LEPI_SIGMOID && ((ldo & 3) || Nr != N)) { set_error("lin_umma: unaligned outputs only through the sigmoid epilogue"); return DXI_E_INVALID; }
   static bool attr_set = false;
   if (!attr_set) { DXI_CUDA(cudaFuncSetAttribute(lin_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM)); attr_set = true; }
   int n_sm = 148;

@@ -252,7 +252,7 @@ int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xb
   const dxi_net_cfg& c = net.cfg;
   if (c.d_model != GN || c.d_model / c.n_heads != HD) { set_error("MHANetV3 path is built for d_model=256, head size 32"); return DXI_E_INVALID; }
   if (c.precision != DXI_PREC_F32 && c.precision != DXI_PREC_F16X3) { set_error("MHANetV3: precisions f32 and f16x3 are built"); return DXI_E_INVALID; }
-  const bool tc = c.precision == DXI_PREC_F16X3;      // the four GEMMs of every block on tcgen05 (mha_umma.cu); first / last layer and attention on the fp32 pipes
+  const bool tc = c.precision == DXI_PREC_F16X3;      // every GEMM (mha_umma.cu) and the attention (attn_umma.cu) on tcgen05
   if (T > c.max_len) { set_error("MHANetV3: %d frames exceed the %d rows of the positional embedding (attention.py:432)", T, c.max_len); return DXI_E_INVALID; }
   if ((int64_t)ws_bytes < mhanet_workspace_bytes(net, B, T)) { set_error("workspace too small"); return DXI_E_NOMEM; }
   const int rows = B * T, d = c.d_model;
@@ -269,8 +269,13 @@ int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xb
   auto Wt = [&](int li, const char* v) { return net.dev_tensor(li, v); };
   GemmArgs g{};
   // x = ReLU(LN(inp W0)) + E[t]
-  g = GemmArgs{mag, c.n_feat, Wt(0, "kernel"), nullptr, nullptr, Wt(1, "gamma"), Wt(1, "beta"), Wt(2, "embeddings"), x, d, rows, d, c.n_feat, T, EPI_LN_RELU_POS};
-  if (int rc = launch_gemm(g, st, "mha_gemm")) return rc;
+  if (tc) {
+    if (int rc = mhanet_umma_linear(net, 4 * c.n_blocks, 2 /* LN, here: + ReLU + positional embedding */, mag, c.n_feat, nullptr, nullptr, Wt(1, "gamma"),
+                                    Wt(1, "beta"), Wt(2, "embeddings"), T, x, d, rows, d, c.n_feat, st)) return rc;
+  } else {
+    g = GemmArgs{mag, c.n_feat, Wt(0, "kernel"), nullptr, nullptr, Wt(1, "gamma"), Wt(1, "beta"), Wt(2, "embeddings"), x, d, rows, d, c.n_feat, T, EPI_LN_RELU_POS};
+    if (int rc = launch_gemm(g, st, "mha_gemm")) return rc;
+  }
   int li = 3;
   for (int blk = 0; blk < c.n_blocks; ++blk) {
     char nm[64];
@@ -278,7 +283,7 @@ int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xb
     auto it = net.d_offset.find(nm);
     if (it == net.d_offset.end()) { set_error("packed QKV weights missing"); return DXI_E_STATE; }
     if (tc) {
-      if (int rc = mhanet_umma_linear(net, blk, 0, x, d, nullptr, nullptr, nullptr, nullptr, qkv, 3 * d, rows, 3 * d, d, st)) return rc;
+      if (int rc = mhanet_umma_linear(net, 4 * blk + 0, 0 /* plain */, x, d, nullptr, nullptr, nullptr, nullptr, nullptr, T, qkv, 3 * d, rows, 3 * d, d, st)) return rc;
     } else {
       g = GemmArgs{x, d, net.d_arena + it->second, nullptr, nullptr, nullptr, nullptr, nullptr, qkv, 3 * d, rows, 3 * d, d, T, EPI_BIAS};
       if (int rc = launch_gemm(g, st, "mha_gemm")) return rc;
@@ -294,9 +299,9 @@ int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xb
     }
     // a = LN(x + att Wp)      (projection_kernel [8,32,256] is [256][256] row-major as stored)
     if (tc) {
-      if (int rc = mhanet_umma_linear(net, blk, 1, att, d, nullptr, x, Wt(li + 1, "gamma"), Wt(li + 1, "beta"), a, d, rows, d, d, st)) return rc;
-      if (int rc = mhanet_umma_linear(net, blk, 2, a, d, Wt(li + 2, "bias"), nullptr, nullptr, nullptr, f, 4 * d, rows, 4 * d, d, st)) return rc;      // f = ReLU(a W1 + b1)
-      if (int rc = mhanet_umma_linear(net, blk, 3, f, 4 * d, Wt(li + 3, "bias"), a, Wt(li + 4, "gamma"), Wt(li + 4, "beta"), x, d, rows, d, 4 * d, st)) return rc;      // x = LN(a + f W2 + b2)
+      if (int rc = mhanet_umma_linear(net, 4 * blk + 1, 2 /* residual + LN */, att, d, nullptr, x, Wt(li + 1, "gamma"), Wt(li + 1, "beta"), nullptr, T, a, d, rows, d, d, st)) return rc;
+      if (int rc = mhanet_umma_linear(net, 4 * blk + 2, 1 /* bias + ReLU */, a, d, Wt(li + 2, "bias"), nullptr, nullptr, nullptr, nullptr, T, f, 4 * d, rows, 4 * d, d, st)) return rc;      // f = ReLU(a W1 + b1)
+      if (int rc = mhanet_umma_linear(net, 4 * blk + 3, 2, f, 4 * d, Wt(li + 3, "bias"), a, Wt(li + 4, "gamma"), Wt(li + 4, "beta"), nullptr, T, x, d, rows, d, 4 * d, st)) return rc;      // x = LN(a + f W2 + b2)
     } else {
     g = GemmArgs{att, d, Wt(li, "projection_kernel"), nullptr, x, Wt(li + 1, "gamma"), Wt(li + 1, "beta"), nullptr, a, d, rows, d, d, T, EPI_RES_LN};
     if (int rc = launch_gemm(g, st, "mha_gemm")) return rc;
@@ -309,6 +314,8 @@ int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xb
     }
     li += 5;
   }
+  if (tc) return mhanet_umma_linear(net, 4 * c.n_blocks + 1, 3 /* sigmoid */, x, d, Wt(li, "bias"), nullptr, nullptr, nullptr, nullptr, T, xbar, c.n_outp,
+                                    rows, c.n_outp, d, st);
   g = GemmArgs{x, d, Wt(li, "kernel"), Wt(li, "bias"), nullptr, nullptr, nullptr, nullptr, xbar, c.n_outp, rows, c.n_outp, d, T, EPI_SIGMOID};
   return launch_gemm(g, st, "mha_gemm");
 }
