@@ -6,12 +6,14 @@
 //
 // One persistent CTA per SM walks (row tile of 128) x (column tile of 256) output tiles, n fastest, so that the column
 // tiles of one row tile run on neighbouring SMs at the same time and share A through L2.  Warp roles:
-//   warps 0-3  producers: a [128 x 64] chunk of A per step: coalesced float4 loads, hi/lo split, stores into the
-//              128-byte-swizzled K-major shared-memory operand (the layout umma_selftest checks); lane 0 of warp 0 also
-//              starts the bulk copy of the matching pre-packed weight chunk (hi | lo, 64 KB);
-//   warp  8    issues the 12 MMAs of a chunk (M 128 x N 256 x K 16, (a_hi, w_hi) + (a_lo, w_hi) + (a_hi, w_lo)) as soon as
+//   warps 0-7  producers, two groups of four: group p owns ring slot p and produces the chunks of parity p, so the global
+//              loads of one chunk are in flight while the other chunk is converted and multiplied.  A [128 x 64] chunk of A per
+//              step: coalesced float4 loads, hi/lo split, stores into the 128-byte-swizzled K-major shared-memory operand (the
+//              layout umma_selftest checks); the group's first lane also starts the bulk copy of the matching pre-packed
+//              weight chunk (hi | lo, 64 KB);
+//   warp 12    issues the 12 MMAs of a chunk (M 128 x N 256 x K 16, (a_hi, w_hi) + (a_lo, w_hi) + (a_hi, w_lo)) as soon as
 //              both operands have landed, releases the ring slot with tcgen05.commit;
-//   warps 4-7  epilogue: thread = output row, 256 fp32 columns from TMEM in chunks of 32: bias / ReLU, or
+//   warps 8-11 epilogue: thread = output row, 256 fp32 columns from TMEM in chunks of 32: bias / ReLU, or
 //              residual + LayerNorm (row statistics by Chan's merge over the 8 chunks, normalised in a second pass
 //              over the tile kept in TMEM); two accumulator buffers, so the epilogue of a tile overlaps the next tile's MMAs.
 // Shared memory: 2 ring slots x (A hi|lo 32 KB + W hi|lo 64 KB) = 192 KB + bias / gamma / beta of the column tile.
@@ -27,7 +29,8 @@ constexpr int LA_PART = LM * 128;                     // one precision part of a
 constexpr int LW_PART = LNT * 128;                    // one precision part of a W chunk: [256 rows x 128 B]
 constexpr int L_SLOT = 2 * LA_PART + 2 * LW_PART;     // 96 KB
 constexpr int L_WCHUNK = 2 * LW_PART;                 // packed weight chunk in global memory: hi | lo
-constexpr int L_THREADS = 9 * 32;
+constexpr int L_PROD_WARPS = 8;                       // two groups of 4: group p fills ring slot p (chunks of parity p)
+constexpr int L_THREADS = (L_PROD_WARPS + 5) * 32;    // + 4 epilogue warps + 1 MMA warp
 constexpr int L_STAGE_LD = 33;
 constexpr int L_SMEM = 1024 + 2 * L_SLOT + 3 * LNT * 4 + LM * L_STAGE_LD * 4;
 enum { LEPI_PLAIN = 0, LEPI_BIAS_RELU = 1, LEPI_RES_LN = 2, LEPI_SIGMOID = 3 };
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
   float* sVec = reinterpret_cast<float*>(ring + 2 * L_SLOT);      // bias[256], gamma[256], beta[256] of the column tile
   float* sStage = sVec + 3 * LNT;                                 // [128][33]: row-major re-ordering of a 32-column chunk (unaligned outputs)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (warp == 8) tmem_alloc(&tmem_slot, 512);
+  if (warp == L_PROD_WARPS + 4) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&full_a[i], 4); mbar_init(&full_w[i], 1); mbar_init(&empty[i], 1);
@@ -68,17 +71,19 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
   const int n_nt = g.N / LNT, n_mt = (g.M + LM - 1) / LM, n_kc = g.K / LK;
   const int n_tiles = n_mt * n_nt;
 
-  if (warp < 4) {
+  if (warp < L_PROD_WARPS) {
     // ================= producers =================
     int gch = 0;                                                  // chunk counter of this CTA: ring slot = gch & 1
-    const int c4 = tid & 15, r0 = tid >> 4;                       // float4 column, first row; rows r0 + 8 j
+    const int grp = warp >> 2, ptid = tid & 127;                  // producer group = the ring slot it owns
+    const int c4 = ptid & 15, r0 = ptid >> 4;                     // float4 column, first row; rows r0 + 8 j
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int mt = t / n_nt, nt = t - mt * n_nt, m0 = mt * LM;
       for (int kc = 0; kc < n_kc; ++kc, ++gch) {
         const int slot = gch & 1, use = gch >> 1;
+        if (slot != grp) continue;                                // the other group's chunk
         if (use >= 1) mbar_wait(&empty[slot], (use - 1) & 1);     // the MMAs that read this slot have completed
         unsigned char* sA = ring + slot * L_SLOT;
-        if (tid == 0) {
+        if (ptid == 0) {
           mbar_arrive_expect_tx(&full_w[slot], L_WCHUNK);
           const unsigned char* src = g.W + ((size_t)nt * n_kc + kc) * L_WCHUNK;
           for (int off = 0; off < L_WCHUNK; off += 16384) bulk_g2s(sA + 2 * LA_PART + off, src + off, 16384, &full_w[slot]);
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
         if (lane == 0) mbar_arrive(&full_a[slot]);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == L_PROD_WARPS + 4) {
     // ================= MMA issue =================
     constexpr uint32_t idesc = make_idesc_f16(LM, LNT);
     int gch = 0, lt = 0;
@@ -144,8 +149,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
       mma_commit_elect(&acc_full[buf]);
     }
   } else {
-    // ================= epilogue (warps 4-7: TMEM lane quarter = warp & 3) =================
-    const int ew = warp & 3, row = ew * 32 + lane, et = tid - 128;      // et: 0..127
+    // ================= epilogue (warps 8-11: TMEM lane quarter = warp & 3) =================
+    const int ew = warp & 3, row = ew * 32 + lane, et = tid - L_PROD_WARPS * 32;      // et: 0..127
     const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
     auto epi_sync = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
     int lt = 0;
@@ -250,7 +255,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(0, 512);
+  if (warp == L_PROD_WARPS + 4) tmem_dealloc(0, 512);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
