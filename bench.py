@@ -150,6 +150,32 @@ def cpu_baseline(n_utt=8):
                       % (n_utt, SECONDS, reps)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pins this process (and therefore the pinned host buffers it allocates next: first touch) to the CPUs of the NUMA node
+    the GPU hangs off, so that the e2e arm's host<->device copies of the N ranks do not cross the socket interconnect.
+    Best effort: returns a short description, or None when the topology cannot be read."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = '%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open('/sys/bus/pci/devices/%s/numa_node' % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(','):
+                lo, _, hi = part.partition('-')
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return 'numa node %d (%d cpus)' % (node, len(cpus))
+    except Exception:
+        return None
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -158,6 +184,7 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if not os.environ.get('DXI_BENCH_NO_NUMA') else None
     if world > 1 and not dist.is_initialized():
         # NCCL prints a version banner on stdout when the communicator is created; stdout must carry exactly
         # ONE JSON line, so fd 1 points at stderr until the first collective has run.
@@ -283,7 +310,8 @@ def run_ours(args, rank, world, local_rank):
         'clocks': clocks,
         'e2e': {'value': audio_s * args.steps / (e2e_ms / 1e3), 'unit': 'audio-s/s',
                 'h2d_bytes_per_step': B * L * 2, 'd2h_bytes_per_step': B * (T + 1) * 256 * 2,
-                'api': 'HostPipeline(DeepXi).submit(pinned int16 in, lens, pinned int16 out): DeepXi.infer_batch on 3 rotating streams'},
+                'api': 'HostPipeline(DeepXi).submit(pinned int16 in, lens, pinned int16 out): DeepXi.infer_batch on 3 rotating streams',
+                'host_binding': numa},
         'gpu_launches': launches,
         'roofline': {'kernel': 'tcn_stage_kernel (tcgen05 / TMEM, %g launches per step)' % st_per_step, 'bound': 'tensor',
                      'achieved': achieved_tf, 'peak': tf_peak, 'unit': 'TFLOP/s',
