@@ -277,12 +277,9 @@ int mhanet_umma_attention(const dxi_net& net, const float* qkv, const uint8_t* v
   const dxi_net_cfg& c = net.cfg;
   if (c.d_model / c.n_heads != AHD || (c.d_model & 3)) { set_error("tcgen05 attention is built for head size 32"); return DXI_E_INVALID; }
   AttnArgs a{qkv, valid, att, B, T, c.d_model, c.n_heads};
-  static bool attr_set = false;
-  if (!attr_set) {
-    DXI_CUDA(cudaFuncSetAttribute(attn_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
-    DXI_CUDA(cudaFuncSetAttribute(attn_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
-    attr_set = true;
-  }
+  // (per call: the attribute is per device, and a process may drive several)
+  DXI_CUDA(cudaFuncSetAttribute(attn_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
+  DXI_CUDA(cudaFuncSetAttribute(attn_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM));
   int n_sm = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   const int items = B * c.n_heads * ((T + AT - 1) / AT);

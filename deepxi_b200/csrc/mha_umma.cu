@@ -327,8 +327,7 @@ int mhanet_umma_linear(const dxi_net& net, int image, int epi, const float* A, i
             out, ldo, M, N, K, epi, Nr, Kr};
   if (epi == LEPI_RES_LN && Nr != LNT) { set_error("lin_umma: LayerNorm epilogue needs N = 256"); return DXI_E_INVALID; }
   if (epi != LEPI_SIGMOID && ((ldo & 3) || Nr != N)) { set_error("lin_umma: unaligned outputs only through the sigmoid epilogue"); return DXI_E_INVALID; }
-  static bool attr_set = false;
-  if (!attr_set) { DXI_CUDA(cudaFuncSetAttribute(lin_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM)); attr_set = true; }
+  DXI_CUDA(cudaFuncSetAttribute(lin_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM));      // per device, so per call
   int n_sm = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   const int tiles = ((M + LM - 1) / LM) * (N / LNT);

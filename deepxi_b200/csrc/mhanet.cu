@@ -120,8 +120,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmArgs g) {
 
 static int launch_gemm(const GemmArgs& g, cudaStream_t st, const char* key) {
   const size_t smem = sizeof(float) * (GK * GM + GK * GN + GM * (GN + 1));
-  static bool attr_set = false;
-  if (!attr_set) { DXI_CUDA(cudaFuncSetAttribute(gemm_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+  DXI_CUDA(cudaFuncSetAttribute(gemm_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      // per device, so per call
   dim3 grid((g.M + GM - 1) / GM, (g.N + GN - 1) / GN);
   ProfScope prof(key, st, 1);
   gemm_f32_kernel<<<grid, 256, smem, st>>>(g);

@@ -828,10 +828,9 @@ int64_t resnet_umma_workspace_bytes(const dxi_net& net, int B, int T) {
   return (int64_t)(256 + h_bytes + 2 * c1_bytes + stats_bytes);
 }
 
-int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, float* xbar, void* ws, size_t ws_bytes,
-                        cudaStream_t st) {
+// One group of whole utterances through stem -> 41 stages -> output layer; every group uses the same workspace region.
+static int resnet_umma_group(const dxi_net& net, const float* mag, int B, int T, float* xbar, void* ws, cudaStream_t st, bool dbg) {
   const dxi_net_cfg& c = net.cfg;
-  if ((int64_t)ws_bytes < resnet_umma_workspace_bytes(net, B, T)) { set_error("workspace too small"); return DXI_E_NOMEM; }
   const int tiles = (T + TILE - 1) / TILE;
   const int Ts = tiles * TILE + 2 * C1_PAD;
   const size_t h_bytes = (size_t)B * tiles * TILE * 256 * 4;
@@ -878,7 +877,7 @@ int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, floa
     a.T = T; a.tiles_per_utt = tiles; a.n_tiles = n_tiles; a.Ts = Ts;
     a.has_back = s >= 1; a.has_front = s < c.n_blocks;
     a.reverse = (s & 1) == 0 && !env_flag("DXI_TCN_NO_REVERSE");      // the stem leaves the last tiles in L2, the output layer starts on the first
-    a.dbg = (s == g_dbg_stage) ? g_dbg_clocks : nullptr;
+    a.dbg = (dbg && s == g_dbg_stage) ? g_dbg_clocks : nullptr;
     a.dbg_flags = g_dbg_flags;
     const int d = s >= 1 ? 1 << ((s - 1) % nd) : 1;
     if (c.padding == DXI_PAD_CAUSAL) { a.shift0 = 2 * d; a.shift1 = d; a.shift2 = 0; }       // tap j reads t-(2-j)d
@@ -896,6 +895,21 @@ int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, floa
     ProfScope prof("tcn_head", st, 1);
     DXI_CUDA(launch_pdl(head_umma_kernel, grid, STAGE_THREADS, smem_head, st, a));
     DXI_LAUNCHED("head_umma_kernel");
+  }
+  return DXI_OK;
+}
+
+int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, float* xbar, void* ws, size_t ws_bytes,
+                        cudaStream_t st) {
+  const dxi_net_cfg& c = net.cfg;
+  if ((int64_t)ws_bytes < resnet_umma_workspace_bytes(net, B, T)) { set_error("workspace too small"); return DXI_E_NOMEM; }
+  // DXI_TCN_GROUP_UTTS=n (tuning experiment): run the whole network over groups of n utterances, one group after the other, so
+  // that a group's residual stream and c1 planes stay closer to L2; 0 / unset: the whole batch at once.
+  static const int group = [] { const char* v = getenv("DXI_TCN_GROUP_UTTS"); return v && *v ? atoi(v) : 0; }();
+  if (group <= 0 || group >= B) return resnet_umma_group(net, mag, B, T, xbar, ws, st, true);
+  for (int b0 = 0; b0 < B; b0 += group) {
+    const int Bg = B - b0 < group ? B - b0 : group;
+    if (int rc = resnet_umma_group(net, mag + (size_t)b0 * T * c.n_feat, Bg, T, xbar + (size_t)b0 * T * c.n_outp, ws, st, b0 == 0)) return rc;
   }
   return DXI_OK;
 }
