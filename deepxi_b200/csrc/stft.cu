@@ -140,19 +140,22 @@ __global__ void __launch_bounds__(256) stft_kernel(const void* __restrict__ wav_
       for (int k2 = 0; k2 < 16; ++k2) fb[lane16 + 16 * k2] = v[fft16_pos(k2)];
     }
     __syncthreads();
-    // ---- split step, magnitude and phase; flat coalesced stores over (frame, bin)
+    // ---- split step, magnitude and phase.  Thread = bin (0..255) for every frame of the pass, so the twiddle and both
+    // exchange indices are loop invariants and a frame's 256 outputs are one coalesced row; the Nyquist bin of frame f is done
+    // by thread f afterwards.
     {
-      int fi = 0, k = tid;                       // flat index i = fi * 257 + k, advanced by 256 per iteration
-      for (int i = tid; i < nf * NBINS; i += 256) {
-        const float2* z = sm.buf + fi * FFT_FRAME_SLOTS;
-        float2 X = rfft_split(z[k & 255], z[(256 - k) & 255], sm.tw512[k]);
+      auto emit = [&](const float2* z, int k, int ia, int ib, float2 w, int64_t o) {
+        float2 X = rfft_split(z[ia], z[ib], w);
         if (k == 0 || k == 256) X.y = 0.0f;
         const float p2 = fmaf(X.x, X.x, X.y * X.y);
-        __stcs(mag + out0 + i, p2 > 0.0f ? p2 * rsqrtf(p2) : 0.0f);       // |X|, 2 ulp
-        __stcs(phase + out0 + i, atan2_poly(X.y, X.x));
-        k += 256;
-        if (k >= NBINS) { k -= NBINS; ++fi; }
-      }
+        __stcs(mag + o, p2 > 0.0f ? p2 * rsqrtf(p2) : 0.0f);       // |X|, 2 ulp
+        __stcs(phase + o, atan2_poly(X.y, X.x));
+      };
+      const int k = tid, ib = (256 - tid) & 255;
+      const float2 w = sm.tw512[k];
+#pragma unroll 4
+      for (int fi = 0; fi < nf; ++fi) emit(sm.buf + fi * FFT_FRAME_SLOTS, k, k, ib, w, out0 + (int64_t)fi * NBINS + k);
+      if (tid < nf) emit(sm.buf + tid * FFT_FRAME_SLOTS, 256, 0, 0, sm.tw512[256], out0 + (int64_t)tid * NBINS + 256);
     }
     __syncthreads();
   }
@@ -202,50 +205,60 @@ __global__ void __launch_bounds__(256, 3) istft_kernel(const float* __restrict__
     // frames hs-1 .. he-1 in passes of FR; the first frame of the strip only provides its tail
     for (int f0 = hs - 1; f0 < he; f0 += FR) {
       const int nf = min(FR, he - f0);
-      // ---- spectrum of every frame: Y = (|X| G) e^{j phase}.  Flat element i = 256 it + tid = 257 it + (tid - it): bin
-      // k = tid - it of frame it (or k + 257 of frame it - 1); two elements per iteration so that six loads are in flight.
-      const int n_el = nf * NBINS;
-      for (int it = 0; it * 256 < n_el; it += 2) {
-        float mv[2], pv[2], gv[2];
-        int kk[2], ff[2];
-        bool inb[2], ok[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          int k = tid - (it + u), fi = it + u;
-          if (k < 0) { k += NBINS; --fi; }
-          kk[u] = k; ff[u] = fi;
-          inb[u] = (it + u) * 256 + tid < n_el;
-          const int t = f0 + fi;
-          ok[u] = inb[u] && t >= 0 && t < T;
-          mv[u] = pv[u] = gv[u] = 0.0f;
-          if (ok[u]) {
-            const int64_t gi = in0 + (int64_t)t * NBINS + k;
-            mv[u] = __ldcs(mag + gi);
-            pv[u] = __ldcs(phase + gi);
-            if (MODE != 0 || gain_or_xbar) gv[u] = __ldcs(gain_or_xbar + gi);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          if (!inb[u]) continue;
-          const int k = kk[u];
+      // ---- spectrum of every frame: Y = (|X| G) e^{j phase}.  Thread = bin (0..255) for every frame of the pass (per-bin
+      // statistics are loop invariants, a frame's 256 inputs are one coalesced row, two frames per iteration so that six loads
+      // are in flight); the Nyquist bin of frame f is done by thread f afterwards.
+      {
+        float mu_k = 0.0f, sg_k = 0.0f, s2_k = 0.0f;
+        auto spectrum = [&](int fi, int k, float m, float p, float gx, bool ok, float muv, float sgv, float s2v) {
           float2 Y = make_float2(0.0f, 0.0f);
-          if (ok[u]) {
-            float m = mv[u];
+          if (ok) {
             if (MODE == 0) {
-              if (gain_or_xbar) m *= gv[u];
+              if (gain_or_xbar) m *= gx;
             } else if (MODE == 1) {
-              float xi = xi_from_xbar(gv[u], __ldg(mu + k), __ldg(sigma + k));
+              const float xi = xi_from_xbar(gx, muv, sgv);
               m = __fmul_rn(m, gfunc_eval(gtype, xi, __fadd_rn(xi, 1.0f)));
             } else {
-              const float sg = __ldg(sigma + k);      // (the 2 KB of statistics stay in L1; shared memory is what bounds occupancy here)
-              m *= lsa_gain_from_xbar_fast(gv[u], __ldg(mu + k), __fmul_rn(sg, 1.41421354f), sg);
+              m *= lsa_gain_from_xbar_fast(gx, muv, s2v, sgv);
             }
             float sn, cs;
-            __sincosf(pv[u], &sn, &cs);                                      // |p| <= pi: abs error < 5e-7
+            __sincosf(p, &sn, &cs);                                        // |p| <= pi: abs error < 5e-7
             Y = make_float2(m * cs, (k == 0 || k == 256) ? 0.0f : m * sn);   // c2r ignores Im of DC / Nyquist
           }
-          sm.buf[ff[u] * FFT_FRAME_SLOTS + k] = Y;
+          sm.buf[fi * FFT_FRAME_SLOTS + k] = Y;
+        };
+        const int k = tid;
+        if (MODE != 0) { mu_k = __ldg(mu + k); sg_k = __ldg(sigma + k); s2_k = __fmul_rn(sg_k, 1.41421354f); }
+        for (int fi = 0; fi < nf; fi += 2) {
+          float mv[2], pv[2], gv[2];
+          bool ok[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int t = f0 + fi + u;
+            ok[u] = fi + u < nf && t >= 0 && t < T;
+            mv[u] = pv[u] = gv[u] = 0.0f;
+            if (ok[u]) {
+              const int64_t gi = in0 + (int64_t)t * NBINS + k;
+              mv[u] = __ldcs(mag + gi);
+              pv[u] = __ldcs(phase + gi);
+              if (MODE != 0 || gain_or_xbar) gv[u] = __ldcs(gain_or_xbar + gi);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+            if (fi + u < nf) spectrum(fi + u, k, mv[u], pv[u], gv[u], ok[u], mu_k, sg_k, s2_k);
+        }
+        if (tid < nf) {      // bin 256 of frame tid
+          const int t = f0 + tid;
+          const bool ok1 = t >= 0 && t < T;
+          float m = 0.0f, p = 0.0f, gx = 0.0f, muv = 0.0f, sgv = 0.0f;
+          if (ok1) {
+            const int64_t gi = in0 + (int64_t)t * NBINS + 256;
+            m = __ldcs(mag + gi); p = __ldcs(phase + gi);
+            if (MODE != 0 || gain_or_xbar) gx = __ldcs(gain_or_xbar + gi);
+            if (MODE != 0) { muv = __ldg(mu + 256); sgv = __ldg(sigma + 256); }
+          }
+          spectrum(tid, 256, m, p, gx, ok1, muv, sgv, __fmul_rn(sgv, 1.41421354f));
         }
       }
       __syncthreads();
