@@ -198,6 +198,23 @@ def test_mhanetv3_tensor_core_path_many_tiles(xi_stats, mask_mode):
     assert np.array_equal(np.asarray(xbar), np.asarray(again))     # no order-dependent arithmetic anywhere
 
 
+@pytest.mark.parametrize('T', [1, 127, 128, 129, 257])
+def test_mhanetv3_tensor_core_path_tile_edges(xi_stats, T):
+    """Tile boundaries of the tcgen05 path: one frame, one short of / exactly / one past a 128-row tile, three tiles with one
+    row in the last (ragged last query tile, key tiles with rows beyond T, B * T not a multiple of 128)."""
+    from oracle import attention as oatt
+    mu, sg = xi_stats['mhanet-1.1c/mu'], xi_stats['mhanet-1.1c/sigma']
+    w = weights.synthetic_mhanetv3(3)
+    rng = np.random.default_rng(T)
+    inp = np.abs(rng.standard_normal((2, T, 257))).astype(np.float32)
+    ref = oatt.mhanetv3_forward(inp, w, mask_mode='none', dtype=torch.float64)
+    net = network_selector('MHANetV3', None, 257, mask_mode='none', precision='f16x3', **MHA_KW).load_weights(w)
+    xbar = np.asarray(net(inp))
+    assert xbar.shape == (2, T, 257)
+    for i in range(2):
+        assert _db_err(xbar[i], ref[i], mu, sg).max() < 5e-3, (T, i)
+
+
 def test_mhanetv3_infer_and_limits(xi_stats):
     w = weights.synthetic_mhanetv3(1)
     dx = DeepXi(512, 256, 512, 16000, 'MagXi', 'MHANetV3', ver='mhanet-1.1c', map_type='DBNormalCDF', map_params=None,
