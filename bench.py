@@ -246,8 +246,8 @@ def run_ours(args, rank, world, local_rank):
     assert torch.isfinite(y).all(), 'non-finite samples in the enhanced waveform'
 
     # ---- e2e: pinned host int16 in -> public API -> pinned host int16 out, copies inside the timed region.
-    # HostPipeline rotates the steps over 3 streams so that the PCIe copies of one step overlap the kernels of
-    # another; every step still copies its whole input in and its whole result out.
+    # HostPipeline chains H2D -> kernels -> D2H of every step over three streams so that the PCIe copies of one step overlap the
+    # kernels of its neighbours; every step still copies its whole input in and its whole result out.
     from deepxi_b200.model import HostPipeline
     pipe = HostPipeline(dx, n_streams=3)
     y_hosts = [torch.empty((B, (T + 1) * 256), dtype=torch.int16).pin_memory() for _ in range(3)]
@@ -310,7 +310,7 @@ def run_ours(args, rank, world, local_rank):
         'clocks': clocks,
         'e2e': {'value': audio_s * args.steps / (e2e_ms / 1e3), 'unit': 'audio-s/s',
                 'h2d_bytes_per_step': B * L * 2, 'd2h_bytes_per_step': B * (T + 1) * 256 * 2,
-                'api': 'HostPipeline(DeepXi).submit(pinned int16 in, lens, pinned int16 out): DeepXi.infer_batch on 3 rotating streams',
+                'api': 'HostPipeline(DeepXi).submit(pinned int16 in, lens, pinned int16 out): H2D, DeepXi.infer_batch and D2H on three event-chained streams, 3 batches in flight',
                 'host_binding': numa},
         'gpu_launches': launches,
         'roofline': {'kernel': 'tcn_stage_kernel (tcgen05 / TMEM, %g launches per step)' % st_per_step, 'bound': 'tensor',

@@ -137,9 +137,12 @@ class DeepXi:
 
 
 class HostPipeline:
-    """Throughput-oriented serving loop over host buffers: every submitted batch is copied host -> device,
-    enhanced, and copied back on one of `n_streams` CUDA streams, so the PCIe copies of one batch overlap the
-    kernels of another.  Inputs / outputs are pinned host tensors owned by the caller.
+    """Throughput-oriented serving loop over host buffers.  Three CUDA streams: one copies inputs host -> device, one runs
+    the kernels, one copies results device -> host; events chain the three steps of a batch, so the PCIe copies of one batch
+    overlap the kernels of its neighbours while the kernels of consecutive batches run back to back on ONE stream (the
+    stages of a forward pass are not interleaved with another batch's: that would break the stage-to-stage L2 reuse and
+    the programmatic-dependent-launch chain).  Inputs / outputs are pinned host tensors owned by the caller; up to
+    `n_streams` batches are in flight.
 
         pipe = HostPipeline(deepxi, n_streams=3)
         for x, lens, y in batches:          # x int16 [B, L] pinned, y int16 [B, (Tmax+1)*256] pinned
@@ -149,24 +152,39 @@ class HostPipeline:
 
     def __init__(self, deepxi, n_streams=3, out_type='y', gain='mmse-lsa'):
         self.dx, self.out_type, self.gain = deepxi, out_type, gain
-        self.streams = [torch.cuda.Stream() for _ in range(n_streams)]
+        self.n_slots = max(1, int(n_streams))
+        self.h2d, self.compute, self.d2h = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
         self._i = 0
-        self._keep = [None] * n_streams
+        self._done = [None] * self.n_slots       # event: slot's device -> host copy finished
+        self._keep = [None] * self.n_slots
 
     def submit(self, x_host, x_len, out_host):
         if not (x_host.is_pinned() and out_host.is_pinned()):
             raise ValueError('HostPipeline needs pinned host tensors')
-        k = self._i % len(self.streams)
+        k = self._i % self.n_slots
         self._i += 1
-        st = self.streams[k]
-        with torch.cuda.stream(st):
+        if self._done[k] is not None:
+            self._done[k].synchronize()     # at most n_slots batches in flight (host-side back-pressure)
+        with torch.cuda.stream(self.h2d):
             xd = x_host.to('cuda', non_blocking=True)
+            ev_in = torch.cuda.Event()
+            ev_in.record(self.h2d)
+        with torch.cuda.stream(self.compute):
+            self.compute.wait_event(ev_in)
+            xd.record_stream(self.compute)
             out, n_frames = self.dx.infer_batch(xd, x_len, self.out_type, self.gain, int16=out_host.dtype == torch.int16)
+            ev_out = torch.cuda.Event()
+            ev_out.record(self.compute)
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(ev_out)
+            out.record_stream(self.d2h)
             out_host.copy_(out, non_blocking=True)
-            self._keep[k] = (xd, out)       # keep the device buffers alive until the stream is reused
+            done = torch.cuda.Event()
+            done.record(self.d2h)
+        self._done[k] = done
+        self._keep[k] = (xd, out)           # keep the device buffers alive until the slot is reused
         return n_frames
 
     def drain(self):
-        for st in self.streams:
+        for st in (self.h2d, self.compute, self.d2h):
             st.synchronize()
-
