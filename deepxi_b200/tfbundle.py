@@ -184,3 +184,80 @@ def keras_weight_shapes(index_path):
     _, entries = read_index(index_path)
     return {n[:-len(suffix)]: e.shape for n, e in entries.items()
             if n.startswith('layer_with_weights-') and n.endswith(suffix) and '.OPTIMIZER_SLOT' not in n}
+
+
+# ---- writer ---------------------------------------------------------------------------------------
+def _put_varint(v):
+    out = bytearray()
+    while True:
+        b = v & 0x7f
+        v >>= 7
+        if v:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def _pb_varint(fno, v):
+    return _put_varint((fno << 3) | 0) + _put_varint(v)
+
+
+def _pb_bytes(fno, b):
+    return _put_varint((fno << 3) | 2) + _put_varint(len(b)) + b
+
+
+def _table_block(entries):
+    """One uncompressed table block (every entry is a restart point) + its trailer (type byte, masked crc32c)."""
+    body, restarts = bytearray(), []
+    for key, val in entries:
+        restarts.append(len(body))
+        body += _put_varint(0) + _put_varint(len(key)) + _put_varint(len(val)) + key + val
+    if not restarts:
+        restarts = [0]
+    for r in restarts:
+        body += struct.pack('<I', r)
+    body += struct.pack('<I', len(restarts))
+    trailer = b'\x00'
+    return bytes(body), trailer + struct.pack('<I', masked_crc32c(bytes(body) + trailer))
+
+
+def save_tensors(prefix, tensors):
+    """Writes {name: float32 ndarray} as a one-shard TF tensor bundle: `<prefix>.index` (LevelDB-format table: header entry ''
+    + one BundleEntryProto per tensor, sorted by name) and `<prefix>.data-00000-of-00001` (raw little-endian tensors), with the
+    per-tensor masked crc32c TensorFlow verifies on load.  The inverse of load_tensors (deepxi/model.py:2377-2383 SaveWeights)."""
+    os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)
+    names = sorted(tensors, key=lambda n: n.encode())
+    entries = [(b'', _pb_varint(1, 1) + _pb_bytes(3, _pb_varint(1, 1)))]          # BundleHeaderProto{num_shards=1, version{producer=1}}
+    offset = 0
+    with open(prefix + '.data-00000-of-00001', 'wb') as f:
+        for n in names:
+            a = np.ascontiguousarray(np.asarray(tensors[n], dtype='<f4'))
+            raw = a.tobytes()
+            f.write(raw)
+            shape = b''.join(_pb_bytes(2, _pb_varint(1, int(d))) for d in a.shape)
+            val = _pb_varint(1, 1) + _pb_bytes(2, shape)                           # dtype DT_FLOAT, TensorShapeProto
+            if offset:
+                val += _pb_varint(4, offset)
+            val += _pb_varint(5, len(raw)) + _put_varint((6 << 3) | 5) + struct.pack('<I', masked_crc32c(raw))
+            entries.append((n.encode(), val))
+            offset += len(raw)
+    out = bytearray()
+    data, trailer = _table_block(entries)
+    data_handle = _put_varint(0) + _put_varint(len(data))
+    out += data + trailer
+    meta, mtrailer = _table_block([])
+    meta_handle = _put_varint(len(out)) + _put_varint(len(meta))
+    out += meta + mtrailer
+    index, itrailer = _table_block([(entries[-1][0] + b'\xff', data_handle)])    # separator >= the last key of the data block
+    index_handle = _put_varint(len(out)) + _put_varint(len(index))
+    out += index + itrailer
+    footer = meta_handle + index_handle
+    out += footer + b'\x00' * (40 - len(footer)) + struct.pack('<Q', _MAGIC)
+    with open(prefix + '.index', 'wb') as f:
+        f.write(bytes(out))
+
+
+def save_keras_weights(prefix, weights):
+    """{'layer_with_weights-<i>/<var>': ndarray} -> a bundle keras_weights() (and Keras' load_weights) can read."""
+    save_tensors(prefix, {n + '/.ATTRIBUTES/VARIABLE_VALUE': v for n, v in weights.items()})

@@ -283,3 +283,23 @@ def test_cli_main_writes_the_reference_layout(tmp_path):
     assert cli.main(base + ['--out_type', 'subband_ibm_hat', '--gain', 'mmse-lsa', '--n_filters', '24']) == 0
     m = utils.read_mat(str(tmp_path / 'out' / 'resnet-1.1c' / 'e200' / 'subband_ibm_hat' / 'utt0.mat'))['subband_ibm_hat']
     assert m.shape == (47, 24)
+
+
+def test_infer_loads_a_written_checkpoint(tmp_path):
+    """model_path/<ver>/epoch-<e-1>/variables/variables written by tfbundle.save_keras_weights is what
+    DeepXi.infer loads (model.py:279-280): same waveform bits as with the weights set explicitly."""
+    from deepxi_b200 import tfbundle
+    w = weights.synthetic_resnetv2(5)
+    tfbundle.save_keras_weights(str(tmp_path / 'model' / 'resnet-1.1c' / 'epoch-199' / 'variables' / 'variables'), w)
+    x = synth.noisy_speech(2, 9000, seed=88)
+    lens = [9000, 5000]
+    dx = DeepXi(512, 256, 512, 16000, 'MagXi', 'ResNetV2', ver='resnet-1.1c', map_type='DBNormalCDF', map_params=None,
+                padding='causal', precision='f16x3', **RES_KW)
+    dx.infer(x, lens, ['a', 'b'], test_epoch=200, model_path=str(tmp_path / 'model' / 'resnet-1.1c'), out_type='y', gain='mmse-lsa',
+             out_path=str(tmp_path / 'out'))
+    ya, _ = wavio.read_wav_int16(str(tmp_path / 'out' / 'resnet-1.1c' / 'e200' / 'y' / 'mmse-lsa' / 'a.wav'))
+    dx2 = DeepXi(512, 256, 512, 16000, 'MagXi', 'ResNetV2', ver='resnet-1.1c', map_type='DBNormalCDF', map_params=None,
+                 padding='causal', precision='f16x3', **RES_KW)
+    dx2.set_weights(w)
+    y2, nfr = dx2.infer_batch(x, lens, 'y', 'mmse-lsa', int16=True)
+    assert np.array_equal(ya, y2.cpu().numpy()[0, :(nfr[0] + 1) * 256])

@@ -177,3 +177,23 @@ def test_cli_flags_mirror_run_sh():
                       outp_act='Sigmoid', precision='f16x3')
     with pytest.raises(NotImplementedError):
         M.main(argv[:-4] + ['--train', '1'])
+
+
+def test_checkpoint_writer_round_trip(tmp_path, golden_dir):
+    """SURVEY 8f N2: tfbundle.save_keras_weights writes model/<ver>/epoch-<n>/variables/variables.{index,data-00000-of-00001};
+    the TensorFlow-free reader gets the same tensors back (per-tensor masked crc32c verified), corruption is detected, and the
+    entry names / shapes equal the ones in the reference's own index file for the same architecture."""
+    w = weights.synthetic_resnetv2(3)
+    model_path = tmp_path / 'model' / 'resnet-1.1c'
+    prefix = model_path / 'epoch-199' / 'variables' / 'variables'
+    tfbundle.save_keras_weights(str(prefix), w)
+    back = weights.load_checkpoint(str(model_path), 199)
+    assert sorted(back) == sorted(w) and all(np.array_equal(back[k], w[k]) and back[k].dtype == np.float32 for k in w)
+    ref_shapes = tfbundle.keras_weight_shapes(os.path.join(golden_dir, 'resnet-1.1c_e199_variables.index'))
+    assert tfbundle.keras_weight_shapes(str(prefix) + '.index') == ref_shapes
+    data = prefix.parent / 'variables.data-00000-of-00001'
+    raw = bytearray(data.read_bytes())
+    raw[1000] ^= 0x40
+    data.write_bytes(bytes(raw))
+    with pytest.raises(IOError):
+        weights.load_checkpoint(str(model_path), 199)
