@@ -13,12 +13,17 @@ from ._tensor import to_dev, ret
 from .map import map_selector
 from .sig import InputTarget
 
-_OTHER = ('MagGamma', 'MagXiGamma', 'MagGain', 'MagMag', 'MagSMM', 'MagPhaXiPha', 'STDCTXiCD', 'MagPhonme')
+_OTHER = ('MagGamma', 'MagMag', 'MagSMM', 'MagPhaXiPha', 'STDCTXiCD', 'MagPhonme')
 
 
 def inp_tgt_selector(inp_tgt_type, N_d, N_s, K, f_s, **kwargs):
     if inp_tgt_type == 'MagXi':
         return MagXi(N_d, N_s, K, f_s, xi_map_type=kwargs['map_type'], xi_map_params=kwargs.get('map_params'))
+    if inp_tgt_type == 'MagXiGamma':      # inp_tgt.py:46-50: map_type / map_params are [xi, gamma] pairs
+        mt, mp = kwargs['map_type'], kwargs.get('map_params') or [None, None]
+        return MagXiGamma(N_d, N_s, K, f_s, xi_map_type=mt[0], xi_map_params=mp[0], gamma_map_type=mt[1], gamma_map_params=mp[1])
+    if inp_tgt_type == 'MagGain':         # inp_tgt.py:51-52
+        return MagGain(N_d, N_s, K, f_s, gain=kwargs['gain'])
     if inp_tgt_type in _OTHER:
         raise NotImplementedError('%s has no committed model: out of scope (SURVEY 2)' % inp_tgt_type)
     raise ValueError('Invalid inp_tgt type.')
@@ -186,3 +191,102 @@ class MagXi(MagTgt):
                                                None if int16 else _lib.ptr(y), _lib.ptr(y) if int16 else None, n_out,
                                                _lib.stream_ptr(mag.device)), value_error=True)
         return ret(y[0] if squeeze else y, was_np)
+
+
+class MagXiGamma(MagTgt):
+    """Magnitude-spectrum input, mapped a priori AND a posteriori SNR target (inp_tgt.py:345-457).  No model of
+    this type is committed to the reference; the target-side arithmetic runs on the same kernels as MagXi."""
+
+    def __init__(self, N_d, N_s, K, f_s, xi_map_type, xi_map_params=None, gamma_map_type=None, gamma_map_params=None):
+        super().__init__(N_d, N_s, K, f_s)
+        self.n_feat = math.ceil(K / 2 + 1)
+        self.n_outp = self.n_feat * 2
+        self.xi_map = map_selector(xi_map_type, xi_map_params)
+        self.gamma_map = map_selector(gamma_map_type if gamma_map_type is not None else xi_map_type, gamma_map_params)
+
+    def set_stats(self, xi_stats, gamma_stats):
+        self.xi_map.set_stats(*xi_stats)
+        self.gamma_map.set_stats(*gamma_stats)
+        return self
+
+    def _split(self, xi_gamma_bar_hat):
+        t, was_np = to_dev(xi_gamma_bar_hat, torch.float32)
+        if t.shape[-1] != self.n_outp:
+            raise ValueError('last dimension must be %d' % self.n_outp)
+        return t[..., :self.n_feat].contiguous(), t[..., self.n_feat:].contiguous(), was_np
+
+    def xi_hat(self, xi_gamma_bar_hat):
+        """inp_tgt.py:431-443."""
+        xb, _, was_np = self._split(xi_gamma_bar_hat)
+        return ret(self.xi_map.inverse(xb), was_np)
+
+    def gamma_hat(self, xi_gamma_bar_hat):
+        """inp_tgt.py:445-457."""
+        _, gb, was_np = self._split(xi_gamma_bar_hat)
+        return ret(self.gamma_map.inverse(gb), was_np)
+
+    def example(self, s, d, s_len, d_len, snr, offsets=None):
+        """x_STMS and concat(xi_bar, gamma_bar) (inp_tgt.py:383-409)."""
+        so, do, xo, nfr = self.mix(s, d, s_len, d_len, snr, offsets)
+        lens = torch.tensor([int(v) for v in s_len], dtype=torch.int32).to(so.device, non_blocking=True)
+        S, _ = self._stft(so, lens)
+        D, _ = self._stft(do, lens)
+        X, _ = self._stft(xo, lens)
+        xi_bar = self.xi_map.map(self.xi(S, D))
+        gamma_bar = self.gamma_map.map(self.gamma(X, D))
+        return X, torch.cat([xi_bar, gamma_bar], dim=-1), nfr
+
+    def enhanced_speech(self, x_STMS, x_STPS, xi_gamma_bar_hat, gtype):
+        """inp_tgt.py:411-429: both SNRs from the network, gain, synthesis."""
+        from .gain import gfunc
+        mag, was_np = to_dev(x_STMS, torch.float32)
+        xb, gb, _ = self._split(xi_gamma_bar_hat)
+        G = gfunc(self.xi_map.inverse(xb), self.gamma_map.inverse(gb), gtype)
+        return ret(_synthesis_with_gain(self, mag, x_STPS, G), was_np)
+
+
+class MagGain(MagTgt):
+    """Magnitude-spectrum input, gain target (inp_tgt.py:459-519)."""
+
+    def __init__(self, N_d, N_s, K, f_s, gain):
+        super().__init__(N_d, N_s, K, f_s)
+        _lib.gtype_code(gain)                      # same ValueError as gfunc for unknown names
+        self.n_feat = math.ceil(K / 2 + 1)
+        self.n_outp = self.n_feat
+        self.gain = gain
+
+    def example(self, s, d, s_len, d_len, snr, offsets=None):
+        """x_STMS and G = gfunc(xi, gamma, self.gain) of the instantaneous SNRs (inp_tgt.py:476-501)."""
+        from .gain import gfunc
+        so, do, xo, nfr = self.mix(s, d, s_len, d_len, snr, offsets)
+        lens = torch.tensor([int(v) for v in s_len], dtype=torch.int32).to(so.device, non_blocking=True)
+        S, _ = self._stft(so, lens)
+        D, _ = self._stft(do, lens)
+        X, _ = self._stft(xo, lens)
+        return X, gfunc(self.xi(S, D), self.gamma(X, D), self.gain), nfr
+
+    def enhanced_speech(self, x_STMS, x_STPS, G_hat, gtype=None):
+        """inp_tgt.py:503-519: the network output IS the gain (thresholded at 0.5 for 'ibm')."""
+        mag, was_np = to_dev(x_STMS, torch.float32)
+        G, _ = to_dev(G_hat, torch.float32)
+        if self.gain == 'ibm':
+            G = (G > 0.5).to(torch.float32)
+        return ret(_synthesis_with_gain(self, mag, x_STPS, G), was_np)
+
+
+def _synthesis_with_gain(it, mag, x_STPS, G):
+    """(|X| G) e^{j phase} -> waveform through dxi_istft (the gain multiply is fused into the synthesis kernel)."""
+    pha, _ = to_dev(x_STPS, torch.float32)
+    G, _ = to_dev(G, torch.float32)
+    if not (mag.shape == pha.shape == G.shape) or mag.shape[-1] != it.n_bins:
+        raise ValueError('x_STMS, x_STPS and the gain must share the shape [..., T, %d]' % it.n_bins)
+    squeeze = mag.dim() == 2
+    if squeeze:
+        mag, pha, G = mag[None], pha[None], G[None]
+    B, T, _ = mag.shape
+    n_out = (T + 1) * it.N_s
+    y = torch.empty((B, n_out), dtype=torch.float32, device=mag.device)
+    if B and T:
+        _lib.check(_lib.load().dxi_istft(_lib.ptr(mag.contiguous()), _lib.ptr(G.contiguous()), _lib.ptr(pha.contiguous()), None, B, T,
+                                         _lib.ptr(y), None, n_out, _lib.stream_ptr(mag.device)))
+    return y[0] if squeeze else y

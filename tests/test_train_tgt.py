@@ -154,3 +154,47 @@ def test_stats_match_oracle_and_set_the_map():
     # half + half = whole (what the all-reduce relies on)
     a = it.xi_db_moments(so[:4], do[:4], s_len[:4]) + it.xi_db_moments(so[4:], do[4:], s_len[4:])
     assert np.allclose(a.cpu().numpy(), acc, rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_magxigamma_and_maggain_targets_match_oracle():
+    """the two other magnitude-domain targets (inp_tgt.py:345-519) on the same kernels: examples and
+    enhanced speech against the oracle's primitives."""
+    from deepxi_b200.inp_tgt import inp_tgt_selector
+    from oracle import gain as ogain
+    mu, sg = stats.packaged('resnet-1.1c')
+    s, d, s_len, d_len, snr, off = _corpus(n=3, seed=13)
+    so, do, xo, nfr = train_tgt.mix(s, d, s_len, d_len, snr, off)
+    xg = inp_tgt_selector('MagXiGamma', 512, 256, 512, 16000, map_type=['DBNormalCDF', 'DBNormalCDF'], map_params=[None, None])
+    xg.set_stats((mu, sg), (mu + 3.0, sg * 0.9))
+    X, tgt, n2 = xg.example(s, d, s_len, d_len, snr, off)
+    assert n2 == nfr and tuple(tgt.shape) == (3, max(nfr), 514)
+    tgt = tgt.cpu().numpy()
+    for i, n in enumerate(nfr):
+        S, _ = sig.polar_analysis(so[i, :s_len[i]]); D, _ = sig.polar_analysis(do[i, :s_len[i]]); Xo, _ = sig.polar_analysis(xo[i, :s_len[i]])
+        r_xi = cdfmap.normal_cdf_map(train_tgt.xi(S, D), mu, sg)
+        r_ga = cdfmap.normal_cdf_map(train_tgt.gamma(Xo, D), mu + 3.0, sg * 0.9)
+        assert np.quantile(np.abs(tgt[i, :n, :257] - r_xi), 0.999) < 2e-4 and np.quantile(np.abs(tgt[i, :n, 257:] - r_ga), 0.999) < 2e-4
+    # enhanced speech from a synthetic network output: both halves inverted, gfunc, synthesis
+    rng = np.random.default_rng(4)
+    xb = rng.uniform(0.02, 0.98, (40, 514)).astype(np.float32)
+    mag = np.abs(rng.standard_normal((40, 257))).astype(np.float32)
+    pha = rng.uniform(-3.1, 3.1, (40, 257)).astype(np.float32)
+    y = xg.enhanced_speech(mag, pha, xb, 'mmse-stsa')
+    xi_o = cdfmap.normal_cdf_inverse(xb[:, :257], mu, sg)
+    ga_o = cdfmap.normal_cdf_inverse(xb[:, 257:], mu + 3.0, sg * 0.9)
+    y_ref = sig.polar_synthesis(mag * ogain.gfunc(xi_o, ga_o, 'mmse-stsa'), pha)
+    err = y[:len(y_ref)] - y_ref
+    assert 10 * np.log10(np.sum(y_ref.astype(np.float64) ** 2) / np.sum(err.astype(np.float64) ** 2)) > 70.0
+    assert np.allclose(xg.xi_hat(xb), xi_o, rtol=3e-5) and np.allclose(xg.gamma_hat(xb), ga_o, rtol=3e-5)
+    # MagGain: target = gfunc of the instantaneous SNRs; enhanced speech = |X| G_hat (thresholded for 'ibm')
+    mg = inp_tgt_selector('MagGain', 512, 256, 512, 16000, gain='irm')
+    X2, G, n3 = mg.example(s, d, s_len, d_len, snr, off)
+    G = G.cpu().numpy()
+    S, _ = sig.polar_analysis(so[0, :s_len[0]]); D, _ = sig.polar_analysis(do[0, :s_len[0]])
+    r_G = ogain.gfunc(train_tgt.xi(S, D), None, 'irm')
+    assert np.quantile(np.abs(G[0, :nfr[0]] - r_G), 0.999) < 2e-4 and G.min() >= 0.0 and G.max() <= 1.0
+    gh = rng.uniform(0, 1, (40, 257)).astype(np.float32)
+    assert np.abs(mg.enhanced_speech(mag, pha, gh)[:len(y_ref)] - sig.polar_synthesis(mag * gh, pha)).max() < 2e-6
+    mi = inp_tgt_selector('MagGain', 512, 256, 512, 16000, gain='ibm')
+    assert np.abs(mi.enhanced_speech(mag, pha, gh)[:len(y_ref)] - sig.polar_synthesis(mag * (gh > 0.5), pha)).max() < 2e-6
