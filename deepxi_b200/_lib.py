@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libdeepxi_b200.so')
 
 GTYPES = {'mmse-lsa': 0, 'mmse-stsa': 1, 'wf': 2, 'srwf': 3, 'cwf': 4, 'irm': 5, 'ibm': 6, 'deepmmse': 7}
-NET_KINDS = {'ResNetV2': 0, 'MHANetV3': 1}
+NET_KINDS = {'ResNetV2': 0, 'MHANetV3': 1, 'ResNet': 2, 'ResNetV3': 3}
 PRECISIONS = {'f32': 0, 'f16x3': 1, 'f16': 2}
 PADDINGS = {'causal': 0, 'same': 1}
 MASK_MODES = {'none': 0, 'causal+pad': 1}

@@ -93,7 +93,7 @@ def get_parser():
     p.add_argument('--map_type', type=str_to_list)
     p.add_argument('--map_params', default=[None, None], type=str_to_list)
     # deepxi_b200 only
-    p.add_argument('--precision', default='f16x3', type=str, help="arithmetic of the network: 'f16x3' (tcgen05, default) | 'f32' | 'f16'")
+    p.add_argument('--precision', default=None, type=str, help="arithmetic of the network: 'f16x3' (tcgen05; default for ResNetV2 / MHANetV3) | 'f32' (default and only mode of ResNet / ResNetV3) | 'f16'")
     p.add_argument('--mask_mode', default='none', type=str, help="MHANetV3: 'none' (shipped behaviour) | 'causal+pad'")
     p.add_argument('--synthetic_weights', default=None, type=int, help='seed of random weights in the checkpoint shapes (the reference tree ships no weight shards); default: load model_path')
     return p

@@ -23,6 +23,31 @@ std::map<std::string, std::vector<int64_t>> expected_shapes(int kind, const dxi_
     }
     s[nm(li, "kernel")] = {1, c.d_model, c.n_outp};
     s[nm(li, "bias")] = {c.n_outp};
+  } else if (kind == DXI_NET_RESNETV3) {      // ResNetV2 without the LayerNorm weights of the first layer (tcn.py:241-244)
+    s[nm(0, "kernel")] = {1, c.n_feat, c.d_model};
+    s[nm(0, "bias")] = {c.d_model};
+    int li = 1;
+    for (int i = 0; i < c.n_blocks; ++i) {
+      s[nm(li, "kernel")] = {1, c.d_model, c.d_f};      s[nm(li, "bias")] = {c.d_f};
+      s[nm(li + 1, "kernel")] = {c.k, c.d_f, c.d_f};    s[nm(li + 1, "bias")] = {c.d_f};
+      s[nm(li + 2, "kernel")] = {1, c.d_f, c.d_model};  s[nm(li + 2, "bias")] = {c.d_model};
+      li += 3;
+    }
+    s[nm(li, "kernel")] = {1, c.d_model, c.n_outp};
+    s[nm(li, "bias")] = {c.n_outp};
+  } else if (kind == DXI_NET_RESNET) {        // tcn.py:17-114; order and sizes as in log/summary/resnet-1.0c.txt (1 975 553 parameters)
+    s[nm(0, "kernel")] = {1, c.n_feat, c.d_model};
+    s[nm(1, "gamma")] = {c.d_model};  s[nm(1, "beta")] = {c.d_model};
+    int li = 2;
+    for (int i = 0; i < c.n_blocks; ++i) {
+      s[nm(li, "gamma")] = {c.d_model};    s[nm(li, "beta")] = {c.d_model};      s[nm(li + 1, "kernel")] = {1, c.d_model, c.d_f};
+      s[nm(li + 2, "gamma")] = {c.d_f};    s[nm(li + 2, "beta")] = {c.d_f};      s[nm(li + 3, "kernel")] = {c.k, c.d_f, c.d_f};
+      s[nm(li + 4, "gamma")] = {c.d_f};    s[nm(li + 4, "beta")] = {c.d_f};      s[nm(li + 5, "kernel")] = {1, c.d_f, c.d_model};
+      s[nm(li + 5, "bias")] = {c.d_model};
+      li += 6;
+    }
+    s[nm(li, "kernel")] = {1, c.d_model, c.n_outp};
+    s[nm(li, "bias")] = {c.n_outp};
   } else {
     const int64_t dk = c.d_model / c.n_heads, dff = 4 * c.d_model;
     s[nm(0, "kernel")] = {1, c.n_feat, c.d_model};
@@ -51,10 +76,13 @@ std::map<std::string, std::vector<int64_t>> expected_shapes(int kind, const dxi_
 extern "C" DXI_API int dxi_net_create(dxi_net_t** h, int kind, const dxi_net_cfg* cfg) {
   if (int rc = check_device()) return rc;
   DXI_REQUIRE(h && cfg, "dxi_net_create: null argument");
-  if (kind != DXI_NET_RESNETV2 && kind != DXI_NET_MHANETV3) { set_error("Invalid network type."); return DXI_E_INVALID; }
+  if (kind < DXI_NET_RESNETV2 || kind > DXI_NET_RESNETV3) { set_error("Invalid network type."); return DXI_E_INVALID; }
+  if ((kind == DXI_NET_RESNET || kind == DXI_NET_RESNETV3) && cfg->precision != DXI_PREC_F32) {
+    set_error("ResNet / ResNetV3 are built for precision f32 only"); return DXI_E_INVALID;
+  }
   DXI_REQUIRE(cfg->precision >= DXI_PREC_F32 && cfg->precision <= DXI_PREC_F16, "dxi_net_create: bad precision");
   DXI_REQUIRE(cfg->n_feat > 0 && cfg->n_outp > 0 && cfg->d_model > 0 && cfg->n_blocks > 0, "dxi_net_create: bad sizes");
-  if (kind == DXI_NET_RESNETV2) {
+  if (kind != DXI_NET_MHANETV3) {
     DXI_REQUIRE(cfg->padding == DXI_PAD_CAUSAL || cfg->padding == DXI_PAD_SAME, "dxi_net_create: bad padding");
     DXI_REQUIRE(cfg->max_d_rate >= 1 && (cfg->max_d_rate & (cfg->max_d_rate - 1)) == 0, "dxi_net_create: max_d_rate must be a power of two");
   } else {
@@ -132,7 +160,7 @@ extern "C" DXI_API int dxi_net_finalize(dxi_net_t* h, void* stream) {
 
 extern "C" DXI_API int64_t dxi_net_workspace_bytes(const dxi_net_t* h, int B, int Tmax) {
   if (!h || B < 0 || Tmax < 0) return DXI_E_INVALID;
-  if (h->kind == DXI_NET_RESNETV2)
+  if (h->kind != DXI_NET_MHANETV3)
     return h->cfg.precision == DXI_PREC_F32 ? resnet_f32_workspace_bytes(*h, B, Tmax) : resnet_umma_workspace_bytes(*h, B, Tmax);
   return mhanet_workspace_bytes(*h, B, Tmax);
 }
@@ -146,7 +174,7 @@ extern "C" DXI_API int dxi_net_forward(dxi_net_t* h, const float* mag, int B, in
   if (B == 0 || Tmax == 0) return DXI_OK;
   DXI_REQUIRE(workspace, "dxi_net_forward: null workspace");
   cudaStream_t st = as_stream(stream);
-  if (h->kind == DXI_NET_RESNETV2) {
+  if (h->kind != DXI_NET_MHANETV3) {
     if (h->cfg.precision == DXI_PREC_F32) return resnet_f32_forward(*h, mag, B, Tmax, xbar, workspace, workspace_bytes, st);
     return resnet_umma_forward(*h, mag, B, Tmax, xbar, workspace, workspace_bytes, st);
   }

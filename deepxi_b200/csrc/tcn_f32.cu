@@ -1,4 +1,8 @@
-// ResNetV2 forward on the fp32 CUDA cores (precision mode DXI_PREC_F32, "exact mode").
+// ResNetV2 forward on the fp32 CUDA cores (precision mode DXI_PREC_F32, "exact mode"), and the two sibling architectures of
+// deepxi/network/tcn.py that only exist in this mode:
+//   ResNet   (tcn.py:17-114)   first layer Conv1D(no bias) -> LN(gamma, beta) -> ReLU; unit LN(gamma, beta) -> ReLU -> Conv1D
+//                              (bias only in the third unit of a block)
+//   ResNetV3 (tcn.py:227-245)  ResNetV2 with the first layer Conv1D+b -> ReLU -> LN(no affine)
 //
 // One kernel per convolutional unit of deepxi/network/tcn.py:116-225:
 //   stem  (tcn.py:166-180)  Conv1D(256,1)+b -> LayerNorm(scale gamma, no centre) -> ReLU
@@ -18,8 +22,8 @@ namespace dxi {
 constexpr int TM = 64;       // frames per CTA
 constexpr int KC = 16;       // K-chunk of the weight stream
 
-enum { PRE_NONE = 0, PRE_RELU_LN = 1 };
-enum { POST_BIAS = 0, POST_RESIDUAL = 1, POST_LN_SCALE_RELU = 2, POST_SIGMOID = 3 };
+enum { PRE_NONE = 0, PRE_RELU_LN = 1, PRE_LN_AFF_RELU = 2 };
+enum { POST_BIAS = 0, POST_RESIDUAL = 1, POST_LN_SCALE_RELU = 2, POST_SIGMOID = 3, POST_RELU_LN = 4, POST_LN_AFF_RELU = 5 };
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -30,7 +34,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <int CIN, int COUT, int TAPS, int PRE, int POST>
 __global__ void __launch_bounds__(256) unit_f32_kernel(const float* __restrict__ in, const float* __restrict__ W,
                                                        const float* __restrict__ bias, const float* __restrict__ gamma,
-                                                       const float* res, float* out, int T,
+                                                       const float* __restrict__ beta, const float* __restrict__ pre_gamma,
+                                                       const float* __restrict__ pre_beta, const float* res, float* out, int T,
                                                        int tiles_per_utt, int d_rate, int causal) {
   constexpr int KT = TAPS * CIN;
   constexpr int LDA = KT + 1;
@@ -65,7 +70,7 @@ __global__ void __launch_bounds__(256) unit_f32_kernel(const float* __restrict__
 #pragma unroll
       for (int i = 0; i < PER; ++i) {
         const int c = lane + 32 * i;
-        x[i] = c < CIN ? fmaxf(src[c], 0.0f) : 0.0f;
+        x[i] = c < CIN ? (PRE == PRE_RELU_LN ? fmaxf(src[c], 0.0f) : src[c]) : 0.0f;
         s += x[i];
       }
       const float mean = warp_sum(s) * (1.0f / CIN);
@@ -81,7 +86,12 @@ __global__ void __launch_bounds__(256) unit_f32_kernel(const float* __restrict__
 #pragma unroll
       for (int i = 0; i < PER; ++i) {
         const int c = lane + 32 * i;
-        if (c < CIN) dst[c] = fmaf(x[i], inv, off);
+        if (c >= CIN) continue;
+        if (PRE == PRE_RELU_LN) dst[c] = fmaf(x[i], inv, off);
+        else {      // LayerNormalization(gamma, beta) -> ReLU   (tcn.py:108-110)
+          const float g = inv * __ldg(pre_gamma + c);
+          dst[c] = fmaxf(fmaf(x[i], g, __ldg(pre_beta + c) - mean * g), 0.0f);
+        }
       }
     }
   }
@@ -120,7 +130,7 @@ __global__ void __launch_bounds__(256) unit_f32_kernel(const float* __restrict__
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
       const int col = tx + 16 * c;
-      if (col < COUT) O[(ty * RM + i) * LDO + col] = acc[i][c] + __ldg(bias + col);
+      if (col < COUT) O[(ty * RM + i) * LDO + col] = acc[i][c] + (bias ? __ldg(bias + col) : 0.0f);
     }
   __syncthreads();
   // ---- phase 3: row-wise epilogue, one warp per row, coalesced stores
@@ -135,16 +145,21 @@ __global__ void __launch_bounds__(256) unit_f32_kernel(const float* __restrict__
       for (int c = lane; c < COUT; c += 32) out[o + c] = res[o + c] + row[c];
     } else if (POST == POST_SIGMOID) {
       for (int c = lane; c < COUT; c += 32) out[o + c] = 1.0f / (1.0f + expf(-row[c]));
-    } else {   // LayerNorm(scale=gamma, centre=False, eps 1e-6) -> ReLU   (tcn.py:176-179)
+    } else {
+      // POST_LN_SCALE_RELU: LayerNorm(scale=gamma, centre=False, eps 1e-6) -> ReLU   (ResNetV2, tcn.py:176-179)
+      // POST_LN_AFF_RELU:   LayerNorm(gamma, beta) -> ReLU                           (ResNet,   tcn.py:73-76)
+      // POST_RELU_LN:       ReLU -> LayerNorm(no affine)                             (ResNetV3, tcn.py:241-244)
       float s = 0.0f;
-      for (int c = lane; c < COUT; c += 32) s += row[c];
+      for (int c = lane; c < COUT; c += 32) s += POST == POST_RELU_LN ? fmaxf(row[c], 0.0f) : row[c];
       const float mean = warp_sum(s) * (1.0f / COUT);
       float q = 0.0f;
-      for (int c = lane; c < COUT; c += 32) { const float dlt = row[c] - mean; q += dlt * dlt; }
+      for (int c = lane; c < COUT; c += 32) { const float dlt = (POST == POST_RELU_LN ? fmaxf(row[c], 0.0f) : row[c]) - mean; q += dlt * dlt; }
       const float rs = rsqrtf(warp_sum(q) * (1.0f / COUT) + 1e-6f);
       for (int c = lane; c < COUT; c += 32) {
+        if (POST == POST_RELU_LN) { out[o + c] = fmaf(fmaxf(row[c], 0.0f), rs, -mean * rs); continue; }
         const float inv = rs * __ldg(gamma + c);
-        out[o + c] = fmaxf(fmaf(row[c], inv, -mean * inv), 0.0f);
+        const float off = (POST == POST_LN_AFF_RELU ? __ldg(beta + c) : 0.0f) - mean * inv;
+        out[o + c] = fmaxf(fmaf(row[c], inv, off), 0.0f);
       }
     }
   }
@@ -152,14 +167,15 @@ __global__ void __launch_bounds__(256) unit_f32_kernel(const float* __restrict__
 
 template <int CIN, int COUT, int TAPS, int PRE, int POST>
 static int launch_unit(const float* in, const float* W, const float* bias, const float* gamma, const float* res,
-                       float* out, int B, int T, int d_rate, int causal, cudaStream_t st) {
+                       float* out, int B, int T, int d_rate, int causal, cudaStream_t st, const float* beta = nullptr,
+                       const float* pre_gamma = nullptr, const float* pre_beta = nullptr) {
   constexpr int KT = TAPS * CIN;
   constexpr int LD = (KT + 1) > (COUT + 1) ? (KT + 1) : (COUT + 1);
   const size_t smem = sizeof(float) * (TM * LD + KC * COUT);
   auto kern = unit_f32_kernel<CIN, COUT, TAPS, PRE, POST>;
   DXI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles = (T + TM - 1) / TM;
-  kern<<<B * tiles, 256, smem, st>>>(in, W, bias, gamma, res, out, T, tiles, d_rate, causal);
+  kern<<<B * tiles, 256, smem, st>>>(in, W, bias, gamma, beta, pre_gamma, pre_beta, res, out, T, tiles, d_rate, causal);
   DXI_LAUNCHED("unit_f32_kernel");
   return DXI_OK;
 }
@@ -184,13 +200,41 @@ int resnet_f32_forward(const dxi_net& net, const float* mag, int B, int T, float
   float* u2 = u1 + rows * 64;
   const int causal = c.padding == DXI_PAD_CAUSAL;
   auto Wt = [&](int li, const char* var) { return net.dev_tensor(li, var); };
-  int rc = launch_unit<257, 256, 1, PRE_NONE, POST_LN_SCALE_RELU>(mag, Wt(0, "kernel"), Wt(0, "bias"), Wt(1, "gamma"),
-                                                                 nullptr, h, B, T, 1, causal, st);
+  int n_rates = 0;
+  for (int m = c.max_d_rate; m > 0; m >>= 1) ++n_rates;          // log2(max_d_rate) + 1   (tcn.py:55-56, :156-157)
+  int rc;
+  if (net.kind == DXI_NET_RESNET) {
+    // layer_with_weights: 0 conv (no bias), 1 LN; per block LN, conv, LN, conv, LN, conv(+bias); last conv (+bias)
+    rc = launch_unit<257, 256, 1, PRE_NONE, POST_LN_AFF_RELU>(mag, Wt(0, "kernel"), nullptr, Wt(1, "gamma"), nullptr, h, B, T, 1,
+                                                              causal, st, Wt(1, "beta"));
+    if (rc) return rc;
+    int li = 2;
+    for (int i = 0; i < c.n_blocks; ++i) {
+      const int d = 1 << (i % n_rates);
+      rc = launch_unit<256, 64, 1, PRE_LN_AFF_RELU, POST_BIAS>(h, Wt(li + 1, "kernel"), nullptr, nullptr, nullptr, u1, B, T, 1, causal, st,
+                                                               nullptr, Wt(li, "gamma"), Wt(li, "beta"));
+      if (rc) return rc;
+      rc = launch_unit<64, 64, 3, PRE_LN_AFF_RELU, POST_BIAS>(u1, Wt(li + 3, "kernel"), nullptr, nullptr, nullptr, u2, B, T, d, causal, st,
+                                                              nullptr, Wt(li + 2, "gamma"), Wt(li + 2, "beta"));
+      if (rc) return rc;
+      rc = launch_unit<64, 256, 1, PRE_LN_AFF_RELU, POST_RESIDUAL>(u2, Wt(li + 5, "kernel"), Wt(li + 5, "bias"), nullptr, h, h, B, T, 1,
+                                                                   causal, st, nullptr, Wt(li + 4, "gamma"), Wt(li + 4, "beta"));
+      if (rc) return rc;
+      li += 6;
+    }
+    return launch_unit<256, 257, 1, PRE_NONE, POST_SIGMOID>(h, Wt(li, "kernel"), Wt(li, "bias"), nullptr, nullptr, xbar, B, T, 1, causal, st);
+  }
+  int li;
+  if (net.kind == DXI_NET_RESNETV3) {      // Conv1D+b -> ReLU -> LN(no affine): no LayerNorm weights, the blocks start at layer 1
+    rc = launch_unit<257, 256, 1, PRE_NONE, POST_RELU_LN>(mag, Wt(0, "kernel"), Wt(0, "bias"), nullptr, nullptr, h, B, T, 1, causal, st);
+    li = 1;
+  } else {
+    rc = launch_unit<257, 256, 1, PRE_NONE, POST_LN_SCALE_RELU>(mag, Wt(0, "kernel"), Wt(0, "bias"), Wt(1, "gamma"),
+                                                               nullptr, h, B, T, 1, causal, st);
+    li = 2;
+  }
   if (rc) return rc;
-  int li = 2;
   for (int i = 0; i < c.n_blocks; ++i) {
-    int n_rates = 0;
-    for (int m = c.max_d_rate; m > 0; m >>= 1) ++n_rates;          // log2(max_d_rate) + 1   (tcn.py:156-157)
     const int d = 1 << (i % n_rates);
     rc = launch_unit<256, 64, 1, PRE_RELU_LN, POST_BIAS>(h, Wt(li, "kernel"), Wt(li, "bias"), nullptr, nullptr, u1, B, T, 1, causal, st);
     if (rc) return rc;

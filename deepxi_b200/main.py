@@ -15,7 +15,7 @@ from .se_batch import Batch
 
 def network_kwargs(args):
     """Constructor arguments of the selected network from the flat flag namespace (what **vars(args) does in main.py:59)."""
-    if args.network_type == 'ResNetV2':
+    if args.network_type in ('ResNetV2', 'ResNetV3', 'ResNet'):
         kw = dict(d_model=args.d_model, n_blocks=args.n_blocks, d_f=args.d_f, k=args.k, max_d_rate=args.max_d_rate,
                   padding=args.padding, unit_type=args.unit_type, outp_act=args.outp_act)
     elif args.network_type in ('MHANetV3', 'MHANetV2'):
@@ -24,7 +24,7 @@ def network_kwargs(args):
     else:
         kw = {}
     kw = {k: v for k, v in kw.items() if v is not None}
-    kw['precision'] = args.precision
+    kw['precision'] = args.precision or ('f32' if args.network_type in ('ResNet', 'ResNetV3') else 'f16x3')
     return kw
 
 
@@ -51,7 +51,8 @@ def main(argv=None):
                     reset_inp_tgt=args.reset_inp_tgt, map_type=map_type, map_params=map_params, **network_kwargs(args))
     if args.synthetic_weights is not None:
         from . import weights
-        make = weights.synthetic_resnetv2 if args.network_type == 'ResNetV2' else weights.synthetic_mhanetv3
+        make = {'ResNetV2': weights.synthetic_resnetv2, 'ResNetV3': weights.synthetic_resnetv3,
+                'ResNet': weights.synthetic_resnet}.get(args.network_type, weights.synthetic_mhanetv3)
         deepxi.set_weights(make(args.synthetic_weights))
     deepxi.infer(test_x=test_x, test_x_len=test_x_len, test_x_base_names=test_x_base_names, test_epoch=args.test_epoch,
                  model_path=args.model_path, out_type=args.out_type, gain=args.gain, out_path=args.out_path,

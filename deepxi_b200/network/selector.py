@@ -1,12 +1,12 @@
 """Mirror of deepxi/network/selector.py network_selector (:8-132).
 
-Same keyword arguments as the reference.  Networks without a committed checkpoint (MHANetV2, MHANet,
-RDLNet, ResNet, ResNetV3, ResNetV4, ResLSTM, ResBiLSTM) raise NotImplementedError; unknown names raise
+Same keyword arguments as the reference.  ResNetV2 and MHANetV3 (the committed checkpoints) run on tcgen05; ResNet and ResNetV3
+run in the exact fp32 mode; the remaining networks (MHANetV2, MHANet, RDLNet, ResNetV4, ResLSTM, ResBiLSTM) raise NotImplementedError; unknown names raise
 ValueError('Invalid network type.') as selector.py:131 does.  `precision` ('f32' | 'f16x3' | 'f16') and
 `mask_mode` are extensions.
 """
 
-_OTHER = ('MHANetV2', 'MHANet', 'RDLNet', 'ResNetV4', 'ResNetV3', 'ResNet', 'ResBiLSTM', 'ResLSTM')
+_OTHER = ('MHANetV2', 'MHANet', 'RDLNet', 'ResNetV4', 'ResBiLSTM', 'ResLSTM')
 
 
 def network_selector(network_type, inp, n_outp, **kwargs):
@@ -22,6 +22,15 @@ def network_selector(network_type, inp, n_outp, **kwargs):
         return ResNetV2(inp=inp, n_outp=n_outp, n_blocks=kwargs['n_blocks'], d_model=kwargs['d_model'],
                         d_f=kwargs['d_f'], k=kwargs['k'], max_d_rate=kwargs['max_d_rate'], padding=kwargs['padding'],
                         unit_type=kwargs['unit_type'], outp_act=kwargs['outp_act'], **extra)
+    if network_type in ('ResNet', 'ResNetV3'):      # selector.py:86-104
+        from .tcn import ResNet, ResNetV3
+        extra.pop('mask_mode', None)
+        extra.setdefault('precision', 'f32')
+        common = dict(inp=inp, n_outp=n_outp, n_blocks=kwargs['n_blocks'], d_model=kwargs['d_model'], d_f=kwargs['d_f'], k=kwargs['k'],
+                      max_d_rate=kwargs['max_d_rate'], padding=kwargs['padding'], outp_act=kwargs['outp_act'], **extra)
+        if network_type == 'ResNet':
+            return ResNet(**common)
+        return ResNetV3(unit_type=kwargs.get('unit_type', 'ReLU->LN->W+b'), **common)
     if network_type in _OTHER:
         raise NotImplementedError('%s has no committed checkpoint: out of scope (SURVEY 2)' % network_type)
     raise ValueError('Invalid network type.')

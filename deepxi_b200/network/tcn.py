@@ -1,5 +1,6 @@
-"""Mirror of deepxi/network/tcn.py ResNetV2 (:116-225): bottleneck residual TCN with cyclic dilation,
-frame-wise layer normalisation without affine parameters inside the blocks, unit "ReLU->LN->W+b"."""
+"""Mirror of deepxi/network/tcn.py: ResNetV2 (:116-225: bottleneck residual TCN with cyclic dilation, frame-wise layer
+normalisation without affine parameters inside the blocks, unit "ReLU->LN->W+b"), and its siblings ResNet (:17-114, the
+resnet-1.0c architecture) and ResNetV3 (:227-245), which run in the exact fp32 mode only."""
 from .. import _lib
 from ._base import DeviceNetwork
 
@@ -24,3 +25,22 @@ class ResNetV2(DeviceNetwork):
                           precision=0)
         self.padding = padding
         super().__init__(cfg, precision)
+
+
+class ResNetV3(ResNetV2):
+    """ResNetV2 with the first layer Conv1D+b -> ReLU -> LayerNorm(no affine) (tcn.py:227-245).  precision 'f32' only."""
+    kind = 'ResNetV3'
+
+    def __init__(self, inp=None, n_outp=257, n_blocks=40, d_model=256, d_f=64, k=3, max_d_rate=16, padding='causal',
+                 unit_type='ReLU->LN->W+b', outp_act='Sigmoid', n_feat=257, precision='f32'):
+        super().__init__(inp, n_outp, n_blocks, d_model, d_f, k, max_d_rate, padding, unit_type, outp_act, n_feat, precision)
+
+
+class ResNet(ResNetV2):
+    """ResNet v1.0 (tcn.py:17-114): first layer Conv1D(no bias) -> LN(gamma, beta) -> ReLU, unit LN(gamma, beta) -> ReLU -> Conv1D,
+    bias only in the third unit of a block.  precision 'f32' only."""
+    kind = 'ResNet'
+
+    def __init__(self, inp=None, n_outp=257, n_blocks=40, d_model=256, d_f=64, k=3, max_d_rate=16, padding='causal',
+                 outp_act='Sigmoid', n_feat=257, precision='f32'):
+        super().__init__(inp, n_outp, n_blocks, d_model, d_f, k, max_d_rate, padding, 'ReLU->LN->W+b', outp_act, n_feat, precision)

@@ -35,6 +35,38 @@ def resnetv2_shapes(n_blocks=40, d_model=256, d_f=64, k=3, n_feat=257, n_outp=25
     return s
 
 
+def resnetv3_shapes(n_blocks=40, d_model=256, d_f=64, k=3, n_feat=257, n_outp=257):
+    """ResNetV3 (tcn.py:227-245): ResNetV2 whose first layer has no LayerNorm weights, so every later index is one lower."""
+    s = {_LW % (0, 'kernel'): (1, n_feat, d_model), _LW % (0, 'bias'): (d_model,)}
+    li = 1
+    for _ in range(n_blocks):
+        for (kk, cin, cout) in ((1, d_model, d_f), (k, d_f, d_f), (1, d_f, d_model)):
+            s[_LW % (li, 'kernel')] = (kk, cin, cout)
+            s[_LW % (li, 'bias')] = (cout,)
+            li += 1
+    s[_LW % (li, 'kernel')] = (1, d_model, n_outp)
+    s[_LW % (li, 'bias')] = (n_outp,)
+    return s
+
+
+def resnet_shapes(n_blocks=40, d_model=256, d_f=64, k=3, n_feat=257, n_outp=257):
+    """ResNet v1.0 (tcn.py:17-114; layer order and sizes of log/summary/resnet-1.0c.txt: 1 975 553 parameters): first conv without
+    bias, LN(gamma, beta); per block LN, conv, LN, conv, LN, conv (+bias only on the last); output conv with bias."""
+    s = {_LW % (0, 'kernel'): (1, n_feat, d_model), _LW % (1, 'gamma'): (d_model,), _LW % (1, 'beta'): (d_model,)}
+    li = 2
+    for _ in range(n_blocks):
+        for j, (kk, cin, cout) in enumerate(((1, d_model, d_f), (k, d_f, d_f), (1, d_f, d_model))):
+            s[_LW % (li, 'gamma')] = (cin,)
+            s[_LW % (li, 'beta')] = (cin,)
+            s[_LW % (li + 1, 'kernel')] = (kk, cin, cout)
+            if j == 2:
+                s[_LW % (li + 1, 'bias')] = (cout,)
+            li += 2
+    s[_LW % (li, 'kernel')] = (1, d_model, n_outp)
+    s[_LW % (li, 'bias')] = (n_outp,)
+    return s
+
+
 def mhanetv3_shapes(n_blocks=5, d_model=256, n_heads=8, max_len=2048, n_feat=257, n_outp=257):
     d_k, d_ff = d_model // n_heads, 4 * d_model
     s = {_LW % (0, 'kernel'): (1, n_feat, d_model), _LW % (1, 'gamma'): (d_model,), _LW % (1, 'beta'): (d_model,),
@@ -85,6 +117,25 @@ def synthetic_resnetv2(seed=0, **kw):
         li = int(name.split('/')[0].split('-')[-1])
         if li == last: return 0.2
         if li >= 2 and (li - 2) % 3 == 2: return 0.3
+        return 1.0
+    return _synth(shapes, seed, rule)
+
+
+def synthetic_resnetv3(seed=0, **kw):
+    shapes = resnetv3_shapes(**kw)
+    last = max(int(n.split('/')[0].split('-')[-1]) for n in shapes)
+    return _synth(shapes, seed, lambda name, shp: 0.2 if int(name.split('/')[0].split('-')[-1]) == last else
+                  (0.3 if (int(name.split('/')[0].split('-')[-1]) - 1) % 3 == 2 and int(name.split('/')[0].split('-')[-1]) >= 1 else 1.0))
+
+
+def synthetic_resnet(seed=0, **kw):
+    shapes = resnet_shapes(**kw)
+    last = max(int(n.split('/')[0].split('-')[-1]) for n in shapes)
+
+    def rule(name, shp):
+        li = int(name.split('/')[0].split('-')[-1])
+        if li == last: return 0.2
+        if li >= 2 and (li - 2) % 6 == 5: return 0.3          # third conv of a block
         return 1.0
     return _synth(shapes, seed, rule)
 

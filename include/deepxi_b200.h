@@ -55,6 +55,8 @@ extern "C" {
 /* network kinds of deepxi/network/selector.py:8-132 that have committed checkpoints */
 #define DXI_NET_RESNETV2  0
 #define DXI_NET_MHANETV3  1
+#define DXI_NET_RESNET    2   /* tcn.py:17-114  (resnet-1.0c architecture; precision f32 only) */
+#define DXI_NET_RESNETV3  3   /* tcn.py:227-245 (precision f32 only) */
 
 /* Conv1D padding of the TCN (main.py:24-25: causal -> "causal", else "same") */
 #define DXI_PAD_CAUSAL 0

@@ -85,3 +85,38 @@ def resnetv2_forward(inp, w, n_blocks=40, max_d_rate=16, padding='causal', dtype
     if return_logits:
         return z.numpy()
     return torch.sigmoid(z).numpy()
+
+
+def resnetv3_forward(inp, w, n_blocks=40, max_d_rate=16, padding='causal', dtype=torch.float32):
+    """ResNetV3 (tcn.py:227-245): first layer Conv1D+b -> ReLU -> LayerNorm(center=False, scale=False); blocks and output as
+    ResNetV2, layer indices one lower (the first LayerNorm has no weights)."""
+    g = lambda name: torch.as_tensor(np.asarray(w[name]), dtype=dtype)
+    x = torch.as_tensor(np.asarray(inp), dtype=dtype)
+    lw = 'layer_with_weights-%d/%s'
+    h = layer_norm(torch.relu(conv1d(x, g(lw % (0, 'kernel')), g(lw % (0, 'bias')))))
+    li = 1
+    for d in dilation_rates(n_blocks, max_d_rate):
+        y = h
+        for d_u in (1, d, 1):
+            y = conv1d(layer_norm(torch.relu(y)), g(lw % (li, 'kernel')), g(lw % (li, 'bias')), d_u, padding)
+            li += 1
+        h = h + y
+    return torch.sigmoid(conv1d(h, g(lw % (li, 'kernel')), g(lw % (li, 'bias')))).numpy()
+
+
+def resnet_forward(inp, w, n_blocks=40, max_d_rate=16, padding='causal', dtype=torch.float32):
+    """ResNet v1.0 (tcn.py:17-114): feedforward Conv1D(no bias) -> LN(gamma, beta) -> ReLU (:62-77); unit LN(gamma, beta) -> ReLU ->
+    Conv1D (:95-114), use_bias only in conv_3 (:79-93); dilation 2**(i % (log2(max_d_rate)+1)) (:55-56)."""
+    g = lambda name: torch.as_tensor(np.asarray(w[name]), dtype=dtype)
+    x = torch.as_tensor(np.asarray(inp), dtype=dtype)
+    lw = 'layer_with_weights-%d/%s'
+    h = torch.relu(layer_norm(conv1d(x, g(lw % (0, 'kernel')), None), g(lw % (1, 'gamma')), g(lw % (1, 'beta'))))
+    li = 2
+    for d in dilation_rates(n_blocks, max_d_rate):
+        y = h
+        for j, d_u in enumerate((1, d, 1)):
+            y = torch.relu(layer_norm(y, g(lw % (li, 'gamma')), g(lw % (li, 'beta'))))
+            y = conv1d(y, g(lw % (li + 1, 'kernel')), g(lw % (li + 1, 'bias')) if j == 2 else None, d_u, padding)
+            li += 2
+        h = h + y
+    return torch.sigmoid(conv1d(h, g(lw % (li, 'kernel')), g(lw % (li, 'bias')))).numpy()

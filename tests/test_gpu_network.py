@@ -64,6 +64,32 @@ def test_resnetv2_forward_vs_oracle(xi_stats, padding, precision, tol_db):
         assert err.max() < 0.1
 
 
+@pytest.mark.parametrize('kind', ['ResNet', 'ResNetV3'])
+@pytest.mark.parametrize('padding', ['causal', 'same'])
+def test_resnet_v1_v3_forward_vs_oracle(xi_stats, kind, padding):
+    """SURVEY 8f N4: ResNet v1.0 (tcn.py:17-114, the resnet-1.0c architecture) and ResNetV3 (tcn.py:227-245), exact fp32 mode;
+    ragged batch with a tile edge (T = 79 > 64 frames per CTA) and a one-frame utterance."""
+    mu, sg = xi_stats['resnet-1.1c/mu'], xi_stats['resnet-1.1c/sigma']
+    w = weights.synthetic_resnet(0) if kind == 'ResNet' else weights.synthetic_resnetv3(0)
+    fwd = otcn.resnet_forward if kind == 'ResNet' else otcn.resnetv3_forward
+    lens = [20000, 12345, 33]
+    inp, _, _ = osig.observation_batch(synth.noisy_speech(3, 20000, seed=32), lens)
+    ref = fwd(inp, w, padding=padding, dtype=torch.float64)
+    kw = dict(RES_KW)
+    if kind == 'ResNet':
+        kw.pop('unit_type')
+    net = network_selector(kind, None, 257, padding=padding, **kw).load_weights(w)
+    assert net.precision == 'f32'
+    xbar = net(inp)
+    assert xbar.shape == ref.shape == (3, 79, 257)
+    err = _db_err(xbar, ref, mu, sg)
+    assert err.max() < 2e-3, (kind, padding, err.max())
+    with pytest.raises(ValueError):                                  # the tensor-core path is ResNetV2 / MHANetV3 only
+        network_selector(kind, None, 257, padding=padding, precision='f16x3', **kw)
+    with pytest.raises(ValueError):                                  # a ResNetV2 checkpoint does not fit
+        network_selector(kind, None, 257, padding=padding, **kw).load_weights(weights.synthetic_resnetv2(0))
+
+
 def test_resnetv2_single_utterance_and_tile_edges(xi_stats):
     mu, sg = xi_stats['resnet-1.1c/mu'], xi_stats['resnet-1.1c/sigma']
     w = weights.synthetic_resnetv2(1)

@@ -109,6 +109,56 @@ def _torch_resnet_reference(inp, w, padding):
     return torch.sigmoid(conv(h, li)).permute(0, 2, 1).numpy()
 
 
+def _torch_resnet_v1_v3(inp, w, kind, padding='causal'):
+    """Independent ResNet (tcn.py:17-114) / ResNetV3 (tcn.py:227-245) with torch.nn.functional conv1d / layer_norm."""
+    import torch.nn.functional as F
+    g = lambda li, v: torch.from_numpy(w['layer_with_weights-%d/%s' % (li, v)])
+    has = lambda li, v: 'layer_with_weights-%d/%s' % (li, v) in w
+
+    def conv(x, li, d=1):
+        k = g(li, 'kernel').shape[0]
+        pad = ((k - 1) * d, 0) if padding == 'causal' else ((k - 1) * d // 2,) * 2
+        return F.conv1d(F.pad(x, pad), g(li, 'kernel').permute(2, 1, 0).contiguous(), g(li, 'bias') if has(li, 'bias') else None, dilation=d)
+
+    def ln(x, li=None):
+        c = x.shape[1]
+        return F.layer_norm(x.permute(0, 2, 1), (c,), g(li, 'gamma') if li is not None else None,
+                            g(li, 'beta') if li is not None else None, 1e-6).permute(0, 2, 1)
+    x = torch.from_numpy(inp).permute(0, 2, 1)
+    if kind == 'ResNet':
+        h, li = F.relu(ln(conv(x, 0), 1)), 2
+    else:
+        h, li = ln(F.relu(conv(x, 0))), 1
+    for d in tcn.dilation_rates():
+        y = h
+        for dd in (1, d, 1):
+            if kind == 'ResNet':
+                y = conv(F.relu(ln(y, li)), li + 1, dd)
+                li += 2
+            else:
+                y = conv(ln(F.relu(y)), li, dd)
+                li += 1
+        h = h + y
+    return torch.sigmoid(conv(h, li)).permute(0, 2, 1).numpy()
+
+
+@pytest.mark.parametrize('kind', ['ResNet', 'ResNetV3'])
+@pytest.mark.parametrize('padding', ['causal', 'same'])
+def test_resnet_v1_v3_oracle_vs_torch_functional(kind, padding):
+    """the resnet-1.0c architecture (1 975 553 parameters, log/summary/resnet-1.0c.txt:857) and ResNetV3."""
+    if kind == 'ResNet':
+        w, fwd = weights.synthetic_resnet(0), tcn.resnet_forward
+        assert sum(int(np.prod(a.shape)) for a in w.values()) == 1975553
+    else:
+        w, fwd = weights.synthetic_resnetv3(0), tcn.resnetv3_forward
+        assert sum(int(np.prod(a.shape)) for a in w.values()) == 1949953 - 256       # ResNetV2 minus the first LayerNorm's gamma
+    inp, _, _ = sig.observation_batch(synth.noisy_speech(2, 12000, seed=3), [12000, 9000])
+    a = fwd(inp, w, padding=padding)
+    b = _torch_resnet_v1_v3(inp, w, kind, padding)
+    assert a.shape == (2, 47, 257) and np.all(a > 0) and np.all(a < 1)
+    assert np.abs(a - b).max() < 2e-5
+
+
 @pytest.mark.parametrize('padding', ['causal', 'same'])
 def test_resnetv2_oracle_vs_torch_functional(padding):
     w = weights.synthetic_resnetv2(0)
