@@ -65,7 +65,11 @@ struct StageArgs {
   int reverse;                   // walk this CTA's tiles last-to-first: consecutive stages alternate, so each starts on what the previous one left in L2
   const float2* stem_stats;     // stage 0 only: per-row partial statistics of the stem pre-activation (8 parts of 32 channels);
                                 // the row is then LayerNorm(gamma) + ReLU'd on load (tcn.py:176-179), gamma in the b3 slot
+  int wait_val;                 // with flags: a tile of this stage may start once flags[.] >= wait_val for it and its neighbours
+  int* flags;                   // flags[tile] = number of stages that have published the tile (zeroed by the host before the stem); nullptr:
+                                // every stage waits for the whole previous launch (griddepcontrol.wait) instead
   int dbg_flags;                // tuning experiments only: 1 = skip residual loads, 2 = skip residual stores, 4 = skip c1 tap loads
+  long long* dbg_cta;           // optional: per-CTA timeline of this launch in globaltimer ns (8 slots per CTA), see scripts/tcn_timeline.py
   long long* dbg;               // optional: clock64 stamps of the epilogue phases (16 per tile), see dxi_debug_tcn_clocks
 };
 
@@ -82,6 +86,20 @@ __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" :
 __device__ __forceinline__ void quarter_barrier(int q) { asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(NSPLIT * 32) : "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // LayerNorm statistics of one row split between NSPLIT threads (n values each): every thread contributes
@@ -107,12 +125,18 @@ __device__ __forceinline__ void ln_merge(float2* red, int row, int qd, float n, 
 template <bool SPLIT>
 __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const StageArgs p) {
   extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bar_w, bar_a1, bar_a2, bar_a3[8], bar_d1, bar_d2[4], bar_d3;
+  __shared__ __align__(8) uint64_t bar_w, bar_a1, bar_a2, bar_a3[8], bar_d1, bar_d2[4], bar_d3, bar_dep, bar_pub;
   __shared__ uint32_t tmem_slot;
   __shared__ float2 red[3][NSPLIT * TILE];
   unsigned char* sW = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const float* sAux = reinterpret_cast<const float*>(sW + IMG_BIAS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long* const tl = p.dbg_cta ? p.dbg_cta + (size_t)blockIdx.x * 8 : nullptr;
+  if (tl && tid == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    tl[0] = globaltimer_ns(); tl[6] = smid;
+  }
 
   if (warp == EPI_WARPS) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
@@ -124,6 +148,8 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
     mbar_init(&bar_d1, 1);
     for (int i = 0; i < 4; ++i) mbar_init(&bar_d2[i], 1);
     mbar_init(&bar_d3, 1);
+    mbar_init(&bar_dep, 1);
+    mbar_init(&bar_pub, EPI_WARPS);
     fence_mbar_init();
   }
   tc_fence_before();
@@ -136,11 +162,25 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
   // init, TMEM allocation, weight load -- overlaps this launch's tail); nothing written by the PREVIOUS launch is
   // touched before griddepcontrol.wait below.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // Tile-level dependencies (p.flags): a stage with a back half does NOT wait for the whole previous launch.  Its CTAs start on
+  // the SMs the previous stage has already left (ragged last round) and take every tile as soon as the previous stage has
+  // published it and its two neighbours in the utterance (left / self: producers of the c1 rows and of h; right: done READING the
+  // c1 plane this stage overwrites, and a producer when the padding is 'same').  So the stages form one continuous stream of
+  // tiles: no idle tail, no cold first round per launch.  Stage 0 still waits for the stem through griddepcontrol.wait.  The two
+  // launches of a pair can be co-resident only because every CTA of the older one is already running when the younger starts
+  // (launch_dependents above is executed by all of them first), so a waiting consumer never keeps its producer off the machine.
+  const bool dep_flags = p.flags != nullptr && p.has_back;      // consume flags instead of griddepcontrol.wait
+  const bool pub_flags = p.flags != nullptr && p.has_front;     // publish this stage's tiles for the next launch
 
   // this CTA's tiles: blockIdx.x, blockIdx.x + grid, ... in ascending or (p.reverse) descending order
   const int n_r = (int)blockIdx.x < p.n_tiles ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-  const int tile_step = p.reverse ? -(int)gridDim.x : (int)gridDim.x;
-  const int tile_first = p.reverse ? (int)blockIdx.x + (n_r - 1) * (int)gridDim.x : (int)blockIdx.x;
+  // Order: the full rounds (every CTA has a tile) ascending or, in a `reverse` stage, descending; consecutive stages alternate so
+  // that each starts on the ~2.5 rounds its predecessor left in L2.  The tile of the ragged last round always comes LAST: the CTAs
+  // of the next stage that start on the SMs this stage has already left then begin with tiles that are complete (and L2-hot)
+  // instead of waiting for the very tiles the ragged round is still producing.
+  const int n_full = p.n_tiles / (int)gridDim.x;
+  auto tile_at = [&](int r) { return (int)blockIdx.x + (r < n_full ? (p.reverse ? n_full - 1 - r : r) : n_full) * (int)gridDim.x; };
+  const int tile_first = tile_at(0);
 
   if (warp == EPI_WARPS) {
     // ================= weight load, L2 prefetch of the next tile, MMA issue =================
@@ -157,11 +197,35 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
     const uint32_t w_hi = smem_u32(sW), w_lo = w_hi + IMG_PART;
     constexpr uint32_t id64 = make_idesc_f16(TILE, 64);
     constexpr int NPART = SPLIT ? 3 : 1;          // (a_hi, w_hi) [+ (a_lo, w_hi) + (a_hi, w_lo)]
-    uint32_t ph = 0;
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    for (int r = 0, tile = tile_first; r < n_r; ++r, tile += tile_step) {
+    uint32_t ph = 0, ppub = 0;
+    // This warp is also the CTA's synchronisation agent, so that the epilogue never pays a gpu-scope fence or a flag round trip.
+    // publish(t): once every epilogue warp has written tile t's h and c1 rows (bar_pub), release them at gpu scope by bumping
+    // flags[t].  await(t): lanes 0..2 poll tiles t-1, t, t+1 of the utterance until the previous stage has published them, then
+    // bar_dep tells the epilogue (one phase per awaited tile; never more than one phase ahead of its consumer, see below).
+    auto publish = [&](int t) {
+      mbar_wait(&bar_pub, ppub); ppub ^= 1;
+      if (elect_one()) { __threadfence(); red_release_gpu_add(p.flags + t, 1); }
+      __syncwarp();
+    };
+    auto await = [&](int t) {
+      const int j = t % p.tiles_per_utt, dj = lane - 1;
+      if (lane < 3 && j + dj >= 0 && j + dj < p.tiles_per_utt) {
+        const int* f = p.flags + t + dj;
+        while (ld_acquire_gpu(f) < p.wait_val) {}
+      }
+      __syncwarp();
+      if (elect_one()) mbar_arrive(&bar_dep);
+      __syncwarp();
+    };
+    if (tl && lane == 0) tl[1] = globaltimer_ns();
+    if (dep_flags) { if (n_r > 0) await(tile_first); }
+    else asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (tl && lane == 0) tl[2] = globaltimer_ns();
+    for (int r = 0; r < n_r; ++r) {
+      const int tile = tile_at(r);
+      if (pub_flags && !p.has_back && r > 0) publish(tile_at(r - 1));
       {   // pull the next tile's residual rows / c1 rows into L2 ahead of their use
-        const int nt = tile + tile_step;
+        const int nt = tile_at(r + 1);
         if (r + 1 < n_r) {
           const char* hn = reinterpret_cast<const char*>(p.h + (size_t)nt * (TILE * 256));
           if (lane < 8) prefetch_l2(hn + lane * 16384, 16384);
@@ -205,6 +269,11 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
           }
           mma_commit_elect(&bar_d2[g]);
         }
+        // bar_a1 of this tile has been seen, so the epilogue has consumed this tile's bar_dep phase and is past the stores of the
+        // previous tile: publish that one, then look at the next tile's dependencies (the epilogue loads its taps after P2 of
+        // this tile).  Both round trips hide behind GEMM2 and the first chunks of P2.
+        if (pub_flags && r > 0) publish(tile_at(r - 1));
+        if (dep_flags && r + 1 < n_r) await(tile_at(r + 1));
       }
       if (p.has_front) {
         uint32_t acc = 0;
@@ -226,12 +295,13 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
       }
       ph ^= 1;
     }
+    if (pub_flags && n_r > 0) publish(tile_at(n_r - 1));
   } else {
     // ================= epilogue: warps (q, qd): TMEM lane quarter q = warp & 3, column quarter qd = warp >> 2 =================
     mbar_wait(&bar_w, 0);        // biases / column sums live in the weight image
     const int qd = warp >> 2, row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    uint32_t ph = 0;
+    uint32_t ph = 0, pdep = 0;
     // one arrival per warp: tcgen05.wait is warp-wide, so once it returns every lane's TMEM traffic is done
     auto warp_arrive = [&](uint64_t* bar) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar); };
     const bool stamp = p.dbg != nullptr && tid == 0;
@@ -250,7 +320,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
         for (int plane = 0; plane < (SPLIT ? 2 : 1); ++plane)
 #pragma unroll
           for (int u = 0; u < 2; ++u)
-            qv[j][plane][u] = (p.dbg_flags & 4) ? make_uint4(0, 0, 0, 0) : __ldg(reinterpret_cast<const uint4*>(cb + ((size_t)(plane * 8 + 2 * qd + u) * p.Ts + r_in) * 8));
+            qv[j][plane][u] = (p.dbg_flags & 4) ? make_uint4(0, 0, 0, 0) : __ldcg(reinterpret_cast<const uint4*>(cb + ((size_t)(plane * 8 + 2 * qd + u) * p.Ts + r_in) * 8));
       }
 #pragma unroll
       for (int j = 0; j < 3; ++j)
@@ -263,9 +333,14 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
       tmem_wait_st(); tc_fence_before();
     };
 
-    asm volatile("griddepcontrol.wait;" ::: "memory");      // the previous launch's h / c1 are complete and visible
-    if (p.has_back && n_r > 0) { load_a1(tile_first); warp_arrive(&bar_a1); }
-    for (int r = 0, tile = tile_first; r < n_r; ++r, tile += tile_step) {
+    // h and the c1 planes are read with ld.global.cg (L2, the point of coherence): with tile-level dependencies the producer may be a
+    // CTA of the previous launch that is still running on another SM
+    auto dep_wait = [&]() { if (dep_flags) { mbar_wait(&bar_dep, pdep); pdep ^= 1; } };
+    if (!dep_flags) asm volatile("griddepcontrol.wait;" ::: "memory");      // the previous launch's h / c1 are complete and visible
+    if (p.has_back && n_r > 0) { dep_wait(); load_a1(tile_first); warp_arrive(&bar_a1); }
+    if (tl && tid == 0) { tl[3] = globaltimer_ns(); tl[7] = n_r; }
+    for (int r = 0; r < n_r; ++r) {
+      const int tile = tile_at(r);
       const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TILE;
       const int t = t0 + row;
       const bool valid = t < p.T;
@@ -321,7 +396,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
         const int cc = qd + 4 * i;
         float4 hv[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) hv[q] = (p.dbg_flags & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4));
+        for (int q = 0; q < 8; ++q) hv[q] = (p.dbg_flags & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(reinterpret_cast<const float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4)));
         float v[32];
         if (p.has_back) {
           mbar_wait(&bar_d2[cc >> 1], ph); tc_fence_after();
@@ -391,9 +466,9 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
       }
       DXI_STAMP(6);
       // ---- the next tile's c1 taps travel to TMEM while this tile's GEMM3 drains
-      const int next = tile + tile_step;
+      const int next = tile_at(r + 1);
       const bool has_next = p.has_back && r + 1 < n_r;
-      if (has_next) load_a1(next);
+      if (has_next) { dep_wait(); load_a1(next); }
       DXI_STAMP(7);
       if (p.has_front) {
         // ---- P3: c1' = LN(ReLU(inv3 (acc3 - mu3 colsum(W1')) + b1')) -> fp16 hi | lo planes in HBM (zeros beyond T)
@@ -429,6 +504,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
           *reinterpret_cast<uint4*>(ob + ((size_t)(2 * qd + u) * p.Ts + r_out) * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           if (SPLIT) *reinterpret_cast<uint4*>(ob + ((size_t)(8 + 2 * qd + u) * p.Ts + r_out) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
+        if (pub_flags) { __syncwarp(); if (lane == 0) mbar_arrive(&bar_pub); }      // this warp's share of the tile's h and c1 rows is written
       } else if (has_next) {
         warp_arrive(&bar_a1);
       }
@@ -436,9 +512,11 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
       ph ^= 1;
     }
 #undef DXI_STAMP
+    if (tl && tid == 0) tl[4] = globaltimer_ns();
   }
   tc_fence_before();
   __syncthreads();
+  if (tl && tid == 0) tl[5] = globaltimer_ns();
   if (warp == EPI_WARPS) tmem_dealloc(0, 512);
 }
 
@@ -825,7 +903,8 @@ int64_t resnet_umma_workspace_bytes(const dxi_net& net, int B, int T) {
   const size_t h_bytes = (size_t)B * tiles * TILE * 256 * 4;
   const size_t c1_bytes = align_up((size_t)B * 2 * 8 * Ts * 16, 256);
   const size_t stats_bytes = (size_t)B * tiles * TILE * 8 * sizeof(float2);
-  return (int64_t)(256 + h_bytes + 2 * c1_bytes + stats_bytes);
+  const size_t flag_bytes = align_up((size_t)B * tiles * sizeof(int), 256);
+  return (int64_t)(256 + h_bytes + 2 * c1_bytes + flag_bytes + stats_bytes);
 }
 
 // One group of whole utterances through stem -> 41 stages -> output layer; every group uses the same workspace region.
@@ -838,9 +917,12 @@ static int resnet_umma_group(const dxi_net& net, const float* mag, int B, int T,
   unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   float* h = reinterpret_cast<float*>(base);
   __half* c1[2] = {reinterpret_cast<__half*>(base + h_bytes), reinterpret_cast<__half*>(base + h_bytes + c1_bytes)};
-  float2* stem_stats = reinterpret_cast<float2*>(base + h_bytes + 2 * c1_bytes);
-  // zero padding rows of the c1 planes (and everything else in them)
-  DXI_CUDA(cudaMemsetAsync(c1[0], 0, 2 * c1_bytes, st));
+  const size_t flag_bytes = align_up((size_t)B * tiles * sizeof(int), 256);
+  int* flags = reinterpret_cast<int*>(base + h_bytes + 2 * c1_bytes);
+  float2* stem_stats = reinterpret_cast<float2*>(base + h_bytes + 2 * c1_bytes + flag_bytes);
+  // zero padding rows of the c1 planes (and everything else in them) and the per-tile stage counters
+  DXI_CUDA(cudaMemsetAsync(c1[0], 0, 2 * c1_bytes + flag_bytes, st));
+  static const bool no_flags = env_flag("DXI_TCN_NO_FLAGS");      // A/B switch: every stage waits for the whole previous launch
 
   const int n_tiles = B * tiles;
   int n_sm = 148;
@@ -878,7 +960,10 @@ static int resnet_umma_group(const dxi_net& net, const float* mag, int B, int T,
     a.has_back = s >= 1; a.has_front = s < c.n_blocks;
     a.reverse = (s & 1) == 0 && !env_flag("DXI_TCN_NO_REVERSE");      // the stem leaves the last tiles in L2, the output layer starts on the first
     a.dbg = (dbg && s == g_dbg_stage) ? g_dbg_clocks : nullptr;
+    a.dbg_cta = (dbg && g_dbg_stage == 255 && g_dbg_clocks) ? g_dbg_clocks + (size_t)s * grid * 8 : nullptr;      // stage 255: CTA timelines of all stages
     a.dbg_flags = g_dbg_flags;
+    a.flags = (no_flags || (dbg && g_dbg_stop_after >= 0)) ? nullptr : flags;
+    a.wait_val = s;               // stage s-1 has published a tile when its counter reaches s
     const int d = s >= 1 ? 1 << ((s - 1) % nd) : 1;
     if (c.padding == DXI_PAD_CAUSAL) { a.shift0 = 2 * d; a.shift1 = d; a.shift2 = 0; }       // tap j reads t-(2-j)d
     else                             { a.shift0 = d;     a.shift1 = 0; a.shift2 = -d; }      // tap j reads t+(j-1)d
