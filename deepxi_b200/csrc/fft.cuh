@@ -111,4 +111,77 @@ __device__ __forceinline__ float atan2_poly(float y, float x) {
   return copysignf(p, y);
 }
 
+// ---- bin-pair formulation of the analysis epilogue --------------------------------------------------------------------------
+// Packed fp32x2 arithmetic (FFMA2 / FMUL2 on sm_100: one issue slot for two lanes); the host twin of the tests runs two scalar
+// operations instead.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+#ifdef __CUDA_ARCH__
+  return __ffma2_rn(a, b, c);
+#else
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+  return __fmul2_rn(a, b);
+#else
+  return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+__device__ __forceinline__ float sqrt_approx(float x) {      // MUFU.SQRT: <= 2 ulp, 0 -> 0
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return sqrtf(x);
+#endif
+}
+__device__ __forceinline__ float rcp_approx(float x) {       // MUFU.RCP
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.0f / x;
+#endif
+}
+
+// Split step for the bin pair (k, 256 - k), 0 <= k <= 128, from Z' = FFT256 of the HALF-scaled samples (the analysis window
+// carries the factor 1/2, an exact scaling): a = X[k], b = X[256 - k].  With E = zk + conj(zn), O = -j (zk - conj(zn)) and
+// T = W512^k O:  X[k] = E + T,  X[256 - k] = conj(E - T).  Bit-identical to rfft_split of the unscaled transform.
+__device__ __forceinline__ void rfft_split_pair(float2 zk, float2 zn, float2 w, float2& a, float2& b) {
+  const float ex = zk.x + zn.x, ey = zk.y - zn.y, ox = zk.y + zn.y, oy = zn.x - zk.x;
+  const float tx = fmaf(w.x, ox, -w.y * oy), ty = fmaf(w.x, oy, w.y * ox);
+  a = make_float2(ex + tx, ey + ty);
+  b = make_float2(ex - tx, ty - ey);
+}
+
+// |a|, |b| and atan2 of both (the polynomial of atan2_poly, evaluated for the two bins at once).
+__device__ __forceinline__ void polar_pair(float2 a, float2 b, float2& mag, float2& pha) {
+  const float2 p2 = fma2(make_float2(a.x, b.x), make_float2(a.x, b.x), mul2(make_float2(a.y, b.y), make_float2(a.y, b.y)));
+  mag = make_float2(sqrt_approx(p2.x), sqrt_approx(p2.y));
+  const float aax = fabsf(a.x), aay = fabsf(a.y), abx = fabsf(b.x), aby = fabsf(b.y);
+  const float2 mn = make_float2(fminf(aax, aay), fminf(abx, aby));
+  const float2 r = make_float2(rcp_approx(fmaxf(fmaxf(aax, aay), 1e-30f)), rcp_approx(fmaxf(fmaxf(abx, aby), 1e-30f)));
+  const float2 t = mul2(mn, r);
+  const float2 s = mul2(t, t);
+  auto c = [](float v) { return make_float2(v, v); };
+  float2 p = c(0.0028340641874819994f);
+  p = fma2(p, s, c(-0.016005029901862144f));
+  p = fma2(p, s, c(0.042587608098983765f));
+  p = fma2(p, s, c(-0.07495445758104324f));
+  p = fma2(p, s, c(0.10636754333972931f));
+  p = fma2(p, s, c(-0.14202570915222168f));
+  p = fma2(p, s, c(0.19992484152317047f));
+  p = fma2(p, s, c(-0.3333306610584259f));
+  p = fma2(p, s, c(1.0f));
+  p = mul2(p, t);
+  if (aay > aax) p.x = 1.57079637f - p.x;
+  if (aby > abx) p.y = 1.57079637f - p.y;
+  if (a.x < 0.0f) p.x = 3.14159274f - p.x;
+  if (b.x < 0.0f) p.y = 3.14159274f - p.y;
+  pha = make_float2(copysignf(p.x, a.y), copysignf(p.y, b.y));
+}
+
 }  // namespace dxi

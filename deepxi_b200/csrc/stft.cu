@@ -12,6 +12,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <mutex>
+#include <type_traits>
 #include "fft.cuh"
 #include "gain_math.cuh"
 
@@ -55,31 +56,69 @@ static int ensure_tables(cudaStream_t stream) {
 
 constexpr int FR = 16;   // frames transformed per CTA pass (16 threads per frame, 256 threads)
 
-struct StftSmem {
+template <bool I16>
+struct StftSmem {                     // 47.5 KB (int16 input) / 56 KB (f32 input): four CTAs per SM
   float2 buf[FR * FFT_FRAME_SLOTS];   // per-frame FFT exchange, then the 256 Z values
-  float xs[(FR + 1) * N_S];           // staged samples of FR overlapping frames
-  float win[N_D];
+  typename std::conditional<I16, int16_t, float>::type raw[(FR + 1) * N_S];   // samples of FR overlapping frames, as they lie in HBM
+  float win[N_D];                     // analysis window x 1/2 (split step) x 1/32768 (sig.py:189-199 normalisation) for int16 input
   float2 tw256[256];
-  float2 tw512[NBINS + 1];
 };
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src, int src_bytes) {      // bytes beyond src_bytes: zeros
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src),
+               "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all(bool wait) {
+  if (!wait) asm volatile("cp.async.commit_group;" ::: "memory");
+  else asm volatile("cp.async.wait_all;" ::: "memory");
+}
 
 // ----------------------------------------------------------------------------------------------
 // Analysis
 // ----------------------------------------------------------------------------------------------
 template <bool I16>
-__global__ void __launch_bounds__(256) stft_kernel(const void* __restrict__ wav_, const int32_t* __restrict__ lens,
+__global__ void __launch_bounds__(256, 4) stft_kernel(const void* __restrict__ wav_, const int32_t* __restrict__ lens,
                                                    int B, int64_t stride, int Tmax, int groups_per_utt,
                                                    int vec_ok, float* __restrict__ mag, float* __restrict__ phase) {
+  using elem_t = typename std::conditional<I16, int16_t, float>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  StftSmem& sm = *reinterpret_cast<StftSmem*>(smem_raw);
+  StftSmem<I16>& sm = *reinterpret_cast<StftSmem<I16>*>(smem_raw);
   const int tid = threadIdx.x;
-  for (int i = tid; i < N_D; i += 256) sm.win[i] = d_win[i];
+  // the factor 1/2 of the split step and the int16 normalisation ride in the window: both are exact scalings by powers of two
+  for (int i = tid; i < N_D; i += 256) sm.win[i] = (I16 ? 0.5f / 32768.0f : 0.5f) * d_win[i];
   sm.tw256[tid] = d_tw256[tid];
-  for (int i = tid; i < NBINS; i += 256) sm.tw512[i] = d_tw512[i];
-  __syncthreads();
+  const float2 w_pair = d_tw512[tid & 127];      // split-step twiddle of this thread's bin pair
 
   const int f = tid >> 4, lane16 = tid & 15;
   const int total = B * groups_per_utt;
+  const elem_t* wav = reinterpret_cast<const elem_t*>(wav_);
+  // The (nf + 1) * 256 samples of a group travel HBM -> shared memory as they are (cp.async, 16 bytes per request, zero fill beyond
+  // the utterance); the request for the NEXT group is issued as soon as the FFT threads have taken the current samples into
+  // registers, so that its latency runs under the split / magnitude / phase phase.  Each sample is read from HBM once.
+  auto stage = [&](int g) {
+    if (g >= total) return;
+    const int b = g / groups_per_utt, t0 = (g - b * groups_per_utt) * FR;
+    const int nf = min(FR, Tmax - t0);
+    int64_t len = lens ? (int64_t)lens[b] : stride;
+    if (len > stride) len = stride;
+    const int64_t s0 = (int64_t)t0 * N_S;
+    if (s0 >= len) return;
+    const elem_t* w = wav + (int64_t)b * stride + s0;
+    const int n_stage = (nf + 1) * N_S;
+    constexpr int PER = 16 / (int)sizeof(elem_t);      // samples per 16-byte request
+    if (vec_ok) {
+      for (int i = tid * PER; i < n_stage; i += 256 * PER) {
+        const int64_t left = len - (s0 + i);
+        const int nb = left >= PER ? 16 : (left > 0 ? (int)left * (int)sizeof(elem_t) : 0);
+        cp_async_16(&sm.raw[i], nb > 0 ? (const void*)(w + i) : (const void*)wav, nb);
+      }
+    } else {
+      for (int i = tid; i < n_stage; i += 256) sm.raw[i] = (s0 + i < len) ? w[i] : (elem_t)0;
+    }
+  };
+  stage(blockIdx.x);
+  cp_async_commit_wait_all(false);
   for (int g = blockIdx.x; g < total; g += gridDim.x) {
     const int b = g / groups_per_utt, t0 = (g - b * groups_per_utt) * FR;
     const int nf = min(FR, Tmax - t0);
@@ -87,38 +126,14 @@ __global__ void __launch_bounds__(256) stft_kernel(const void* __restrict__ wav_
     if (len > stride) len = stride;
     const int64_t s0 = (int64_t)t0 * N_S;
     const int64_t out0 = ((int64_t)b * Tmax + t0) * NBINS;
+    cp_async_commit_wait_all(true);
+    __syncthreads();      // this group's samples have landed (and, first pass, the tables); the previous group's Z values are consumed
     if (s0 >= len) {   // frames at or beyond ceil(len/256): zeros (model.py:2246-2253 leaves them zero)
+      stage(g + gridDim.x);
+      cp_async_commit_wait_all(false);
       for (int i = tid; i < nf * NBINS; i += 256) { __stcs(mag + out0 + i, 0.0f); __stcs(phase + out0 + i, 0.0f); }
       continue;
     }
-    // ---- stage (nf+1)*256 samples, normalised (sig.py:189-199: int16 -> f32 / 32768)
-    const int n_stage = (nf + 1) * N_S;
-    if (I16) {
-      const int16_t* w = reinterpret_cast<const int16_t*>(wav_) + (int64_t)b * stride + s0;
-      for (int i = tid * 8; i < n_stage; i += 256 * 8) {
-        if (vec_ok && s0 + i + 8 <= len) {
-          int4 q = __ldcs(reinterpret_cast<const int4*>(w + i));
-          const int16_t* h = reinterpret_cast<const int16_t*>(&q);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) sm.xs[i + j] = (float)h[j] * (1.0f / 32768.0f);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) sm.xs[i + j] = (s0 + i + j < len) ? (float)w[i + j] * (1.0f / 32768.0f) : 0.0f;
-        }
-      }
-    } else {
-      const float* w = reinterpret_cast<const float*>(wav_) + (int64_t)b * stride + s0;
-      for (int i = tid * 4; i < n_stage; i += 256 * 4) {
-        if (vec_ok && s0 + i + 4 <= len) {
-          float4 q = __ldcs(reinterpret_cast<const float4*>(w + i));
-          sm.xs[i] = q.x; sm.xs[i + 1] = q.y; sm.xs[i + 2] = q.z; sm.xs[i + 3] = q.w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) sm.xs[i + j] = (s0 + i + j < len) ? w[i + j] : 0.0f;
-        }
-      }
-    }
-    __syncthreads();
     // ---- window + 256-point complex FFT of z[m] = x[2m] + j x[2m+1]
     float2* fb = sm.buf + f * FFT_FRAME_SLOTS;
     float2 v[16];
@@ -126,7 +141,13 @@ __global__ void __launch_bounds__(256) stft_kernel(const void* __restrict__ wav_
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) {
         const int n = 32 * n1 + 2 * lane16;
-        float2 x = *reinterpret_cast<const float2*>(&sm.xs[f * N_S + n]);
+        float2 x;
+        if (I16) {
+          const uint32_t pr = *reinterpret_cast<const uint32_t*>(&sm.raw[f * N_S + n]);
+          x = make_float2((float)(int16_t)(pr & 0xffffu), (float)(int16_t)(pr >> 16));
+        } else {
+          x = *reinterpret_cast<const float2*>(&sm.raw[f * N_S + n]);
+        }
         float2 w = *reinterpret_cast<const float2*>(&sm.win[n]);
         v[n1] = make_float2(x.x * w.x, x.y * w.y);
       }
@@ -140,24 +161,35 @@ __global__ void __launch_bounds__(256) stft_kernel(const void* __restrict__ wav_
       for (int k2 = 0; k2 < 16; ++k2) fb[lane16 + 16 * k2] = v[fft16_pos(k2)];
     }
     __syncthreads();
-    // ---- split step, magnitude and phase.  Thread = bin (0..255) for every frame of the pass, so the twiddle and both
-    // exchange indices are loop invariants and a frame's 256 outputs are one coalesced row; the Nyquist bin of frame f is done
-    // by thread f afterwards.
+    stage(g + gridDim.x);      // every thread has taken its samples: the buffer is free for the next group
+    cp_async_commit_wait_all(false);
+    // ---- split step, magnitude and phase.  Thread = bin PAIR (j, 256 - j), j = 0..127, for every second frame of the pass (the
+    // two halves of the CTA take the even / the odd frames): the pair shares both exchange loads, E, O and the twiddle product,
+    // the two magnitudes and phase polynomials run as packed fp32x2 operations, the twiddle and both exchange indices are loop
+    // invariants and a frame's outputs are two coalesced runs (ascending from bin 0, descending from bin 256).  Bin 128 of frame f
+    // (its own partner) is done by thread f afterwards.
     {
-      auto emit = [&](const float2* z, int k, int ia, int ib, float2 w, int64_t o) {
-        float2 X = rfft_split(z[ia], z[ib], w);
-        if (k == 0 || k == 256) X.y = 0.0f;
-        const float p2 = fmaf(X.x, X.x, X.y * X.y);
-        __stcs(mag + o, p2 > 0.0f ? p2 * rsqrtf(p2) : 0.0f);       // |X|, 2 ulp
+      const int j = tid & 127, ib = (256 - j) & 255;
+      const float2 w = w_pair;
+#pragma unroll 2
+      for (int fi = tid >> 7; fi < nf; fi += 2) {
+        const float2* z = sm.buf + fi * FFT_FRAME_SLOTS;
+        float2 a, c, m, ph;
+        rfft_split_pair(z[j], z[ib], w, a, c);
+        if (j == 0) { a.y = 0.0f; c.y = 0.0f; }       // DC and Nyquist are real
+        polar_pair(a, c, m, ph);
+        const int64_t o = out0 + (int64_t)fi * NBINS;
+        __stcs(mag + o + j, m.x);   __stcs(mag + o + 256 - j, m.y);
+        __stcs(phase + o + j, ph.x); __stcs(phase + o + 256 - j, ph.y);
+      }
+      if (tid < nf) {      // bin 128: X = conj(Z[128]) = 2 conj(Z'[128])
+        const float2 z = sm.buf[tid * FFT_FRAME_SLOTS + 128];
+        const float2 X = make_float2(2.0f * z.x, -2.0f * z.y);
+        const int64_t o = out0 + (int64_t)tid * NBINS + 128;
+        __stcs(mag + o, sqrt_approx(fmaf(X.x, X.x, X.y * X.y)));
         __stcs(phase + o, atan2_poly(X.y, X.x));
-      };
-      const int k = tid, ib = (256 - tid) & 255;
-      const float2 w = sm.tw512[k];
-#pragma unroll 4
-      for (int fi = 0; fi < nf; ++fi) emit(sm.buf + fi * FFT_FRAME_SLOTS, k, k, ib, w, out0 + (int64_t)fi * NBINS + k);
-      if (tid < nf) emit(sm.buf + tid * FFT_FRAME_SLOTS, 256, 0, 0, sm.tw512[256], out0 + (int64_t)tid * NBINS + 256);
+      }
     }
-    __syncthreads();
   }
 }
 
@@ -348,8 +380,8 @@ extern "C" DXI_API int dxi_stft(const void* wav, int wav_is_i16, const int32_t* 
   const int groups = (Tmax + FR - 1) / FR;
   const int64_t total = (int64_t)B * groups;
   DXI_REQUIRE(total < (1LL << 31), "dxi_stft: batch too large");
-  const int grid = (int)(total < 148 * 3 ? total : 148 * 3);
-  const size_t smem = sizeof(StftSmem);
+  const int grid = (int)(total < 148 * 4 ? total : 148 * 4);
+  const size_t smem = wav_is_i16 ? sizeof(StftSmem<true>) : sizeof(StftSmem<false>);
   const int elem = wav_is_i16 ? 2 : 4;
   ProfScope prof("stft", st, 1);
   const int vec_ok = ((reinterpret_cast<uintptr_t>(wav) % 16) == 0 && ((wav_stride * elem) % 16) == 0) ? 1 : 0;

@@ -59,18 +59,25 @@ void host_stft_frame(const float* x, float* mag, float* phase) {
   for (int lane = 0; lane < 16; ++lane) {
     for (int n1 = 0; n1 < 16; ++n1) {
       int n = 32 * n1 + 2 * lane;
-      v[lane][n1] = make_float2(x[n] * g_win[n], x[n + 1] * g_win[n + 1]);
+      v[lane][n1] = make_float2(x[n] * (0.5f * g_win[n]), x[n + 1] * (0.5f * g_win[n + 1]));      // half-scaled, as in the kernel
     }
     fft256_pass1<-1>(v[lane], buf, g_tw256, lane);
   }
   for (int lane = 0; lane < 16; ++lane) fft256_pass2<-1>(v[lane], buf, lane);
   for (int lane = 0; lane < 16; ++lane)
     for (int k2 = 0; k2 < 16; ++k2) buf[lane + 16 * k2] = v[lane][fft16_pos(k2)];
-  for (int k = 0; k < 257; ++k) {
-    float2 X = rfft_split(buf[k & 255], buf[(256 - k) & 255], g_tw512[k]);
-    if (k == 0 || k == 256) X.y = 0.0f;
-    mag[k] = sqrtf(fmaf(X.x, X.x, X.y * X.y));
-    phase[k] = atan2_poly(X.y, X.x);
+  for (int j = 0; j < 128; ++j) {      // bin pairs (j, 256 - j)
+    float2 a, c, m, ph;
+    rfft_split_pair(buf[j], buf[(256 - j) & 255], g_tw512[j], a, c);
+    if (j == 0) { a.y = 0.0f; c.y = 0.0f; }
+    polar_pair(a, c, m, ph);
+    mag[j] = m.x; mag[256 - j] = m.y;
+    phase[j] = ph.x; phase[256 - j] = ph.y;
+  }
+  {
+    const float2 X = make_float2(2.0f * buf[128].x, -2.0f * buf[128].y);
+    mag[128] = sqrt_approx(fmaf(X.x, X.x, X.y * X.y));
+    phase[128] = atan2_poly(X.y, X.x);
   }
 }
 
