@@ -99,22 +99,20 @@ __global__ void __launch_bounds__(256, 4) stft_kernel(const void* __restrict__ w
   auto stage = [&](int g) {
     if (g >= total) return;
     const int b = g / groups_per_utt, t0 = (g - b * groups_per_utt) * FR;
-    const int nf = min(FR, Tmax - t0);
-    int64_t len = lens ? (int64_t)lens[b] : stride;
-    if (len > stride) len = stride;
+    const int64_t len = min(lens ? (int64_t)lens[b] : stride, stride);
     const int64_t s0 = (int64_t)t0 * N_S;
     if (s0 >= len) return;
     const elem_t* w = wav + (int64_t)b * stride + s0;
-    const int n_stage = (nf + 1) * N_S;
-    constexpr int PER = 16 / (int)sizeof(elem_t);      // samples per 16-byte request
+    const int n_stage = (min(FR, Tmax - t0) + 1) * N_S;
+    const int left = (int)min(len - s0, (int64_t)n_stage);      // samples of the group that exist
+    constexpr int PER = 16 / (int)sizeof(elem_t);                // samples per 16-byte request
     if (vec_ok) {
       for (int i = tid * PER; i < n_stage; i += 256 * PER) {
-        const int64_t left = len - (s0 + i);
-        const int nb = left >= PER ? 16 : (left > 0 ? (int)left * (int)sizeof(elem_t) : 0);
+        const int nb = min(max(left - i, 0), PER) * (int)sizeof(elem_t);
         cp_async_16(&sm.raw[i], nb > 0 ? (const void*)(w + i) : (const void*)wav, nb);
       }
     } else {
-      for (int i = tid; i < n_stage; i += 256) sm.raw[i] = (s0 + i < len) ? w[i] : (elem_t)0;
+      for (int i = tid; i < n_stage; i += 256) sm.raw[i] = i < left ? w[i] : (elem_t)0;
     }
   };
   stage(blockIdx.x);
@@ -122,22 +120,16 @@ __global__ void __launch_bounds__(256, 4) stft_kernel(const void* __restrict__ w
   for (int g = blockIdx.x; g < total; g += gridDim.x) {
     const int b = g / groups_per_utt, t0 = (g - b * groups_per_utt) * FR;
     const int nf = min(FR, Tmax - t0);
-    int64_t len = lens ? (int64_t)lens[b] : stride;
-    if (len > stride) len = stride;
-    const int64_t s0 = (int64_t)t0 * N_S;
+    const int64_t len = min(lens ? (int64_t)lens[b] : stride, stride);
+    const bool live = (int64_t)t0 * N_S < len;      // else: frames at or beyond ceil(len/256), zeros (model.py:2246-2253 leaves them zero)
     const int64_t out0 = ((int64_t)b * Tmax + t0) * NBINS;
     cp_async_commit_wait_all(true);
     __syncthreads();      // this group's samples have landed (and, first pass, the tables); the previous group's Z values are consumed
-    if (s0 >= len) {   // frames at or beyond ceil(len/256): zeros (model.py:2246-2253 leaves them zero)
-      stage(g + gridDim.x);
-      cp_async_commit_wait_all(false);
-      for (int i = tid; i < nf * NBINS; i += 256) { __stcs(mag + out0 + i, 0.0f); __stcs(phase + out0 + i, 0.0f); }
-      continue;
-    }
     // ---- window + 256-point complex FFT of z[m] = x[2m] + j x[2m+1]
     float2* fb = sm.buf + f * FFT_FRAME_SLOTS;
     float2 v[16];
-    if (f < nf) {
+    const bool mine = live && f < nf;
+    if (mine) {
 #pragma unroll
       for (int n1 = 0; n1 < 16; ++n1) {
         const int n = 32 * n1 + 2 * lane16;
@@ -154,15 +146,19 @@ __global__ void __launch_bounds__(256, 4) stft_kernel(const void* __restrict__ w
       fft256_pass1<-1>(v, fb, sm.tw256, lane16);
     }
     __syncwarp();
-    if (f < nf) fft256_pass2<-1>(v, fb, lane16);
+    if (mine) fft256_pass2<-1>(v, fb, lane16);
     __syncwarp();
-    if (f < nf) {
+    if (mine) {
 #pragma unroll
       for (int k2 = 0; k2 < 16; ++k2) fb[lane16 + 16 * k2] = v[fft16_pos(k2)];
     }
     __syncthreads();
     stage(g + gridDim.x);      // every thread has taken its samples: the buffer is free for the next group
     cp_async_commit_wait_all(false);
+    if (!live) {
+      for (int i = tid; i < nf * NBINS; i += 256) { __stcs(mag + out0 + i, 0.0f); __stcs(phase + out0 + i, 0.0f); }
+      continue;
+    }
     // ---- split step, magnitude and phase.  Thread = bin PAIR (j, 256 - j), j = 0..127, for every second frame of the pass (the
     // two halves of the CTA take the even / the odd frames): the pair shares both exchange loads, E, O and the twiddle product,
     // the two magnitudes and phase polynomials run as packed fp32x2 operations, the twiddle and both exchange indices are loop
