@@ -257,11 +257,12 @@ __global__ void __launch_bounds__(256, 3) istft_kernel(const float* __restrict__
         };
         const int k = tid;
         if (MODE != 0) { mu_k = __ldg(mu + k); sg_k = __ldg(sigma + k); s2_k = __fmul_rn(sg_k, 1.41421354f); }
-        for (int fi = 0; fi < nf; fi += 2) {
-          float mv[2], pv[2], gv[2];
-          bool ok[2];
+        constexpr int NU = 4;      // frames per iteration: 3 NU loads in flight per thread
+        for (int fi = 0; fi < nf; fi += NU) {
+          float mv[NU], pv[NU], gv[NU];
+          bool ok[NU];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
+          for (int u = 0; u < NU; ++u) {
             const int t = f0 + fi + u;
             ok[u] = fi + u < nf && t >= 0 && t < T;
             mv[u] = pv[u] = gv[u] = 0.0f;
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(256, 3) istft_kernel(const float* __restrict__
             }
           }
 #pragma unroll
-          for (int u = 0; u < 2; ++u)
+          for (int u = 0; u < NU; ++u)
             if (fi + u < nf) spectrum(fi + u, k, mv[u], pv[u], gv[u], ok[u], mu_k, sg_k, s2_k);
         }
         if (tid < nf) {      // bin 256 of frame tid
