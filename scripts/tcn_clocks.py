@@ -24,14 +24,18 @@ names = ['wait GEMM1', 'P1 (A2)', 'merge2', 'wait GEMM2 g0', 'P2 (h, A3)', 'merg
 print('flags', flags, 'tiles', n_tiles, 'stage', stage, ' total per tile: median %.0f cycles' % np.median(c[:, 9] - c[:, 0]))
 for i, n in enumerate(names):
     print('%-16s median %7.0f  mean %7.0f  p90 %7.0f' % (n, np.median(d[:, i]), d[:, i].mean(), np.percentile(d[:, i], 90)))
-# tile ownership: chained kernel -> CTA c owns tiles [c m, (c+1) m); per-stage launches -> c, c + 148, ...
-chain = False      # (the chained-kernel experiment is in git history only; note: odd stages now walk tiles in reverse)
-g = 148
-if chain:
-    m = -(-n_tiles // g)
-    owned = [list(range(cta * m, min((cta + 1) * m, n_tiles))) for cta in range(-(-n_tiles // m))]
-else:
-    owned = [list(range(cta, n_tiles, g)) for cta in range(min(g, n_tiles))]
+# tile ownership in time order (tcn_umma.cu tile_at): CTA c walks the full rounds ascending, or descending in a `reverse`
+# stage (even stages), and takes the tile of the ragged last round last
+g = min(148, n_tiles)
+n_full = n_tiles // g
+reverse = (stage & 1) == 0 and not os.environ.get('DXI_TCN_NO_REVERSE')
+def tiles_of(cta):
+    rounds = list(range(n_full))[::-1] if reverse else list(range(n_full))
+    ts = [cta + r * g for r in rounds]
+    if cta + n_full * g < n_tiles:
+        ts.append(cta + n_full * g)
+    return ts
+owned = [tiles_of(cta) for cta in range(g)]
 gaps = [c[ts[i + 1], 0] - c[ts[i], 9] for ts in owned for i in range(len(ts) - 1)]
 print('inter-tile gap median %.0f' % np.median(gaps))
 
@@ -47,4 +51,4 @@ spans = np.array([c[ts[-1], 9] - c[ts[0], 0] for ts in owned])
 print('per-CTA busy span: median %.0f  max %.0f  min %.0f cycles (%.1f us at 1.965 GHz max)' % (np.median(spans), spans.max(), spans.min(), spans.max() / 1965.0))
 for r in range(max(len(ts) for ts in owned)):
     ts = np.array([o[r] for o in owned if len(o) > r])
-    print('  round %d: tiles %4d  median tile %6.0f  mean %6.0f' % (r, len(ts), np.median(c[ts, 9] - c[ts, 0]), (c[ts, 9] - c[ts, 0]).mean()))
+    print('  step %d of the CTAs: tiles %4d  median tile %6.0f  mean %6.0f' % (r, len(ts), np.median(c[ts, 9] - c[ts, 0]), (c[ts, 9] - c[ts, 0]).mean()))
