@@ -319,8 +319,8 @@ def run_ours(args, rank, world, local_rank):
                      'traffic_source': 'profiles/r01_prof_tcn_stage_final.csv (bytes per launch; algorithmic %.0f)' % st_bytes_per_launch,
                      'hbm_view': {'bound': 'hbm', 'achieved': st_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                                   'frac': (st_gbs / hbm_peak) if st_gbs else None, 'bytes_per_frame_and_stage': TCN_STAGE_BYTES_PER_FRAME,
-                                  'note': 'as launched (one stage per launch) the kernel streams the fp32 residual through HBM: '
-                                          'this is the bound that binds today, the tensor figure is the target'},
+                                  'note': 'one stage per launch, chained tile by tile through flags: the kernel streams the fp32 residual '
+                                          'through HBM at loaded-latency speed; this is the bound that binds today, the tensor figure is the target'},
                      'peak_source': peak_src + ' bf16 sustained (MEASURED_PEAKS.json)',
                      'algorithmic_flop_per_launch': flops_per_launch, 'ms_per_launch': st_ms_per_launch,
                      'share_of_step': st_ms / ms if ms else None,
