@@ -79,6 +79,13 @@ constexpr int NSPLIT = 4;                         // threads per frame
 constexpr int EPI_WARPS = 4 * NSPLIT;
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int STAGE_THREADS = EPI_THREADS + 32;   // + 1 warp: weight load, L2 prefetch, MMA issue
+// tcn_stage_kernel: the MMA warp's warpgroup is launched whole (3 idle warps) so that setmaxnreg can move registers from it to the
+// epilogue.  A CTA is allocated in units of four warps anyway (17 warps cost 20; measured: 21 warps x 96 registers do not launch),
+// the kernel is compiled for 96 registers per thread = a pool of 640 x 96 = 61 440, redistributed as 512 x 104 + 128 x 64.  The
+// epilogue's eight extra registers remove most of its spills (-4.5 % stage time); below 64 the MMA warp spills its descriptors and
+// the kernel gets slower (40 / 104: +2.5 %).
+constexpr int TCN_THREADS = EPI_THREADS + 128;
+constexpr int TCN_REGS_MMA = 64, TCN_REGS_EPI = 104;
 
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 // The NSPLIT threads that share a frame sit in the NSPLIT warps with the same lane quarter q = warp & 3: statistics
@@ -123,7 +130,7 @@ __device__ __forceinline__ void ln_merge(float2* red, int row, int qd, float n, 
 }
 
 template <bool SPLIT>
-__global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const StageArgs p) {
+__global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageArgs p) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_w, bar_a1, bar_a2, bar_a3[8], bar_d1, bar_d2[4], bar_d3, bar_dep, bar_pub;
   __shared__ uint32_t tmem_slot;
@@ -182,6 +189,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
   auto tile_at = [&](int r) { return (int)blockIdx.x + (r < n_full ? (p.reverse ? n_full - 1 - r : r) : n_full) * (int)gridDim.x; };
   const int tile_first = tile_at(0);
 
+  if (warp >= EPI_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(TCN_REGS_MMA));
   if (warp == EPI_WARPS) {
     // ================= weight load, L2 prefetch of the next tile, MMA issue =================
     // The whole warp runs this code convergently; single-thread operations elect a lane inside the asm.
@@ -194,7 +202,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
     }
     __syncwarp();
     mbar_wait(&bar_w, 0);
-    const uint32_t w_hi = smem_u32(sW), w_lo = w_hi + IMG_PART;
+    uint32_t w_hi = smem_u32(sW), w_lo = w_hi + IMG_PART;
     constexpr uint32_t id64 = make_idesc_f16(TILE, 64);
     constexpr int NPART = SPLIT ? 3 : 1;          // (a_hi, w_hi) [+ (a_lo, w_hi) + (a_hi, w_lo)]
     uint32_t ph = 0, ppub = 0;
@@ -223,6 +231,9 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
     if (tl && lane == 0) tl[2] = globaltimer_ns();
     for (int r = 0; r < n_r; ++r) {
       const int tile = tile_at(r);
+      // the shared-memory descriptors are recomputed per tile (a handful of integer adds) instead of being kept as ~100 loop
+      // invariants: this warp lives on 32 registers so that the epilogue can have 112 (setmaxnreg)
+      asm volatile("" : "+r"(w_hi), "+r"(w_lo));
       if (pub_flags && !p.has_back && r > 0) publish(tile_at(r - 1));
       {   // pull the next tile's residual rows / c1 rows into L2 ahead of their use
         const int nt = tile_at(r + 1);
@@ -296,7 +307,8 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) tcn_stage_kernel(const Stage
       ph ^= 1;
     }
     if (pub_flags && n_r > 0) publish(tile_at(n_r - 1));
-  } else {
+  } else if (warp < EPI_WARPS) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(TCN_REGS_EPI));
     // ================= epilogue: warps (q, qd): TMEM lane quarter q = warp & 3, column quarter qd = warp >> 2 =================
     mbar_wait(&bar_w, 0);        // biases / column sums live in the weight image
     const int qd = warp >> 2, row = (warp & 3) * 32 + lane;
@@ -967,8 +979,8 @@ static int resnet_umma_group(const dxi_net& net, const float* mag, int B, int T,
     const int d = s >= 1 ? 1 << ((s - 1) % nd) : 1;
     if (c.padding == DXI_PAD_CAUSAL) { a.shift0 = 2 * d; a.shift1 = d; a.shift2 = 0; }       // tap j reads t-(2-j)d
     else                             { a.shift0 = d;     a.shift1 = 0; a.shift2 = -d; }      // tap j reads t+(j-1)d
-    if (split) DXI_CUDA(launch_pdl(tcn_stage_kernel<true>, grid, STAGE_THREADS, smem, st, a));
-    else       DXI_CUDA(launch_pdl(tcn_stage_kernel<false>, grid, STAGE_THREADS, smem, st, a));
+    if (split) DXI_CUDA(launch_pdl(tcn_stage_kernel<true>, grid, TCN_THREADS, smem, st, a));
+    else       DXI_CUDA(launch_pdl(tcn_stage_kernel<false>, grid, TCN_THREADS, smem, st, a));
     DXI_LAUNCHED("tcn_stage_kernel");
   }
   }
