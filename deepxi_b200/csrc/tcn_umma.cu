@@ -65,6 +65,7 @@ struct StageArgs {
   int reverse;                   // walk this CTA's tiles last-to-first: consecutive stages alternate, so each starts on what the previous one left in L2
   const float2* stem_stats;     // stage 0 only: per-row partial statistics of the stem pre-activation (8 parts of 32 channels);
                                 // the row is then LayerNorm(gamma) + ReLU'd on load (tcn.py:176-179), gamma in the b3 slot
+  int zero;                     // always 0 (see the MMA warp's descriptor arithmetic)
   int wait_val;                 // with flags: a tile of this stage may start once flags[.] >= wait_val for it and its neighbours
   int* flags;                   // flags[tile] = number of stages that have published the tile (zeroed by the host before the stem); nullptr:
                                 // every stage waits for the whole previous launch (griddepcontrol.wait) instead
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
     }
     __syncwarp();
     mbar_wait(&bar_w, 0);
-    uint32_t w_hi = smem_u32(sW), w_lo = w_hi + IMG_PART;
+    const uint32_t w_base = smem_u32(sW);
     constexpr uint32_t id64 = make_idesc_f16(TILE, 64);
     constexpr int NPART = SPLIT ? 3 : 1;          // (a_hi, w_hi) [+ (a_lo, w_hi) + (a_hi, w_lo)]
     uint32_t ph = 0, ppub = 0;
@@ -231,9 +232,10 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
     if (tl && lane == 0) tl[2] = globaltimer_ns();
     for (int r = 0; r < n_r; ++r) {
       const int tile = tile_at(r);
-      // the shared-memory descriptors are recomputed per tile (a handful of integer adds) instead of being kept as ~100 loop
-      // invariants: this warp lives on 32 registers so that the epilogue can have 112 (setmaxnreg)
-      asm volatile("" : "+r"(w_hi), "+r"(w_lo));
+      // The shared-memory descriptors are recomputed per tile (a handful of uniform-datapath adds) instead of being kept as ~100
+      // spilled loop invariants: p.zero (= 0, but only the host knows) makes the base depend on the iteration without taking it
+      // out of the uniform registers the MMA instruction reads its operands from.
+      const uint32_t w_hi = w_base + (uint32_t)(p.zero * r), w_lo = w_hi + IMG_PART;
       if (pub_flags && !p.has_back && r > 0) publish(tile_at(r - 1));
       {   // pull the next tile's residual rows / c1 rows into L2 ahead of their use
         const int nt = tile_at(r + 1);
@@ -258,8 +260,8 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
           for (int part = 0; part < NPART; ++part) {
             const uint32_t a0 = part == 1 ? COL_A1_LO : COL_A1_HI, w0 = (part == 2 ? w_lo : w_hi) + IMG_W2;
 #pragma unroll
-            for (int ks = 0; ks < 12; ++ks) {
-              mma_ts_elect(COL_D1, a0 + 8 * ks, make_smem_desc_sw128(w0 + (ks >> 2) * 64 * 128 + (ks & 3) * 32), id64, acc);
+            for (int kc = 0; kc < 3; ++kc) {      // one tap = one 64-wide K chunk = four K16 steps
+              mma_ts_elect_k<4>(COL_D1, a0 + 32 * kc, make_smem_desc_sw128(w0 + kc * 64 * 128), id64, acc);
               acc = 1;
             }
           }
@@ -272,11 +274,8 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
 #pragma unroll
           for (int part = 0; part < NPART; ++part) {
             const uint32_t a0 = part == 1 ? COL_A2_LO : COL_A2_HI, w0 = (part == 2 ? w_lo : w_hi) + IMG_W3 + g * 64 * 128;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              mma_ts_elect(COL_D2 + 64 * g, a0 + 8 * ks, make_smem_desc_sw128(w0 + ks * 32), id64, acc);
-              acc = 1;
-            }
+            mma_ts_elect_k<4>(COL_D2 + 64 * g, a0, make_smem_desc_sw128(w0), id64, acc);
+            acc = 1;
           }
           mma_commit_elect(&bar_d2[g]);
         }
@@ -294,12 +293,9 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
 #pragma unroll
           for (int part = 0; part < NPART; ++part) {
             const uint32_t a0 = COL_D2 + 32 * cc + (part == 1 ? 16 : 0), w0 = (part == 2 ? w_lo : w_hi) + IMG_W1;
-#pragma unroll
-            for (int k2 = 0; k2 < 2; ++k2) {
-              const int ks = 2 * cc + k2;
-              mma_ts_elect(COL_D3, a0 + 8 * k2, make_smem_desc_sw128(w0 + (ks >> 2) * 64 * 128 + (ks & 3) * 32), id64, acc);
-              acc = 1;
-            }
+            // chunk cc holds K16 steps 2cc, 2cc + 1: half of the 64-wide K chunk cc >> 1
+            mma_ts_elect_k<2>(COL_D3, a0, make_smem_desc_sw128(w0 + (cc >> 1) * 64 * 128 + (cc & 1) * 64), id64, acc);
+            acc = 1;
           }
         }
         mma_commit_elect(&bar_d3);

@@ -179,6 +179,37 @@ __device__ __forceinline__ void mma_ts_elect(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// NK consecutive K = 16 steps of one 64-wide K chunk under ONE election: step i reads A at tmem_a + 8 i columns (16 fp16) and B at
+// bdesc + 2 i (32 bytes further along the 128-byte swizzled row); the first step accumulates iff `accumulate`, the others always.
+// One ELECT / predicate set-up per group instead of per MMA, and the derived operands are formed next to the instruction that
+// uses them: the issuing warp spends ~19 SASS instructions per MMA with mma_ts_elect, and its issue time is on the critical
+// path of every tile.
+template <int NK>
+__device__ __forceinline__ void mma_ts_elect_k(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  static_assert(NK == 2 || NK == 4, "NK");
+  if (NK == 4) {
+    asm volatile(
+        "{\n\t.reg .pred p, e, t;\n\t.reg .b64 b1, b2, b3;\n\t.reg .b32 a1, a2, a3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 t, 0, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+        "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %3, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], b2, %3, t;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], b3, %3, t;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, e, t;\n\t.reg .b64 b1;\n\t.reg .b32 a1;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 t, 0, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "add.u32 a1, %1, 8;\n\tadd.u64 b1, %2, 2;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], b1, %3, t;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
 __device__ __forceinline__ void mma_ss_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
