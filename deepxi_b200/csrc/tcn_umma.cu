@@ -139,8 +139,9 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
   unsigned char* sW = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const float* sAux = reinterpret_cast<const float*>(sW + IMG_BIAS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  long long* const tl = p.dbg_cta ? p.dbg_cta + (size_t)blockIdx.x * 8 : nullptr;
-  if (tl && tid == 0) {
+  // (debug) per-CTA timeline slots: the pointer is re-formed from the kernel parameters at every use instead of living in registers
+#define tl (p.dbg_cta + (size_t)blockIdx.x * 8)
+  if (p.dbg_cta && tid == 0) {
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     tl[0] = globaltimer_ns(); tl[6] = smid;
@@ -226,10 +227,10 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
       if (elect_one()) mbar_arrive(&bar_dep);
       __syncwarp();
     };
-    if (tl && lane == 0) tl[1] = globaltimer_ns();
+    if (p.dbg_cta && lane == 0) tl[1] = globaltimer_ns();
     if (dep_flags) { if (n_r > 0) await(tile_first); }
     else asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (tl && lane == 0) tl[2] = globaltimer_ns();
+    if (p.dbg_cta && lane == 0) tl[2] = globaltimer_ns();
     for (int r = 0; r < n_r; ++r) {
       const int tile = tile_at(r);
       // The shared-memory descriptors are recomputed per tile (a handful of uniform-datapath adds) instead of being kept as ~100
@@ -346,7 +347,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
     auto dep_wait = [&]() { if (dep_flags) { mbar_wait(&bar_dep, pdep); pdep ^= 1; } };
     if (!dep_flags) asm volatile("griddepcontrol.wait;" ::: "memory");      // the previous launch's h / c1 are complete and visible
     if (p.has_back && n_r > 0) { dep_wait(); load_a1(tile_first); warp_arrive(&bar_a1); }
-    if (tl && tid == 0) { tl[3] = globaltimer_ns(); tl[7] = n_r; }
+    if (p.dbg_cta && tid == 0) { tl[3] = globaltimer_ns(); tl[7] = n_r; }
     for (int r = 0; r < n_r; ++r) {
       const int tile = tile_at(r);
       const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TILE;
@@ -520,11 +521,12 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
       ph ^= 1;
     }
 #undef DXI_STAMP
-    if (tl && tid == 0) tl[4] = globaltimer_ns();
+    if (p.dbg_cta && tid == 0) tl[4] = globaltimer_ns();
   }
   tc_fence_before();
   __syncthreads();
-  if (tl && tid == 0) tl[5] = globaltimer_ns();
+  if (p.dbg_cta && tid == 0) tl[5] = globaltimer_ns();
+#undef tl
   if (warp == EPI_WARPS) tmem_dealloc(0, 512);
 }
 
