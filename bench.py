@@ -37,7 +37,7 @@ FLOP_PER_FRAME_STAGES = 40 * 2 * (256 * 64 + 3 * 64 * 64 + 64 * 256)     # the 4
 FLOP_PER_FRAME_TOTAL = 3867648                                           # whole ResNetV2
 STFT_BYTES_PER_FRAME = 512 + 2 * 257 * 4                                 # int16 in, mag + phase out
 TCN_STAGE_BYTES_PER_FRAME = 2 * 1024 + 256 + 256                         # per stage: h read + write (fp32), c1 write, c1 read (once)
-NCU_TCN_STAGE_TRAFFIC = 398.75e6      # dram__bytes_read.sum + dram__bytes_write.sum of one tcn_stage_kernel<true> launch (238.21 + 160.54 MB), profiles/r01_prof_tcn_stage_final.csv
+NCU_TCN_STAGE_TRAFFIC = 385.43e6      # dram__bytes_read.sum + dram__bytes_write.sum of one tcn_stage_kernel<true> launch (231.75 + 153.68 MB), profiles/r01_prof_tcn_stage_final.csv
 RES_KW = dict(d_model=256, n_blocks=40, d_f=64, k=3, max_d_rate=16, unit_type='ReLU->LN->W+b', outp_act='Sigmoid')
 
 
