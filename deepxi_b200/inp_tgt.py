@@ -182,8 +182,14 @@ class MagXi(MagTgt):
         mu, sigma = self.xi_map._stats_dev(mag.device)
         n_out = (T + 1) * self.N_s
         nf = None
-        if n_frames is not None:
-            nf = torch.as_tensor(np.asarray(n_frames, np.int32)).to(mag.device, non_blocking=True)
+        if n_frames is not None:      # the frame counts of a repeated batch are uploaded once per stream (as the lengths are)
+            key = (str(mag.device), torch.cuda.current_stream(mag.device).cuda_stream, tuple(int(n) for n in n_frames))
+            cache = self.__dict__.setdefault('_nf_cache', {})
+            if key not in cache:
+                if len(cache) > 16:
+                    cache.clear()
+                cache[key] = torch.as_tensor(np.asarray(n_frames, np.int32)).to(mag.device, non_blocking=True)
+            nf = cache[key]
         y = torch.empty((B, n_out), dtype=torch.int16 if int16 else torch.float32, device=mag.device)
         if B and T:
             _lib.check(_lib.load().dxi_enhance(_lib.ptr(mag), _lib.ptr(pha), _lib.ptr(xb), _lib.ptr(mu), _lib.ptr(sigma),
