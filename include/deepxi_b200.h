@@ -194,6 +194,9 @@ DXI_API int64_t dxi_net_workspace_bytes(const dxi_net_t* h, int B, int Tmax);
 /*
  * Forward: mag [B, Tmax, n_feat] -> xbar [B, Tmax, n_outp] in (0,1).  All Tmax frames of every
  * utterance are computed as the reference does (zero-padded frames are zero-input frames).
+ * The workspace belongs to the call in stream order (activations and, for the tcgen05 ResNetV2 path, the per-tile
+ * stage counters that chain its 41 stage launches; zeroed by the call): forward passes that may overlap on
+ * different streams need different workspaces.
  */
 DXI_API int dxi_net_forward(dxi_net_t* h, const float* mag, int B, int Tmax, float* xbar, void* workspace,
                     size_t workspace_bytes, void* stream);

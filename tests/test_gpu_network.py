@@ -1,4 +1,6 @@
 """GPU parity tests of the a priori SNR estimators (through the C ABI) against the oracle."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -329,3 +331,26 @@ def test_infer_loads_a_written_checkpoint(tmp_path):
     dx2.set_weights(w)
     y2, nfr = dx2.infer_batch(x, lens, 'y', 'mmse-lsa', int16=True)
     assert np.array_equal(ya, y2.cpu().numpy()[0, :(nfr[0] + 1) * 256])
+
+
+def test_tile_level_stage_dependencies_are_bit_exact(tmp_path):
+    """The stage launches of the tcgen05 ResNetV2 path are chained by per-tile flags; with DXI_TCN_NO_FLAGS=1 every
+    stage waits for its whole predecessor instead.  The switch is read once per process, so each mode runs in its own process
+    (scripts/flags_check.py: ragged lengths, 'causal' over several rounds of tiles and 'same' with neighbours on both sides); the
+    outputs must be identical bit for bit and repeatable."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for B, L, pad in ((40, 70000, 'causal'), (3, 20000, 'same')):
+        outs = []
+        for mode in ('flags', 'noflags'):
+            env = dict(os.environ)
+            env.pop('DXI_TCN_NO_FLAGS', None)
+            if mode == 'noflags':
+                env['DXI_TCN_NO_FLAGS'] = '1'
+            f = str(tmp_path / ('%s_%s.npy' % (pad, mode)))
+            r = subprocess.run([sys.executable, os.path.join(root, 'scripts', 'flags_check.py'), f, str(B), str(L), pad], env=env,
+                               capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stdout + r.stderr
+            outs.append(np.load(f))
+        assert outs[0].shape == outs[1].shape and np.array_equal(outs[0], outs[1])
+        assert np.isfinite(outs[0]).all() and outs[0].min() >= 0.0 and outs[0].max() <= 1.0
