@@ -29,6 +29,13 @@
 // LayerNorm statistics merged with Chan's formula through shared memory).  Warp 16: weight load (bulk async
 // copy), L2 prefetch of the next tile, warp-convergent MMA issue.  GEMM2 is committed in four column groups and
 // GEMM3 is issued in eight K-chunks as the epilogue produces them.
+//
+// Launch structure: stem x 2, 41 stage launches, output layer, all with programmatic dependent launch.  The stage launches depend on
+// each other TILE BY TILE through counters in the workspace (flags[tile] = number of stages that have published the tile, see
+// the kernel), not launch by launch: a stage's CTAs start on the SMs its predecessor has already left and the 41 launches
+// form one uninterrupted stream of tiles.  Registers: the MMA warp's warpgroup is launched whole and setmaxnreg moves
+// registers from it (64) to the epilogue (104); the MMA warp re-forms its shared-memory descriptors per tile instead of
+// keeping them as (spilled) loop invariants.  DESIGN.md section 4 has the measurements behind both.
 #include <cstdlib>
 #include <vector>
 #include "net.cuh"
