@@ -362,6 +362,14 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
       const bool valid = t < p.T;
       float* hrow = p.h + (size_t)tile * (TILE * 256) + row * 4;          // + c4 * 512
       DXI_STAMP(0);
+      // The first residual chunk of the tile is requested here, ahead of P1: since the MMA warp issues GEMM2 promptly its wait no
+      // longer covers the round trip of these loads, P1 and the statistics merge do.
+      float4 hv[8];
+      auto load_h = [&](int cc_) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) hv[q] = (p.dbg_flags & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(reinterpret_cast<const float4*>(hrow + (size_t)(cc_ * 8 + q) * (TILE * 4)));
+      };
+      load_h(qd);
       float mu2 = 0.0f, inv2 = 0.0f;
       if (p.has_back) {
         // ---- P1: r2 = ReLU(acc1 + b2) -> A2 at once (un-normalised); statistics merged while GEMM2 runs
@@ -410,9 +418,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int cc = qd + 4 * i;
-        float4 hv[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) hv[q] = (p.dbg_flags & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(reinterpret_cast<const float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4)));
+        if (i == 1) load_h(cc);
         float v[32];
         if (p.has_back) {
           mbar_wait(&bar_d2[cc >> 1], ph); tc_fence_after();
