@@ -171,20 +171,28 @@ class HostPipeline:
             ev_in.record(self.h2d)
         with torch.cuda.stream(self.compute):
             self.compute.wait_event(ev_in)
-            xd.record_stream(self.compute)
             out, n_frames = self.dx.infer_batch(xd, x_len, self.out_type, self.gain, int16=out_host.dtype == torch.int16)
             ev_out = torch.cuda.Event()
             ev_out.record(self.compute)
         with torch.cuda.stream(self.d2h):
             self.d2h.wait_event(ev_out)
-            out.record_stream(self.d2h)
             out_host.copy_(out, non_blocking=True)
             done = torch.cuda.Event()
             done.record(self.d2h)
         self._done[k] = done
-        self._keep[k] = (xd, out)           # keep the device buffers alive until the slot is reused
+        # The device buffers of a slot stay alive until the slot is reused, and the slot is reused only after its `done` event has
+        # been synchronised (above): every stream is finished with them by then.  That is why no record_stream() is used here: it
+        # would make the caching allocator defer the reuse of these blocks to an event it polls lazily, and fall back to a
+        # (device-synchronising) cudaMalloc whenever the poll comes too early -- an occasional stall of the whole pipeline.
+        self._keep[k] = (xd, out)
         return n_frames
 
     def drain(self):
         for st in (self.h2d, self.compute, self.d2h):
             st.synchronize()
+
+    def __del__(self):
+        try:
+            self.drain()      # the kept buffers must not return to the allocator while a copy still reads them
+        except Exception:
+            pass
