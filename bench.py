@@ -59,24 +59,33 @@ class ClockSampler:
         self.idx, self.lines, self.proc = gpu_index, [], None
 
     def start(self):
+        """Started BEFORE the warm-up steps: nvidia-smi needs ~0.1 s to produce its first line, more than a whole timed region of
+        ten 4.5 ms steps.  Every line is stamped on arrival; stop() keeps the ones that arrived inside the timed windows."""
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, text=True)
+                                          '--format=csv,noheader,nounits', '-lms', '20'], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, windows=()):
+        """windows: (t_begin, t_end) pairs of time.time() bracketing the timed regions (device-timed steps, e2e steps)."""
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        inside = [ln for t, ln in self.lines if any(a <= t <= b + 0.01 for a, b in windows)]
+        window = 'timed regions (device-timed steps + e2e steps)'
+        if not inside:      # a timed region shorter than one sampling period: the samples of the same load just around it
+            lo = min((a for a, _ in windows), default=0.0) - 0.5
+            inside = [ln for t, ln in self.lines if t >= lo]
+            window = 'no sample fell inside the timed regions: samples from 0.5 s before them (warm-up steps, same load) to their end'
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(',')]
             if len(f) < 9:
                 continue
@@ -89,7 +98,7 @@ class ClockSampler:
                     reasons.add(name)
         busy = [s for s in sm if s > 0]
         return {'sm_mhz': float(np.median(busy)) if busy else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm), 'window': window}
 
 
 def run_reference(args, rank, world):
@@ -221,25 +230,27 @@ def run_ours(args, rank, world, local_rank):
         xbar = dx.network(inp)
         return it.enhanced_speech(inp, pha, xbar, 'mmse-lsa', n_frames=None)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         y = step(i)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
     _lib.profile_enable(True)
     for k in ('stft', 'tcn_stage', 'tcn_stem', 'tcn_head', 'enhance'):
         _lib.profile_read(k)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(); torch.cuda.synchronize()
-    if rank == 0:
-        sampler.start()
     _lib.launch_count_reset()
+    win_dev0 = time.time()
     e0.record()
     for i in range(args.steps):
         y = step(i)
     e1.record()
-    torch.cuda.synchronize(); barrier()
+    torch.cuda.synchronize()
+    win_dev1 = time.time()
+    barrier()
     launches = _lib.launch_count()
-    clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     prof = {k: _lib.profile_read(k) for k in ('stft', 'tcn_stage', 'tcn_stem', 'tcn_head', 'enhance')}
     _lib.profile_enable(False)
@@ -255,6 +266,7 @@ def run_ours(args, rank, world, local_rank):
         pipe.submit(x_host, lens, y_hosts[i % 3])
     pipe.drain()
     torch.cuda.synchronize(); barrier()
+    win_e2e0 = time.time()
     t0 = time.perf_counter()
     marks = []
     for i in range(args.steps):
@@ -263,6 +275,7 @@ def run_ours(args, rank, world, local_rank):
     pipe.drain()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop([(win_dev0, win_dev1), (win_e2e0, time.time())]) if rank == 0 else None
     if os.environ.get('DXI_BENCH_DEBUG'):
         sys.stderr.write('rank %d e2e submit marks %s total %.4f\n' % (rank, ['%.4f' % m for m in marks], e2e_s))
     barrier()
