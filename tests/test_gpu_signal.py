@@ -187,3 +187,28 @@ def test_subband_ibm_matches_oracle(xi_stats):
     assert np.array_equal(ibm[sure], r_ibm[sure])
     sub24, _ = it.subband(xi[0], 24, want_mask=False)
     assert np.allclose(sub24, osig.subband_ibm(xi[0], 24)[0], rtol=2e-6)
+
+
+def test_degenerate_inputs(xi_stats):
+    """Empty and zero-length inputs (SURVEY 8c edge cases): an empty waveform has no frames, a zero-length utterance inside a
+    batch is all padding, element-wise functions keep empty shapes."""
+    a = AnalysisSynthesis(512, 256, 512, 16000)
+    mag, pha = a.polar_analysis(np.zeros(0, np.float32))
+    m_ref, p_ref = osig.polar_analysis(np.zeros(0, np.float32))
+    assert mag.shape == pha.shape == m_ref.shape == (0, 257)
+    it = _magxi(xi_stats)
+    x = synth.noisy_speech(2, 600, seed=3)
+    lens = [600, 0]
+    inp, phs, nfr = it.observation_batch(x, lens)
+    r_inp, r_pha, r_nfr = osig.observation_batch(x, lens)
+    assert nfr == r_nfr == [3, 0] and tuple(inp.shape) == r_inp.shape == (2, 3, 257)
+    inp_h, phs_h = inp.cpu().numpy(), phs.cpu().numpy()
+    assert not inp_h[1].any() and not phs_h[1].any()
+    assert (np.abs(inp_h[0] - r_inp[0]).max(axis=-1) <= 1e-5 * r_inp[0].max(axis=-1)).all()
+    xbar = torch.full((2, 3, 257), 0.5, device='cuda')
+    y = it.enhanced_speech(inp, phs, xbar, 'mmse-lsa', n_frames=nfr).cpu().numpy()
+    assert y.shape == (2, 4 * 256) and np.isfinite(y).all() and not y[1].any() and np.abs(y[0]).max() > 0
+    for g in ('mmse-lsa', 'ibm'):
+        G = dgain.gfunc(np.zeros((0, 257), np.float32), np.zeros((0, 257), np.float32), g)
+        assert G.shape == (0, 257)
+    assert it.xi_hat(np.zeros((0, 257), np.float32)).shape == (0, 257)
