@@ -69,10 +69,8 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src
                "r"(src_bytes)
                : "memory");
 }
-__device__ __forceinline__ void cp_async_commit_wait_all(bool wait) {
-  if (!wait) asm volatile("cp.async.commit_group;" ::: "memory");
-  else asm volatile("cp.async.wait_all;" ::: "memory");
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------------------------
 // Analysis
@@ -116,14 +114,14 @@ __global__ void __launch_bounds__(256, 4) stft_kernel(const void* __restrict__ w
     }
   };
   stage(blockIdx.x);
-  cp_async_commit_wait_all(false);
+  cp_async_commit();
   for (int g = blockIdx.x; g < total; g += gridDim.x) {
     const int b = g / groups_per_utt, t0 = (g - b * groups_per_utt) * FR;
     const int nf = min(FR, Tmax - t0);
     const int64_t len = min(lens ? (int64_t)lens[b] : stride, stride);
     const bool live = (int64_t)t0 * N_S < len;      // else: frames at or beyond ceil(len/256), zeros (model.py:2246-2253 leaves them zero)
     const int64_t out0 = ((int64_t)b * Tmax + t0) * NBINS;
-    cp_async_commit_wait_all(true);
+    cp_async_wait_all();
     __syncthreads();      // this group's samples have landed (and, first pass, the tables); the previous group's Z values are consumed
     // ---- window + 256-point complex FFT of z[m] = x[2m] + j x[2m+1]
     float2* fb = sm.buf + f * FFT_FRAME_SLOTS;
@@ -154,7 +152,7 @@ __global__ void __launch_bounds__(256, 4) stft_kernel(const void* __restrict__ w
     }
     __syncthreads();
     stage(g + gridDim.x);      // every thread has taken its samples: the buffer is free for the next group
-    cp_async_commit_wait_all(false);
+    cp_async_commit();
     if (!live) {
       for (int i = tid; i < nf * NBINS; i += 256) { __stcs(mag + out0 + i, 0.0f); __stcs(phase + out0 + i, 0.0f); }
       continue;
