@@ -340,7 +340,7 @@ def test_tile_level_stage_dependencies_are_bit_exact(tmp_path):
     outputs must be identical bit for bit and repeatable."""
     import subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for B, L, pad in ((40, 70000, 'causal'), (3, 20000, 'same')):
+    for B, L, pad in ((48, 100000, 'causal'), (3, 20000, 'same')):      # 192 tiles: one full round + a ragged one; 3 tiles: all stages co-resident
         outs = []
         for mode in ('flags', 'noflags'):
             env = dict(os.environ)
