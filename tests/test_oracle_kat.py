@@ -264,3 +264,21 @@ def test_precision_budget_of_a_narrower_residual_stream(xi_stats):
 
     assert max_db_err(forward(15)) < 0.02
     assert max_db_err(forward(10)) > 0.1
+
+
+def test_oracle_network_forwards_match_their_committed_digest(golden_dir):
+    """Regression pin of the ORACLE itself (tests/golden/oracle_digest.json, written by tests/golden/make_oracle_digest.py): shape,
+    sum, sum of squares and eight probes of x_bar for every network on seeded inputs and seeded weights.  No reference artefact
+    pins the networks; this keeps the checker from drifting unnoticed."""
+    import importlib.util, json
+    spec = importlib.util.spec_from_file_location('make_oracle_digest', os.path.join(golden_dir, 'make_oracle_digest.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = json.load(open(os.path.join(golden_dir, 'oracle_digest.json')))
+    got = mod.compute()
+    assert set(got) == set(want)
+    for k in want:
+        assert got[k]['shape'] == want[k]['shape'], k
+        assert abs(got[k]['sum'] - want[k]['sum']) <= 1e-4 * abs(want[k]['sum']), k            # fp32 torch-CPU kernels: thread-count dependent sums
+        assert abs(got[k]['sumsq'] - want[k]['sumsq']) <= 1e-4 * want[k]['sumsq'], k
+        assert np.allclose(got[k]['probes'], want[k]['probes'], rtol=0, atol=2e-5), k
