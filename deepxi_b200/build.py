@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'libdeepxi_b200.so')
-SOURCES = ['common.cu', 'gain.cu', 'stft.cu', 'net.cu', 'tcn_f32.cu', 'tcn_umma.cu', 'umma_selftest.cu', 'mhanet.cu', 'mha_umma.cu', 'attn_umma.cu', 'train_tgt.cu']
+SOURCES = ['common.cu', 'gain.cu', 'stft.cu', 'net.cu', 'tcn_f32.cu', 'tcn_umma.cu', 'tcn_chain.cu', 'umma_selftest.cu', 'mhanet.cu', 'mha_umma.cu', 'attn_umma.cu', 'train_tgt.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
          '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']

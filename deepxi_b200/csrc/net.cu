@@ -185,6 +185,7 @@ extern "C" DXI_API int dxi_net_destroy(dxi_net_t* h) {
   if (!h) return DXI_OK;
   if (h->d_arena) cudaFree(h->d_arena);
   if (h->d_umma) cudaFree(h->d_umma);
+  if (h->d_chain) cudaFree(h->d_chain);
   delete h;
   return DXI_OK;
 }

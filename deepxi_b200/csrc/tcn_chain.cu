@@ -1,0 +1,617 @@
+// ResNetV2 (causal) residual blocks, DEPTH FIRST: one CTA takes a tile of 128 frames through all n_blocks blocks while the
+// tile's fp32 residual stream never leaves the SM.  Restates deepxi/network/tcn.py:182-223 (block / unit), :156-157 (dilation cycle).
+//
+// Why.  The stage-per-launch formulation (tcn_umma.cu: tcn_stage_kernel, kept for padding='same') moves the fp32 residual
+// stream through HBM once per block: 2560 B per frame and block, 15.8 GB per forward of 256 x 10 s against 0.33 GB of
+// algorithmic traffic; it runs at 0.7 of the HBM copy rate and 0.1 of the tensor peak.  Here the residual tile lives in
+// tensor memory for the whole network and the weights stream instead (176 KB per block from L2, shared by all SMs):
+//
+//   TMEM columns [0,256)    H    fp32 residual sum of the tile WITHOUT the conv_3 biases: GEMM2 accumulates straight into it
+//                                (D += A B), the cumulative bias B3cum_b = sum_{i<b} b3_i is added when the row is read
+//                [256,320)  D13  accumulators of GEMM3 (c1 pre-activation), then of GEMM1 (c2 pre-activation)
+//                [320,384)  A2   LN(ReLU(c2)) as fp16 hi | lo: A operand of GEMM2
+//                [384,512)  A3   ring of four 32-channel chunks of ReLU(h) as fp16 hi | lo: A operand of GEMM3
+//   shared memory           W1 | W2 | W3 of the current block (fp16 hi + lo, 128-byte swizzle, written by tensor-map TMA and
+//                                re-filled with the next block's matrix as soon as the GEMM that reads it has committed),
+//                           c1 tile: 32 halo rows + 128 rows, fp16 hi | lo planes, [unit of 8 channels][row][16 B] = the
+//                                canonical no-swizzle K-major layout, so the three taps of the dilated causal conv are three
+//                                A-operand descriptors whose start address is shifted by 0 / d / 2d rows (SS-mode MMA).
+//
+// Per block b (d = dilation):   P2  r3 = ReLU(H + B3cum_b) * s  -> A3 chunks (un-normalised: deferred LayerNorm, as in tcn_umma.cu)
+//                               GEMM3  D13 = r3 W1_b            (K = 256, issued chunk by chunk as P2 produces them)
+//                               P3  c1 = LN(ReLU(inv (D13 - mu colsum(W1)) + b1)) -> shared memory (+ last 32 rows -> halo in HBM)
+//                               GEMM1  D13 = [c1(t-2d) | c1(t-d) | c1(t)] W2_b       (K = 192, both operands in shared memory)
+//                               P1  A2 = LN(ReLU(D13 + b2))     (normalised BEFORE the GEMM: its output lands in H)
+//                               GEMM2  H += A2 W3_b             (K = 64, four 64-column groups committed separately)
+// s is an exact power of two per row (the exponent of 1/std of the row one block earlier): it keeps the un-normalised fp16 hi/lo
+// operands inside fp16's normal range whatever the magnitude of the residual stream; LayerNorm is scale invariant, the epsilon
+// is scaled by s^2, so the result is the same as without it.
+//
+// Time order.  Work items are tiles ordered (tile index in the utterance, utterance); CTAs claim them from an atomic counter.
+// A tile needs, for block b, the last 2d <= 32 rows of c1_b of its predecessor in the utterance: the predecessor writes them to
+// a halo buffer in HBM / L2 and bumps flags[tile] (release); the consumer's agent warp polls (acquire) before the epilogue
+// loads them.  An item only ever waits for an item that was claimed earlier by a CTA that is already running, so the scheme
+// cannot deadlock whatever the residency of the grid.
+//
+// Warps 0-15 epilogue (thread = (row, column quarter), as in tcn_umma.cu), 16 MMA issue, 17 weight loader (TMA) + work claims,
+// 18 flag agent, 19 idle (completes the warpgroup setmaxnreg takes registers from).  Every wait is bounded: a protocol error
+// traps instead of hanging the GPU.
+#include <cuda.h>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "launch.cuh"
+#include "net.cuh"
+#include "umma.cuh"
+
+namespace dxi {
+using namespace umma;
+
+namespace chain {
+constexpr int TILE = 128, HALO = 32, C1_ROWS = HALO + TILE;
+constexpr int NSPLIT = 4, EPI_WARPS = 16, EPI_THREADS = 512, THREADS = 640;
+constexpr int REGS_EPI = 104, REGS_AUX = 64;
+// shared memory map (bytes from the 1024-aligned base)
+constexpr int SM_W1 = 0, W1_PART = 32768;                  // [part][4 K-chunks][64 rows x 128 B]
+constexpr int SM_W2 = 65536, W2_PART = 24576;              // [part][3 taps][64 rows x 128 B]
+constexpr int SM_W3 = 114688, W3_PART = 32768;             // [part][256 rows x 128 B]
+constexpr int SM_C1 = 180224, C1_UNIT = C1_ROWS * 16, C1_PLANE = 8 * C1_UNIT;   // [plane][unit][row][16 B]
+constexpr int SM_AUXA = SM_C1 + 2 * C1_PLANE;              // [2 slots][b1 64 | colsum(W1) 64 | b2 64] fp32
+constexpr int SM_B3 = SM_AUXA + 2 * 192 * 4;               // B3cum[256] fp32 (single buffer)
+constexpr int SM_RED = SM_B3 + 1024;                       // LayerNorm partials [2][4][128] float2
+constexpr int SM_BAR = SM_RED + 2 * NSPLIT * TILE * 8;
+enum { B_W1 = 0, B_W2, B_W3, B_A3, B_FREE = B_A3 + 8, B_D3 = B_FREE + 4, B_D1, B_D2, B_C1 = B_D2 + 4, B_A2, B_DEP, B_PUB, N_BAR };
+constexpr int SM_MISC = SM_BAR + N_BAR * 8;                // tmem slot, item[2]
+constexpr int SMEM_BYTES = SM_MISC + 16;
+static_assert(SMEM_BYTES <= 232448, "shared memory map exceeds the 227 KB a CTA can have");
+constexpr int AUX_FLOATS = 448, AUX_B3 = 192;              // global aux record per block: b1 | colsum(W1) | b2 | B3cum
+// TMEM column map
+constexpr uint32_t COL_H = 0, COL_D13 = 256, COL_A2_HI = 320, COL_A2_LO = 352, COL_A3 = 384;
+}  // namespace chain
+
+struct ChainArgs {
+  const float* aux;            // [n_blocks + 1][AUX_FLOATS]
+  const float* gamma;          // LayerNorm scale of the first layer [256] (tcn.py:176-179)
+  float* h;                    // tiled residual buffer [tile][c/4][row][4]: in = stem pre-activation, out = residual sum after the last block
+  const float2* stem_stats;    // [n_tiles * 128][8] partial (mean, M2) of the stem pre-activation
+  __half* halo;                // [B][2][n_blocks][2 planes][8 units][32 rows][8]: c1 rows 96..127 of the utterance's previous tile
+  int* flags;                  // [B * tiles_per_utt]: number of blocks whose halo rows the tile has published
+  int* counter;                // work-item counter (zeroed by the host with the flags)
+  int T, tiles_per_utt, B, n_items, n_blocks, nd;
+  int zero;                    // always 0 (keeps the MMA warp's descriptors out of its loop invariants, see tcn_umma.cu)
+};
+
+__device__ __forceinline__ float relu(float x) { return fmaxf(x, 0.0f); }
+__device__ __forceinline__ void quarter_barrier(int q) { asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(chain::NSPLIT * 32) : "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// LayerNorm statistics of a row held by NSPLIT threads (n values each): (mean_i, M2_i) per thread, merged with Chan's formula.
+__device__ __forceinline__ void ln_merge(float2* red, int row, int qd, float n, float mean_i, float m2_i, float eps, float& mean, float& inv) {
+  using namespace chain;
+  red[qd * TILE + row] = make_float2(mean_i, m2_i);
+  quarter_barrier(row >> 5);
+  float2 pt[NSPLIT];
+#pragma unroll
+  for (int i = 0; i < NSPLIT; ++i) pt[i] = red[i * TILE + row];
+  float m = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NSPLIT; ++i) m += pt[i].x;
+  m *= (1.0f / NSPLIT);
+  float m2 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NSPLIT; ++i) { const float d = pt[i].x - m; m2 += pt[i].y + n * d * d; }
+  mean = m;
+  inv = rsqrtf(m2 / (n * NSPLIT) + eps);
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(chain::THREADS, 1)
+tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
+                 const __grid_constant__ CUtensorMap tm_w3, const ChainArgs p) {
+  using namespace chain;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_MISC);
+  volatile int* s_item = reinterpret_cast<volatile int*>(smem + SM_MISC + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int NPART = SPLIT ? 3 : 1, NPLANE = SPLIT ? 2 : 1;
+
+  if ((smem_u32(smem) & 1023u) != 0) __trap();      // the swizzled operand images need a 1024-byte aligned base
+  if (warp == 16) tmem_alloc(tmem_slot, 512);
+  if (tid == 0) {
+    mbar_init(&bars[B_W1], 1); mbar_init(&bars[B_W2], 1); mbar_init(&bars[B_W3], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&bars[B_A3 + i], 4);       // a 32-channel chunk belongs to the 4 warps of one column quarter
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[B_FREE + i], 1);
+    mbar_init(&bars[B_D3], 1); mbar_init(&bars[B_D1], 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[B_D2 + i], 1);
+    mbar_init(&bars[B_C1], EPI_WARPS); mbar_init(&bars[B_A2], EPI_WARPS);
+    mbar_init(&bars[B_DEP], 1); mbar_init(&bars[B_PUB], EPI_WARPS);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (*tmem_slot != 0) __trap();                    // one CTA per SM owns all 512 columns: addresses below are constants
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  const int nb = p.n_blocks;
+  // ---- weight / aux loads of one block (loader warp, one elected lane)
+  auto issue_w1 = [&](int b) {       // + the aux record of the block (biases, column sums, cumulative conv_3 bias)
+    mbar_arrive_expect_tx(&bars[B_W1], (uint32_t)(NPLANE * W1_PART + AUX_FLOATS * 4));
+    for (int part = 0; part < NPLANE; ++part)
+      for (int kc = 0; kc < 4; ++kc)
+        tma_load_2d(smem + SM_W1 + part * W1_PART + kc * 8192, &tm_w1, kc * 64, (b * 2 + part) * 64, &bars[B_W1]);
+    const float* a = p.aux + (size_t)b * AUX_FLOATS;
+    bulk_g2s(smem + SM_AUXA + (b & 1) * 768, a, 768, &bars[B_W1]);
+    bulk_g2s(smem + SM_B3, a + AUX_B3, 1024, &bars[B_W1]);
+  };
+  auto issue_aux_final = [&]() {     // after the last block only the cumulative bias is needed
+    mbar_arrive_expect_tx(&bars[B_W1], 1024u);
+    bulk_g2s(smem + SM_B3, p.aux + (size_t)nb * AUX_FLOATS + AUX_B3, 1024, &bars[B_W1]);
+  };
+  auto issue_w2 = [&](int b) {
+    mbar_arrive_expect_tx(&bars[B_W2], (uint32_t)(NPLANE * W2_PART));
+    for (int part = 0; part < NPLANE; ++part)
+      for (int kc = 0; kc < 3; ++kc)
+        tma_load_2d(smem + SM_W2 + part * W2_PART + kc * 8192, &tm_w2, kc * 64, (b * 2 + part) * 64, &bars[B_W2]);
+  };
+  auto issue_w3 = [&](int b) {
+    mbar_arrive_expect_tx(&bars[B_W3], (uint32_t)(NPLANE * W3_PART));
+    for (int part = 0; part < NPLANE; ++part)
+      tma_load_2d(smem + SM_W3 + part * W3_PART, &tm_w3, 0, (b * 2 + part) * 256, &bars[B_W3]);
+  };
+
+  if (warp >= EPI_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+
+  // The weights do not depend on the previous launch: the first block's matrices travel while it drains.
+  if (warp == 17) {
+    if (elect_one()) {
+      tma_prefetch_desc(&tm_w1); tma_prefetch_desc(&tm_w2); tma_prefetch_desc(&tm_w3);
+      issue_w1(0); issue_w2(0); issue_w3(0);
+    }
+    __syncwarp();
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");      // stem output, flags and the work counter are complete and visible
+  if (tid == 17 * 32) s_item[0] = atomicAdd(p.counter, 1);
+  __syncthreads();
+
+  uint32_t it = 0;      // blocks processed by this CTA: parity of the once-per-block barriers
+  for (int n = 0;; ++n) {
+    const int item = s_item[n & 1];
+    if (item >= p.n_items) break;
+    const int j = item / p.B, u = item - j * p.B, tile = u * p.tiles_per_utt + j;
+    const bool has_prev = j > 0, has_next = j + 1 < p.tiles_per_utt;
+
+    if (warp == 16) {
+      // ================= MMA issue (whole warp convergent, one lane elected inside the asm) =================
+      constexpr uint32_t id64 = make_idesc_f16(TILE, 64);
+      uint32_t pw1 = (uint32_t)(n * (nb + 1)) & 1u;
+      for (int b = 0; b < nb; ++b, ++it) {
+        const uint32_t ph = it & 1u;
+        const uint32_t sbase = smem_u32(smem) + (uint32_t)(p.zero * (int)it);
+        const int d = 1 << (b % p.nd);
+        // ---- GEMM3: D13 = ReLU(h) W1_b, K = 256 in eight 32-channel chunks, issued as the epilogue produces them
+        mbar_wait_bounded(&bars[B_W1], pw1); pw1 ^= 1u;
+        {
+          uint32_t acc = 0;
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) {
+            mbar_wait_bounded(&bars[B_A3 + cc], ph); tc_fence_after();
+#pragma unroll
+            for (int part = 0; part < NPART; ++part) {
+              const uint32_t a0 = COL_A3 + 32 * (cc & 3) + (part == 1 ? 16 : 0);
+              const uint32_t w0 = sbase + SM_W1 + (part == 2 ? W1_PART : 0) + (cc >> 1) * 8192 + (cc & 1) * 64;
+              mma_ts_elect_k<2>(COL_D13, a0, make_smem_desc_sw128(w0), id64, acc);
+              acc = 1;
+            }
+            if (cc < 4) mma_commit_elect(&bars[B_FREE + cc]);      // ring slot cc may be overwritten by chunk cc + 4
+          }
+          mma_commit_elect(&bars[B_D3]);
+        }
+        // ---- GEMM1: D13 = [c1(t-2d) | c1(t-d) | c1(t)] W2_b, A and B in shared memory; tap kc starts (2 - kc) d rows early
+        mbar_wait_bounded(&bars[B_W2], ph);
+        mbar_wait_bounded(&bars[B_C1], ph); tc_fence_after();
+        {
+          uint32_t acc = 0;
+#pragma unroll
+          for (int part = 0; part < NPART; ++part) {
+            const uint32_t c1b = sbase + SM_C1 + (part == 1 ? C1_PLANE : 0), w0 = sbase + SM_W2 + (part == 2 ? W2_PART : 0);
+#pragma unroll
+            for (int kc = 0; kc < 3; ++kc) {
+              const uint32_t a_addr = c1b + (uint32_t)(HALO - (2 - kc) * d) * 16;
+              mma_ss_elect_k4<2 * C1_UNIT / 16>(COL_D13, make_smem_desc_noswz(a_addr, C1_UNIT, 128), make_smem_desc_sw128(w0 + kc * 8192), id64, acc);
+              acc = 1;
+            }
+          }
+          mma_commit_elect(&bars[B_D1]);
+        }
+        // ---- GEMM2: H += LN(ReLU(c2)) W3_b, K = 64, four 64-column groups committed one by one
+        mbar_wait_bounded(&bars[B_W3], ph);
+        mbar_wait_bounded(&bars[B_A2], ph); tc_fence_after();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+          for (int part = 0; part < NPART; ++part) {
+            const uint32_t a0 = part == 1 ? COL_A2_LO : COL_A2_HI, w0 = sbase + SM_W3 + (part == 2 ? W3_PART : 0) + g * 8192;
+            mma_ts_elect_k<4>(COL_H + 64 * g, a0, make_smem_desc_sw128(w0), id64, 1u);
+          }
+          mma_commit_elect(&bars[B_D2 + g]);
+        }
+      }
+      mbar_wait_bounded(&bars[B_W1], pw1);      // the end-of-tile aux record: keeps this warp's view of the barrier in step
+    } else if (warp == 17) {
+      // ================= weight loader: re-fill a matrix as soon as the GEMM that reads it has committed =================
+      int next = 0;
+      if (lane == 0) { next = atomicAdd(p.counter, 1); s_item[(n + 1) & 1] = next; }
+      next = __shfl_sync(0xffffffffu, next, 0);
+      const bool more = next < p.n_items;
+      for (int b = 0; b < nb; ++b, ++it) {
+        const uint32_t ph = it & 1u;
+        const bool last = b + 1 == nb;
+        mbar_wait_bounded(&bars[B_D3], ph);
+        if (elect_one()) { if (!last) issue_w1(b + 1); else issue_aux_final(); }
+        __syncwarp();
+        mbar_wait_bounded(&bars[B_D1], ph);
+        if (elect_one()) { if (!last) issue_w2(b + 1); else if (more) issue_w2(0); }
+        __syncwarp();
+        mbar_wait_bounded(&bars[B_D2 + 3], ph);
+        if (elect_one()) { if (!last) issue_w3(b + 1); else if (more) issue_w3(0); }
+        __syncwarp();
+      }
+    } else if (warp == 18) {
+      // ================= flag agent: acquire the predecessor's halo rows, release this tile's =================
+      for (int b = 0; b < nb; ++b, ++it) {
+        if (has_prev && lane == 0) {
+          const int* f = p.flags + tile - 1;
+          if (ld_acquire_gpu(f) <= b) {
+            const long long t0 = clock64();
+            uint32_t spins = 0;
+            while (ld_acquire_gpu(f) <= b)
+              if ((++spins & 255u) == 0 && clock64() - t0 > SPIN_LIMIT_CYCLES) __trap();
+          }
+        }
+        __syncwarp();
+        if (elect_one()) mbar_arrive(&bars[B_DEP]);
+        __syncwarp();
+        mbar_wait_bounded(&bars[B_PUB], it & 1u);      // every epilogue warp has written its c1 rows of block b
+        if (has_next && elect_one()) { __threadfence(); red_release_gpu_add(p.flags + tile, 1); }
+        __syncwarp();
+      }
+    } else if (warp < EPI_WARPS) {
+      // ================= epilogue: TMEM lane quarter q = warp & 3, column quarter qd = warp >> 2 =================
+      const int qd = warp >> 2, row = (warp & 3) * 32 + lane;
+      const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+      const int t = j * TILE + row;
+      const bool valid = t < p.T;
+      float* hrow = p.h + (size_t)tile * (TILE * 256) + row * 4;
+      float2* red = reinterpret_cast<float2*>(smem + SM_RED);
+      const float* sB3 = reinterpret_cast<const float*>(smem + SM_B3);
+      auto warp_arrive = [&](uint64_t* bar) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar); };
+      uint32_t pw1 = (uint32_t)(n * (nb + 1)) & 1u, pd2 = (uint32_t)(n * nb) & 1u, mrg = 0;
+      // this thread's piece of a halo record (8 KB = 512 x 16 B): plane = tid >> 8, unit = (tid >> 5) & 7, row = tid & 31
+      unsigned char* halo_dst = smem + SM_C1 + (tid >> 8) * C1_PLANE + ((tid >> 5) & 7) * C1_UNIT + (tid & 31) * 16;
+      const bool halo_mine = SPLIT || tid < 256;
+      const __half* halo_in = p.halo + ((size_t)(u * 2 + ((j + 1) & 1)) * nb) * 4096 + tid * 8;        // written by tile j - 1
+      __half* halo_out = p.halo + ((size_t)(u * 2 + (j & 1)) * nb) * 4096;
+
+      // ---- tile prologue: H <- ReLU(LayerNorm(z) * gamma) of the stem pre-activation z (tcn.py:176-179); rows beyond T are zero
+      {
+        const float2* sp = p.stem_stats + ((size_t)tile * TILE + row) * 8;
+        float2 pt[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pt[i] = sp[i];
+        float m = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m += pt[i].x;
+        m *= 0.125f;
+        float m2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float dd = pt[i].x - m; m2 += pt[i].y + 32.0f * dd * dd; }
+        const float inv0 = rsqrtf(m2 * (1.0f / 256.0f) + 1e-6f), mean0 = m;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int cc = qd + 4 * i;
+          float4 hv[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) hv[q] = __ldcs(reinterpret_cast<const float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4)));
+          const float4* gm = reinterpret_cast<const float4*>(p.gamma + 32 * cc);
+          uint32_t v[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 g = __ldg(gm + q);
+            const float g0 = inv0 * g.x, g1 = inv0 * g.y, g2 = inv0 * g.z, g3 = inv0 * g.w;
+            v[4 * q]     = __float_as_uint(valid ? relu(fmaf(hv[q].x, g0, -mean0 * g0)) : 0.0f);
+            v[4 * q + 1] = __float_as_uint(valid ? relu(fmaf(hv[q].y, g1, -mean0 * g1)) : 0.0f);
+            v[4 * q + 2] = __float_as_uint(valid ? relu(fmaf(hv[q].z, g2, -mean0 * g2)) : 0.0f);
+            v[4 * q + 3] = __float_as_uint(valid ? relu(fmaf(hv[q].w, g3, -mean0 * g3)) : 0.0f);
+          }
+          tmem_st32(lane_addr + COL_H + 32 * cc, v);
+        }
+        tmem_wait_st();
+        if (!has_prev && halo_mine) *reinterpret_cast<uint4*>(halo_dst) = make_uint4(0, 0, 0, 0);      // causal zero padding
+      }
+      float sc = 1.0f;      // power-of-two operand scale of the row (see the header)
+      for (int b = 0; b < nb; ++b, ++it) {
+        const uint32_t ph = it & 1u;
+        const float* auxa = reinterpret_cast<const float*>(smem + SM_AUXA + (b & 1) * 768);
+        // ---- P2: r3 = ReLU(H + B3cum_b) * sc -> A3 ring (un-normalised fp16 hi | lo), row sums for the deferred LayerNorm
+        mbar_wait_bounded(&bars[B_W1], pw1); pw1 ^= 1u;      // aux record of block b
+        float2 s1v = make_float2(0.0f, 0.0f), s2v = make_float2(0.0f, 0.0f);
+        const float2 scv = make_float2(sc, sc);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int cc = qd + 4 * i;
+          if (b > 0) mbar_wait_bounded(&bars[B_D2 + (cc >> 1)], pd2);      // GEMM2 of the previous block has written these columns
+          tc_fence_after();
+          float v[32];
+          tmem_ld32(lane_addr + COL_H + 32 * cc, v); tmem_wait_ld();
+          const float4* bc = reinterpret_cast<const float4*>(sB3 + 32 * cc);
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bq = bc[q];
+            const float2 t0 = __fadd2_rn(make_float2(v[4 * q], v[4 * q + 1]), make_float2(bq.x, bq.y));
+            const float2 t1 = __fadd2_rn(make_float2(v[4 * q + 2], v[4 * q + 3]), make_float2(bq.z, bq.w));
+            const float2 r0 = __fmul2_rn(make_float2(relu(t0.x), relu(t0.y)), scv);
+            const float2 r1 = __fmul2_rn(make_float2(relu(t1.x), relu(t1.y)), scv);
+            s1v = __fadd2_rn(s1v, r0); s2v = __ffma2_rn(r0, r0, s2v);
+            s1v = __fadd2_rn(s1v, r1); s2v = __ffma2_rn(r1, r1, s2v);
+            to_h2<SPLIT>(r0.x, r0.y, hi[2 * q], lo[2 * q]);
+            to_h2<SPLIT>(r1.x, r1.y, hi[2 * q + 1], lo[2 * q + 1]);
+          }
+          if (i == 1) { mbar_wait_bounded(&bars[B_FREE + qd], ph); tc_fence_after(); }      // the MMAs of chunk qd have read ring slot qd
+          tmem_st16(lane_addr + COL_A3 + 32 * qd, hi);
+          if (SPLIT) tmem_st16(lane_addr + COL_A3 + 32 * qd + 16, lo);
+          tmem_wait_st(); warp_arrive(&bars[B_A3 + cc]);
+        }
+        if (b > 0) pd2 ^= 1u;
+        float mu3, inv3;
+        {
+          const float s1 = s1v.x + s1v.y, s2 = s2v.x + s2v.y, m1 = s1 * (1.0f / 64.0f);
+          ln_merge(red + (mrg & 1) * (NSPLIT * TILE), row, qd, 64.0f, m1, fmaxf(s2 - s1 * m1, 0.0f), 1e-6f * sc * sc, mu3, inv3);
+          ++mrg;
+        }
+        // ---- P3: c1 = LN(ReLU(inv3 (D13 - mu3 colsum(W1)) + b1)) -> shared memory rows 32.., rows 96..127 also to the halo buffer
+        mbar_wait_bounded(&bars[B_DEP], ph);
+        uint4 hal = make_uint4(0, 0, 0, 0);
+        if (has_prev && halo_mine) hal = __ldcg(reinterpret_cast<const uint4*>(halo_in + (size_t)b * 4096));
+        mbar_wait_bounded(&bars[B_D3], ph); tc_fence_after();
+        {
+          float a[16];
+          tmem_ld16(lane_addr + COL_D13 + 16 * qd, a); tmem_wait_ld();
+          const float nim3 = -inv3 * mu3;
+          float s = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            a[k] = relu(fmaf(inv3, a[k], fmaf(nim3, auxa[64 + 16 * qd + k], auxa[16 * qd + k])));
+            s += a[k];
+          }
+          const float mean_i = s * (1.0f / 16.0f);
+          float q2 = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) { const float dd = a[k] - mean_i; q2 = fmaf(dd, dd, q2); }
+          float mean, inv;
+          ln_merge(red + (mrg & 1) * (NSPLIT * TILE), row, qd, 16.0f, mean_i, q2, 1e-6f, mean, inv);
+          ++mrg;
+          const float off = -mean * inv;
+          unsigned char* c1w = smem + SM_C1 + (2 * qd) * C1_UNIT + (HALO + row) * 16;
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float x0 = valid ? fmaf(a[8 * e + 2 * k], inv, off) : 0.0f, x1 = valid ? fmaf(a[8 * e + 2 * k + 1], inv, off) : 0.0f;
+              to_h2<SPLIT>(x0, x1, hi[k], lo[k]);
+            }
+            const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(c1w + e * C1_UNIT) = vh;
+            if (SPLIT) *reinterpret_cast<uint4*>(c1w + C1_PLANE + e * C1_UNIT) = vl;
+            if (has_next && row >= TILE - HALO) {
+              __half* ho = halo_out + (size_t)b * 4096 + ((size_t)(2 * qd + e) * HALO + (row - (TILE - HALO))) * 8;
+              *reinterpret_cast<uint4*>(ho) = vh;
+              if (SPLIT) *reinterpret_cast<uint4*>(ho + 8 * HALO * 8) = vl;
+            }
+          }
+          if (has_prev && halo_mine) *reinterpret_cast<uint4*>(halo_dst) = hal;
+          fence_proxy_async();      // generic-proxy writes of the c1 tile -> visible to the tensor core's reads
+          warp_arrive(&bars[B_C1]);
+          if (lane == 0) mbar_arrive(&bars[B_PUB]);      // after the __syncwarp of warp_arrive: this warp's halo rows are written
+        }
+        // ---- P1: A2 = LN(ReLU(D13 + b2)) as fp16 hi | lo (normalised here: GEMM2 accumulates into H)
+        mbar_wait_bounded(&bars[B_D1], ph); tc_fence_after();
+        {
+          float a[16];
+          tmem_ld16(lane_addr + COL_D13 + 16 * qd, a); tmem_wait_ld();
+          float s = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) { a[k] = relu(a[k] + auxa[128 + 16 * qd + k]); s += a[k]; }
+          const float mean_i = s * (1.0f / 16.0f);
+          float q2 = 0.0f;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) { const float dd = a[k] - mean_i; q2 = fmaf(dd, dd, q2); }
+          float mean, inv;
+          ln_merge(red + (mrg & 1) * (NSPLIT * TILE), row, qd, 16.0f, mean_i, q2, 1e-6f, mean, inv);
+          ++mrg;
+          const float off = -mean * inv;
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) to_h2<SPLIT>(fmaf(a[2 * k], inv, off), fmaf(a[2 * k + 1], inv, off), hi[k], lo[k]);
+          tmem_st8(lane_addr + COL_A2_HI + 8 * qd, hi);
+          if (SPLIT) tmem_st8(lane_addr + COL_A2_LO + 8 * qd, lo);
+          tmem_wait_st(); warp_arrive(&bars[B_A2]);
+        }
+        // operand scale of the next block: the exponent of this block's 1 / std (true scale = inv3 * sc)
+        sc = __uint_as_float(__float_as_uint(fminf(fmaxf(inv3 * sc, 1e-30f), 1e30f)) & 0x7F800000u);
+      }
+      // ---- tile end: residual sum after the last block = H + B3cum_nb -> tiled buffer for the output layer
+      mbar_wait_bounded(&bars[B_W1], pw1);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int cc = qd + 4 * i;
+        mbar_wait_bounded(&bars[B_D2 + (cc >> 1)], pd2); tc_fence_after();
+        float v[32];
+        tmem_ld32(lane_addr + COL_H + 32 * cc, v); tmem_wait_ld();
+        const float4* bc = reinterpret_cast<const float4*>(sB3 + 32 * cc);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bq = bc[q];
+          *reinterpret_cast<float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4)) =
+              valid ? make_float4(v[4 * q] + bq.x, v[4 * q + 1] + bq.y, v[4 * q + 2] + bq.z, v[4 * q + 3] + bq.w) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      tc_fence_before();
+    } else {
+      it += nb;      // warp 19: idle
+    }
+    __syncthreads();      // tile end: the next item is known, B3cum / TMEM / the c1 tile are quiescent
+    if (warp == 17) {
+      const int next = s_item[(n + 1) & 1];
+      if (next < p.n_items && elect_one()) issue_w1(0);
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc(0, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &f, 12000, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// [rows][K] fp16 row-major -> tensor map whose box is {64 K-elements = 128 bytes, box_rows}, 128-byte swizzle: what lands in
+// shared memory is the UMMA K-major SWIZZLE_128B operand image of one 64-wide K chunk.
+int make_weight_map(void* out, const void* dev, int K, size_t rows, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return DXI_E_CUDA; }
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(dev), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return DXI_E_CUDA; }
+  return DXI_OK;
+}
+
+// W [K][N] fp32 (Keras layout flattened) -> [N][K] fp16 hi and lo (K contiguous); colsum over the effective weights.
+static void pack_nk(__half* hi, __half* lo, int N, int K, const float* W, bool split, float* colsum) {
+  for (int n = 0; n < N; ++n) {
+    double cs = 0.0;
+    for (int k = 0; k < K; ++k) {
+      const float w = W[(size_t)k * N + n];
+      const __half h = __float2half_rn(w);
+      const __half l = __float2half_rn(w - __half2float(h));
+      hi[(size_t)n * K + k] = h;
+      lo[(size_t)n * K + k] = l;
+      cs += (double)__half2float(h) + (split ? (double)__half2float(l) : 0.0);
+    }
+    if (colsum) colsum[n] = (float)cs;
+  }
+}
+
+bool resnet_chain_supported(const dxi_net& net) {
+  static const bool off = [] { const char* v = getenv("DXI_TCN_STAGED"); return v && *v && *v != '0'; }();
+  return !off && net.cfg.padding == DXI_PAD_CAUSAL;
+}
+
+int resnet_chain_prepare(dxi_net& net, cudaStream_t st) {
+  using namespace chain;
+  const dxi_net_cfg& c = net.cfg;
+  const int nb = c.n_blocks;
+  const bool split = c.precision == DXI_PREC_F16X3;
+  // global images: W1 [nb][2][64][256], W2 [nb][2][64][192], W3 [nb][2][256][64] fp16; aux [nb + 1][448] fp32
+  const size_t n1 = (size_t)nb * 2 * 64 * 256, n2 = (size_t)nb * 2 * 64 * 192, n3 = (size_t)nb * 2 * 256 * 64;
+  const size_t off2 = align_up(n1 * 2, 1024), off3 = off2 + align_up(n2 * 2, 1024), offa = off3 + align_up(n3 * 2, 1024);
+  const size_t total = offa + (size_t)(nb + 1) * AUX_FLOATS * 4;
+  std::vector<unsigned char> img(total, 0);
+  __half* w1 = reinterpret_cast<__half*>(img.data());
+  __half* w2 = reinterpret_cast<__half*>(img.data() + off2);
+  __half* w3 = reinterpret_cast<__half*>(img.data() + off3);
+  float* aux = reinterpret_cast<float*>(img.data() + offa);
+  std::vector<double> b3cum(256, 0.0);
+  for (int b = 0; b <= nb; ++b) {
+    float* a = aux + (size_t)b * AUX_FLOATS;
+    for (int k = 0; k < 256; ++k) a[AUX_B3 + k] = (float)b3cum[k];
+    if (b == nb) break;
+    const int li = 2 + 3 * b;
+    pack_nk(w1 + (size_t)b * 2 * 64 * 256, w1 + ((size_t)b * 2 + 1) * 64 * 256, 64, 256, net.host_tensor(li, "kernel")->data(), split, a + 64);
+    pack_nk(w2 + (size_t)b * 2 * 64 * 192, w2 + ((size_t)b * 2 + 1) * 64 * 192, 64, 192, net.host_tensor(li + 1, "kernel")->data(), split, nullptr);
+    pack_nk(w3 + (size_t)b * 2 * 256 * 64, w3 + ((size_t)b * 2 + 1) * 256 * 64, 256, 64, net.host_tensor(li + 2, "kernel")->data(), split, nullptr);
+    memcpy(a, net.host_tensor(li, "bias")->data(), 64 * 4);
+    memcpy(a + 128, net.host_tensor(li + 1, "bias")->data(), 64 * 4);
+    const float* b3 = net.host_tensor(li + 2, "bias")->data();
+    for (int k = 0; k < 256; ++k) b3cum[k] += (double)b3[k];
+  }
+  if (net.d_chain) { cudaFree(net.d_chain); net.d_chain = nullptr; }
+  DXI_CUDA(cudaMalloc(&net.d_chain, total));
+  DXI_CUDA(cudaMemcpyAsync(net.d_chain, img.data(), total, cudaMemcpyHostToDevice, st));
+  DXI_CUDA(cudaStreamSynchronize(st));      // img is a local
+  unsigned char* d = reinterpret_cast<unsigned char*>(net.d_chain);
+  net.chain_aux_offset = offa;
+  if (int rc = make_weight_map(net.chain_tm[0], d, 256, (size_t)nb * 2 * 64, 64)) return rc;
+  if (int rc = make_weight_map(net.chain_tm[1], d + off2, 192, (size_t)nb * 2 * 64, 64)) return rc;
+  if (int rc = make_weight_map(net.chain_tm[2], d + off3, 64, (size_t)nb * 2 * 256, 256)) return rc;
+  return DXI_OK;
+}
+
+size_t resnet_chain_extra_workspace(const dxi_net& net, int B, int tiles) {
+  return align_up((size_t)B * tiles * sizeof(int) + 64, 256) + (size_t)B * 2 * net.cfg.n_blocks * 8192;
+}
+
+// The residual blocks of one batch: h (tiled, stem pre-activation + stem_stats in, residual sum out).  `extra` is
+// resnet_chain_extra_workspace() bytes, 256-byte aligned; its first align_up(B * tiles * 4 + 64, 256) bytes (tile flags + work
+// counter) must have been zeroed earlier in the stream (before the stem launches, so that the launch chain stays kernel -> kernel).
+int resnet_chain_blocks(const dxi_net& net, float* h, const float2* stem_stats, int B, int T, void* extra, int n_sm, cudaStream_t st) {
+  using namespace chain;
+  const dxi_net_cfg& c = net.cfg;
+  const int tiles = (T + TILE - 1) / TILE;
+  const size_t flag_bytes = align_up((size_t)B * tiles * sizeof(int) + 64, 256);
+  int* flags = reinterpret_cast<int*>(extra);
+  int* counter = flags + (size_t)B * tiles;
+  __half* halo = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(extra) + flag_bytes);      // the caller has zeroed [extra, extra + flag_bytes)
+  ChainArgs a{};
+  a.aux = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(net.d_chain) + net.chain_aux_offset);
+  a.gamma = net.dev_tensor(1, "gamma");
+  a.h = h; a.stem_stats = stem_stats; a.halo = halo; a.flags = flags; a.counter = counter;
+  a.T = T; a.tiles_per_utt = tiles; a.B = B; a.n_items = B * tiles; a.n_blocks = c.n_blocks;
+  a.nd = 0;
+  for (int m = c.max_d_rate; m > 0; m >>= 1) ++a.nd;
+  a.zero = 0;
+  const int grid = a.n_items < n_sm ? a.n_items : n_sm;
+  CUtensorMap tm[3];
+  memcpy(tm, net.chain_tm, sizeof(tm));
+  const bool split = c.precision == DXI_PREC_F16X3;
+  auto kern = split ? tcn_chain_kernel<true> : tcn_chain_kernel<false>;
+  DXI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  ProfScope prof("tcn_chain", st, 1);
+  DXI_CUDA(launch_pdl(kern, grid, THREADS, (size_t)SMEM_BYTES, st, tm[0], tm[1], tm[2], a));
+  DXI_LAUNCHED("tcn_chain_kernel");
+  return DXI_OK;
+}
+
+}  // namespace dxi

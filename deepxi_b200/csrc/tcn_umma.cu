@@ -38,6 +38,7 @@
 // keeping them as (spilled) loop invariants.  DESIGN.md section 4 has the measurements behind both.
 #include <cstdlib>
 #include <vector>
+#include "launch.cuh"
 #include "net.cuh"
 #include "umma.cuh"
 
@@ -830,25 +831,6 @@ static void pack_b_sw128(unsigned char* hi, unsigned char* lo, int N, int K, con
     for (int n = 0; n < N; ++n) colsum[n] = (float)cs[n];
 }
 
-static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-
-// Launch with programmatic stream serialization: the kernel may be scheduled while its predecessor in the stream
-// drains; it calls griddepcontrol.wait before touching anything the predecessor wrote.
-template <typename Args>
-static cudaError_t launch_pdl(void (*kern)(const Args), int grid, int block, size_t smem, cudaStream_t st, const Args& a) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(block);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, a);
-}
-
 static int n_dilations(int max_d_rate) { int n = 0; for (int m = max_d_rate; m > 0; m >>= 1) ++n; return n; }
 
 int resnet_umma_prepare(dxi_net& net, cudaStream_t st) {
@@ -913,6 +895,7 @@ int resnet_umma_prepare(dxi_net& net, cudaStream_t st) {
   DXI_CUDA(cudaMemcpyAsync(net.d_umma, img.data(), img.size(), cudaMemcpyHostToDevice, st));
   DXI_CUDA(cudaStreamSynchronize(st));   // img is a local
   net.umma_bytes = img.size();
+  if (resnet_chain_supported(net)) return resnet_chain_prepare(net, st);
   return DXI_OK;
 }
 
@@ -927,7 +910,8 @@ int64_t resnet_umma_workspace_bytes(const dxi_net& net, int B, int T) {
   const size_t c1_bytes = align_up((size_t)B * 2 * 8 * Ts * 16, 256);
   const size_t stats_bytes = (size_t)B * tiles * TILE * 8 * sizeof(float2);
   const size_t flag_bytes = align_up((size_t)B * tiles * sizeof(int), 256);
-  return (int64_t)(256 + h_bytes + 2 * c1_bytes + flag_bytes + stats_bytes);
+  const size_t chain_bytes = resnet_chain_supported(net) ? 256 + resnet_chain_extra_workspace(net, B, tiles) : 0;
+  return (int64_t)(256 + h_bytes + 2 * c1_bytes + flag_bytes + stats_bytes + chain_bytes);
 }
 
 // One group of whole utterances through stem -> 41 stages -> output layer; every group uses the same workspace region.
@@ -943,8 +927,16 @@ static int resnet_umma_group(const dxi_net& net, const float* mag, int B, int T,
   const size_t flag_bytes = align_up((size_t)B * tiles * sizeof(int), 256);
   int* flags = reinterpret_cast<int*>(base + h_bytes + 2 * c1_bytes);
   float2* stem_stats = reinterpret_cast<float2*>(base + h_bytes + 2 * c1_bytes + flag_bytes);
-  // zero padding rows of the c1 planes (and everything else in them) and the per-tile stage counters
-  DXI_CUDA(cudaMemsetAsync(c1[0], 0, 2 * c1_bytes + flag_bytes, st));
+  const bool chain = resnet_chain_supported(net);      // causal padding: depth-first residual blocks (tcn_chain.cu)
+  const size_t stats_bytes = (size_t)B * tiles * TILE * 8 * sizeof(float2);
+  unsigned char* chain_ws = reinterpret_cast<unsigned char*>(align_up(reinterpret_cast<uintptr_t>(base + h_bytes + 2 * c1_bytes + flag_bytes + stats_bytes), 256));
+  if (chain) {
+    // per-tile published-block counters + the work-item counter (the halo records behind them need no initialisation)
+    DXI_CUDA(cudaMemsetAsync(chain_ws, 0, align_up((size_t)B * tiles * sizeof(int) + 64, 256), st));
+  } else {
+    // zero padding rows of the c1 planes (and everything else in them) and the per-tile stage counters
+    DXI_CUDA(cudaMemsetAsync(c1[0], 0, 2 * c1_bytes + flag_bytes, st));
+  }
   static const bool no_flags = env_flag("DXI_TCN_NO_FLAGS");      // A/B switch: every stage waits for the whole previous launch
 
   const int n_tiles = B * tiles;
@@ -963,6 +955,9 @@ static int resnet_umma_group(const dxi_net& net, const float* mag, int B, int T,
       DXI_LAUNCHED("stem_umma_kernel");
     }
   }
+  if (chain) {
+    if (int rc = resnet_chain_blocks(net, h, stem_stats, B, T, chain_ws, n_sm, st)) return rc;
+  } else {
   // ---- 41 tensor-core stages
   const bool split = c.precision == DXI_PREC_F16X3;
   const size_t smem = IMG_BYTES + 1024;
@@ -993,6 +988,7 @@ static int resnet_umma_group(const dxi_net& net, const float* mag, int B, int T,
     if (split) DXI_CUDA(launch_pdl(tcn_stage_kernel<true>, grid, TCN_THREADS, smem, st, a));
     else       DXI_CUDA(launch_pdl(tcn_stage_kernel<false>, grid, TCN_THREADS, smem, st, a));
     DXI_LAUNCHED("tcn_stage_kernel");
+  }
   }
   }
   // ---- output layer (tcgen05 + one fp32 column): tiled h -> sigmoid(W h + b), row-major x_bar

@@ -44,6 +44,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
+// Same, but a wait that lasts longer than ~2 s of SM clocks is a protocol error (a missed arrival, a producer that never
+// ran): trap, so that the launch fails with an error instead of hanging the GPU.
+constexpr long long SPIN_LIMIT_CYCLES = 4000000000ll;
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t n = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++n & 1023u) == 0 && clock64() - t0 > SPIN_LIMIT_CYCLES) __trap();
+  }
+}
 
 // ---- bulk async copy global -> shared (TMA engine, no tensor map); bytes % 16 == 0 ---------------
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
@@ -53,6 +64,18 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- tensor-map TMA (cp.async.bulk.tensor): a 2-D box of a global tensor -> shared memory, swizzled by the engine as the
+// tensor map says; `tmap` points at a CUtensorMap in kernel-parameter (__grid_constant__) or global memory.
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
 
 // ---- tensor memory ----------------------------------------------------------------------------------
 // Whole-warp calls.  ncols: power of two >= 32.  The allocated base address is written to *smem_slot.
@@ -209,6 +232,23 @@ __device__ __forceinline__ void mma_ts_elect_k(uint32_t tmem_d, uint32_t tmem_a,
         "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
   }
+}
+// Four consecutive K = 16 steps with BOTH operands in shared memory under one election: step i reads A at adesc + i * A_STEP
+// (descriptor start-address units of 16 bytes: the distance between two K16 slices of the A image) and B at bdesc + 2 i (32 bytes
+// along the 128-byte swizzled row).  The first step accumulates iff `accumulate`, the others always.
+template <int A_STEP>
+__device__ __forceinline__ void mma_ss_elect_k4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e, t;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 t, 0, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "add.u64 a1, %1, %5;\n\tadd.u64 a2, %1, %6;\n\tadd.u64 a3, %1, %7;\n\t"
+      "add.u64 b1, %2, 2;\n\tadd.u64 b2, %2, 4;\n\tadd.u64 b3, %2, 6;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "n"(A_STEP), "n"(2 * A_STEP), "n"(3 * A_STEP)
+      : "memory");
 }
 __device__ __forceinline__ void mma_ss_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(

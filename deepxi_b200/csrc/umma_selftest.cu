@@ -4,25 +4,39 @@
 //   bit0  A operand: 0 = tensor memory (the production path), 1 = shared memory (128B swizzle)
 //   bit1  B operand layout: 0 = 128-byte swizzle (production), 1 = no swizzle (8x16B core matrices)
 //   bit2  A-in-TMEM half order: 0 = even k in the low half (production), 1 = swapped
+//   bit3  A operand in shared memory WITHOUT swizzle as [unit of 8 k][32 zero rows + 128 rows][16 B] and a descriptor whose start
+//         address is shifted SHIFT = 5 rows back: D[m] = A[m - 5] B^T with zero rows before the first (the c1 taps of tcn_chain.cu)
+//   bit4  B operand written by tensor-map TMA (cp.async.bulk.tensor.2d, 128-byte swizzle applied by the engine) instead of by threads
+#include <cuda.h>
 #include "umma.cuh"
 
 namespace dxi {
 using namespace umma;
 
-__global__ void __launch_bounds__(128) umma_selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ Bm,
-                                                            int N, int K, int variant, float* __restrict__ D) {
+constexpr int ST_SHIFT = 5, ST_ROWS = 160;
+
+__global__ void __launch_bounds__(128) umma_selftest_kernel(const __grid_constant__ CUtensorMap tm_b, const __half* __restrict__ A,
+                                                            const __half* __restrict__ Bm, int N, int K, int variant, float* __restrict__ D) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar, bar_tma;
   __shared__ uint32_t tmem_base_slot;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const bool a_smem = variant & 1, b_noswz = variant & 2, a_swap = variant & 4;
+  const bool a_smem = variant & 1, b_noswz = variant & 2, a_swap = variant & 4, a_taps = variant & 8, b_tma = variant & 16;
   unsigned char* sB = smem;                               // K/64 chunks of [N x 128 B]  (or no-swizzle image)
   unsigned char* sA = smem + (size_t)N * K * 2;           // K/64 chunks of [128 x 128 B]
 
   if (warp == 0) tmem_alloc(&tmem_base_slot, 512);
-  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(&bar, 1); mbar_init(&bar_tma, 1); fence_mbar_init(); }
+  __syncthreads();
   // ---- B image
+  if (b_tma) {
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&bar_tma, (uint32_t)(N * K * 2));
+      for (int c = 0; c < K / 64; ++c) tma_load_2d(sB + (size_t)c * N * 128, &tm_b, c * 64, 0, &bar_tma);
+    }
+    mbar_wait_bounded(&bar_tma, 0);
+  } else
   for (int i = tid; i < N * (K / 8); i += 128) {          // one 16-byte unit (8 halves) per step
     const int n = i / (K / 8), u = i - n * (K / 8);       // unit u covers k = 8u .. 8u+7
     uint4 val = *reinterpret_cast<const uint4*>(Bm + (size_t)n * K + 8 * u);
@@ -35,7 +49,14 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __half* __rest
     }
     *reinterpret_cast<uint4*>(sB + off) = val;
   }
-  if (a_smem) {
+  if (a_taps) {
+    for (int i = tid; i < ST_ROWS * (K / 8); i += 128) {
+      const int u = i / ST_ROWS, r = i - u * ST_ROWS;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (r >= 32) val = *reinterpret_cast<const uint4*>(A + (size_t)(r - 32) * K + 8 * u);
+      *reinterpret_cast<uint4*>(sA + ((size_t)u * ST_ROWS + r) * 16) = val;
+    }
+  } else if (a_smem) {
     for (int i = tid; i < 128 * (K / 8); i += 128) {
       const int m = i / (K / 8), u = i - m * (K / 8);
       uint4 val = *reinterpret_cast<const uint4*>(A + (size_t)m * K + 8 * u);
@@ -51,7 +72,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __half* __rest
   const uint32_t tbase = tmem_base_slot;
   const uint32_t lane_base = (uint32_t)(warp * 32);
   const uint32_t a_col = 256;
-  if (!a_smem) {
+  if (!a_smem && !a_taps) {
     // thread tid owns row tid: pack its K halves into K/2 columns starting at a_col
     for (int c0 = 0; c0 < K / 2; c0 += 16) {
       uint32_t r[16];
@@ -75,7 +96,10 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __half* __rest
       uint64_t bdesc;
       if (!b_noswz) bdesc = make_smem_desc_sw128(smem_u32(sB + (size_t)c * N * 128) + kk * 32);
       else          bdesc = make_smem_desc_noswz(smem_u32(sB) + k16 * 256, 128, (K / 8) * 128);
-      if (!a_smem) {
+      if (a_taps) {
+        uint64_t adesc = make_smem_desc_noswz(smem_u32(sA) + (2 * k16) * ST_ROWS * 16 + (32 - ST_SHIFT) * 16, ST_ROWS * 16, 128);
+        mma_ss(tbase, adesc, bdesc, idesc, k16 > 0);
+      } else if (!a_smem) {
         mma_ts(tbase, tmem_addr(tbase, 0, a_col + 8 * k16), bdesc, idesc, k16 > 0);
       } else {
         uint64_t adesc = make_smem_desc_sw128(smem_u32(sA + (size_t)c * 128 * 128) + kk * 32);
@@ -140,6 +164,9 @@ __global__ void __launch_bounds__(1024) tmem_bw_kernel(int mode, int rounds, lon
 
 using namespace dxi;
 
+namespace dxi { int make_weight_map(void* out, const void* dev, int K, size_t rows, int box_rows); }
+static int selftest_weight_map(CUtensorMap* tm, const void* b, int K, int N) { return dxi::make_weight_map(tm, b, K, (size_t)N, N); }
+
 extern "C" DXI_API int dxi_debug_tmem_bw(int mode, int warps, int rounds, long long* dev_out, void* stream) {
   if (int rc = check_device()) return rc;
   DXI_REQUIRE(warps >= 4 && warps <= 32 && warps % 4 == 0 && rounds > 0 && dev_out, "dxi_debug_tmem_bw: bad argument");
@@ -154,9 +181,14 @@ extern "C" DXI_API int dxi_selftest_umma(const void* a_f16, const void* b_f16, i
   DXI_REQUIRE(a_f16 && b_f16 && d_out, "dxi_selftest_umma: null argument");
   DXI_REQUIRE(N >= 32 && N <= 256 && N % 32 == 0, "dxi_selftest_umma: N must be a multiple of 32 in [32,256]");
   DXI_REQUIRE(K >= 64 && K <= 256 && K % 64 == 0, "dxi_selftest_umma: K must be a multiple of 64 in [64,256]");
-  const size_t smem = (size_t)N * K * 2 + 128 * (size_t)K * 2 + 2048;
+  const size_t smem = (size_t)N * K * 2 + ST_ROWS * (size_t)K * 2 + 2048;
   DXI_CUDA(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  umma_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(reinterpret_cast<const __half*>(a_f16),
+  CUtensorMap tm{};
+  if (variant & 16) {
+    DXI_REQUIRE(!(variant & 2), "dxi_selftest_umma: the TMA-loaded B operand is the 128-byte swizzled one");
+    if (int rc = selftest_weight_map(&tm, b_f16, K, N)) return rc;
+  }
+  umma_selftest_kernel<<<1, 128, smem, as_stream(stream)>>>(tm, reinterpret_cast<const __half*>(a_f16),
                                                             reinterpret_cast<const __half*>(b_f16), N, K, variant, d_out);
   DXI_LAUNCHED("umma_selftest_kernel");
   return DXI_OK;

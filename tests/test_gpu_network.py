@@ -22,9 +22,10 @@ def _db_err(xbar, ref64, mu, sg):
     return np.abs(a - b)[m]
 
 
-@pytest.mark.parametrize('variant', range(8))
+@pytest.mark.parametrize('variant', list(range(8)) + [8, 10, 16, 17, 24])
 def test_umma_selftest(variant):
-    """tcgen05 building blocks: D = A B^T with A from TMEM / smem and B in 128B-swizzled / plain smem."""
+    """tcgen05 building blocks: D = A B^T with A from TMEM / smem and B in 128B-swizzled / plain smem; bit 3: A as the row-shifted
+    no-swizzle shared-memory operand of the c1 taps (tcn_chain.cu); bit 4: B written by tensor-map TMA."""
     if variant & 4 and variant & 1:
         pytest.skip('half-order swap only applies to A in TMEM')
     lib = _lib.load()
@@ -37,6 +38,8 @@ def test_umma_selftest(variant):
         _lib.check(lib.dxi_selftest_umma(_lib.ptr(dA), _lib.ptr(dB), N, K, variant, _lib.ptr(D), _lib.stream_ptr()))
         torch.cuda.synchronize()
         ref = A.astype(np.float32) @ B.astype(np.float32).T
+        if variant & 8:                # rows shifted by 5 with zeros before the first
+            ref = np.concatenate([np.zeros((5, N), np.float32), ref[:-5]])
         err = np.abs(D.cpu().numpy() - ref).max()
         if variant & 4:
             assert err > 1.0           # the swapped half order must NOT match: proves the test can see layout errors
