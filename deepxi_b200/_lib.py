@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libdeepxi_b200.so')
+LIB_PATH = os.environ.get('DXI_LIB') or os.path.join(_HERE, 'libdeepxi_b200.so')      # DXI_LIB: the tuning build (deepxi_b200/build.py)
 
 GTYPES = {'mmse-lsa': 0, 'mmse-stsa': 1, 'wf': 2, 'srwf': 3, 'cwf': 4, 'irm': 5, 'ibm': 6, 'deepmmse': 7}
 NET_KINDS = {'ResNetV2': 0, 'MHANetV3': 1, 'ResNet': 2, 'ResNetV3': 3}

@@ -12,12 +12,15 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-OBJ = os.path.join(HERE, 'build')
-LIB = os.path.join(HERE, 'libdeepxi_b200.so')
+# DXI_DEBUG_BUILD=1: the tuning build (-DDXI_ENABLE_DEBUG: phase clocks, per-CTA timelines, the dxi_debug_* entry points of
+# include/deepxi_b200_debug.h) as libdeepxi_b200_dbg.so next to the product library; DXI_LIB selects it at run time.
+DEBUG = bool(os.environ.get('DXI_DEBUG_BUILD'))
+OBJ = os.path.join(HERE, 'build_dbg' if DEBUG else 'build')
+LIB = os.path.join(HERE, 'libdeepxi_b200_dbg.so' if DEBUG else 'libdeepxi_b200.so')
 SOURCES = ['common.cu', 'gain.cu', 'stft.cu', 'net.cu', 'tcn_f32.cu', 'tcn_umma.cu', 'tcn_chain.cu', 'umma_selftest.cu', 'mhanet.cu', 'mha_umma.cu', 'attn_umma.cu', 'train_tgt.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
-         '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']
+         '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr'] + (['-DDXI_ENABLE_DEBUG'] if DEBUG else [])
 
 
 def _stale(target, deps):

@@ -47,6 +47,8 @@ int resnet_umma_prepare(dxi_net& net, cudaStream_t st);
 int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, float* xbar, void* ws, size_t ws_bytes,
                         cudaStream_t st);
 bool resnet_chain_supported(const dxi_net& net);
+float resnet_first_operand_scale(const dxi_net& net);
+float weight_pow2_scale(const float* W, size_t n, bool half);
 int resnet_chain_prepare(dxi_net& net, cudaStream_t st);
 size_t resnet_chain_extra_workspace(const dxi_net& net, int B, int tiles);
 int resnet_chain_blocks(const dxi_net& net, float* h, const float2* stem_stats, int B, int T, void* extra, int n_sm, cudaStream_t st);

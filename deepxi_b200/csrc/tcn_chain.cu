@@ -38,6 +38,7 @@
 // traps instead of hanging the GPU.
 #include <cuda.h>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <vector>
 #include "launch.cuh"
@@ -49,22 +50,22 @@ using namespace umma;
 
 namespace chain {
 constexpr int TILE = 128, HALO = 32, C1_ROWS = HALO + TILE;
-constexpr int NSPLIT = 4, EPI_WARPS = 16, EPI_THREADS = 512, THREADS = 640;
-constexpr int REGS_EPI = 104, REGS_AUX = 64;
+constexpr int NSPLIT = 4, EPI_WARPS = 16, THREADS = 640;
 // shared memory map (bytes from the 1024-aligned base)
 constexpr int SM_W1 = 0, W1_PART = 32768;                  // [part][4 K-chunks][64 rows x 128 B]
 constexpr int SM_W2 = 65536, W2_PART = 24576;              // [part][3 taps][64 rows x 128 B]
 constexpr int SM_W3 = 114688, W3_PART = 32768;             // [part][256 rows x 128 B]
 constexpr int SM_C1 = 180224, C1_UNIT = C1_ROWS * 16, C1_PLANE = 8 * C1_UNIT;   // [plane][unit][row][16 B]
-constexpr int SM_AUXA = SM_C1 + 2 * C1_PLANE;              // [2 slots][b1 64 | colsum(W1) 64 | b2 64] fp32
-constexpr int SM_B3 = SM_AUXA + 2 * 192 * 4;               // B3cum[256] fp32 (single buffer)
+constexpr int AUXA_FLOATS = 196;                           // b1 64 | colsum(W1) 64 | b2 64 | 1/s1, 1/s2, 1/s3, pad (weight scales, see pack_nk)
+constexpr int SM_AUXA = SM_C1 + 2 * C1_PLANE;              // [2 slots][AUXA_FLOATS] fp32
+constexpr int SM_B3 = SM_AUXA + 2 * AUXA_FLOATS * 4;               // B3cum[256] fp32 (single buffer)
 constexpr int SM_RED = SM_B3 + 1024;                       // LayerNorm partials [2][4][128] float2
 constexpr int SM_BAR = SM_RED + 2 * NSPLIT * TILE * 8;
 enum { B_W1 = 0, B_W2, B_W3, B_A3, B_FREE = B_A3 + 8, B_D3 = B_FREE + 4, B_D1, B_D2, B_C1 = B_D2 + 4, B_A2, B_DEP, B_PUB, N_BAR };
 constexpr int SM_MISC = SM_BAR + N_BAR * 8;                // tmem slot, item[2]
 constexpr int SMEM_BYTES = SM_MISC + 16;
 static_assert(SMEM_BYTES <= 232448, "shared memory map exceeds the 227 KB a CTA can have");
-constexpr int AUX_FLOATS = 448, AUX_B3 = 192;              // global aux record per block: b1 | colsum(W1) | b2 | B3cum
+constexpr int AUX_FLOATS = AUXA_FLOATS + 256, AUX_B3 = AUXA_FLOATS;      // global aux record per block: b1 | colsum(W1) | b2 | scales | B3cum
 // TMEM column map
 constexpr uint32_t COL_H = 0, COL_D13 = 256, COL_A2_HI = 320, COL_A2_LO = 352, COL_A3 = 384;
 }  // namespace chain
@@ -79,7 +80,17 @@ struct ChainArgs {
   int* counter;                // work-item counter (zeroed by the host with the flags)
   int T, tiles_per_utt, B, n_items, n_blocks, nd;
   int zero;                    // always 0 (keeps the MMA warp's descriptors out of its loop invariants, see tcn_umma.cu)
+  float sc0;                   // operand scale of the first block: power of two next to 1 / rms(gamma) (the first layer's output is LN * gamma)
 };
+
+#ifdef DXI_ENABLE_DEBUG
+// Tuning build only: clock64 stamps of one work item (32 per block: 0-15 epilogue thread 0, 16-31 MMA warp), scripts/chain_clocks.py
+__device__ long long* g_chain_dbg = nullptr;
+__device__ int g_chain_dbg_item = -1;
+#define CH_STAMP(k) do { if (dbgp) dbgp[b * 32 + (k)] = clock64(); } while (0)
+#else
+#define CH_STAMP(k) do { } while (0)
+#endif
 
 __device__ __forceinline__ float relu(float x) { return fmaxf(x, 0.0f); }
 __device__ __forceinline__ void quarter_barrier(int q) { asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(chain::NSPLIT * 32) : "memory"); }
@@ -120,7 +131,9 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_MISC);
   volatile int* s_item = reinterpret_cast<volatile int*>(smem + SM_MISC + 4);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index and work item go through a lane-0 broadcast: that is what tells ptxas they are warp-uniform, so that the MMA
+  // warp's descriptor arithmetic stays in uniform registers
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   constexpr int NPART = SPLIT ? 3 : 1, NPLANE = SPLIT ? 2 : 1;
 
   if ((smem_u32(smem) & 1023u) != 0) __trap();      // the swizzled operand images need a 1024-byte aligned base
@@ -149,7 +162,7 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
       for (int kc = 0; kc < 4; ++kc)
         tma_load_2d(smem + SM_W1 + part * W1_PART + kc * 8192, &tm_w1, kc * 64, (b * 2 + part) * 64, &bars[B_W1]);
     const float* a = p.aux + (size_t)b * AUX_FLOATS;
-    bulk_g2s(smem + SM_AUXA + (b & 1) * 768, a, 768, &bars[B_W1]);
+    bulk_g2s(smem + SM_AUXA + (b & 1) * (AUXA_FLOATS * 4), a, AUXA_FLOATS * 4, &bars[B_W1]);
     bulk_g2s(smem + SM_B3, a + AUX_B3, 1024, &bars[B_W1]);
   };
   auto issue_aux_final = [&]() {     // after the last block only the cumulative bias is needed
@@ -168,8 +181,9 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
       tma_load_2d(smem + SM_W3 + part * W3_PART, &tm_w3, 0, (b * 2 + part) * 256, &bars[B_W3]);
   };
 
-  if (warp >= EPI_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
-  else asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+  // No setmaxnreg here (tcn_umma.cu moves registers from the MMA warpgroup to the epilogue): with it ptxas keeps the MMA warp's
+  // descriptor arithmetic in vector registers (13 instructions per UTCHMMA, R2UR + VOTEU for every operand) instead of the
+  // uniform datapath (3-4), and this kernel is bound by that warp's issue rate; the epilogue fits the 96 registers of a 640-thread CTA.
 
   // The weights do not depend on the previous launch: the first block's matrices travel while it drains.
   if (warp == 17) {
@@ -183,68 +197,94 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
   if (tid == 17 * 32) s_item[0] = atomicAdd(p.counter, 1);
   __syncthreads();
 
-  uint32_t it = 0;      // blocks processed by this CTA: parity of the once-per-block barriers
   for (int n = 0;; ++n) {
-    const int item = s_item[n & 1];
+    const int item = __shfl_sync(0xffffffffu, s_item[n & 1], 0);
     if (item >= p.n_items) break;
     const int j = item / p.B, u = item - j * p.B, tile = u * p.tiles_per_utt + j;
     const bool has_prev = j > 0, has_next = j + 1 < p.tiles_per_utt;
+    // blocks this CTA has processed so far: the parity of the once-per-block barriers.  Every role keeps its own copy derived from
+    // the tile counter (a variable merged across the role branches would count as divergent and push the MMA warp's operand
+    // arithmetic out of the uniform datapath)
+    uint32_t it = (uint32_t)(n * nb);
+#ifdef DXI_ENABLE_DEBUG
+    long long* const dbgp = ((tid == 0 || tid == 16 * 32) && item == g_chain_dbg_item) ? g_chain_dbg : nullptr;
+#endif
 
     if (warp == 16) {
-      // ================= MMA issue (whole warp convergent, one lane elected inside the asm) =================
+      // ================= MMA issue: the whole warp runs this convergently, the lane elected here issues (see umma.cuh) =================
       constexpr uint32_t id64 = make_idesc_f16(TILE, 64);
+      constexpr uint32_t A_HI = desc_hi_noswz(128);
+      const uint32_t e = elect_leader();
       uint32_t pw1 = (uint32_t)(n * (nb + 1)) & 1u;
       for (int b = 0; b < nb; ++b, ++it) {
         const uint32_t ph = it & 1u;
-        const uint32_t sbase = smem_u32(smem) + (uint32_t)(p.zero * (int)it);
+        // p.zero (= 0, but only the host knows) makes every operand base depend on the iteration, so that the ~130 descriptors of
+        // a block are formed as base + immediate in uniform registers instead of being kept (and spilled) as loop invariants
+        const uint32_t z = (uint32_t)(p.zero * (int)it), sbase = smem_u32(smem) + z;
+        const uint32_t w1 = desc_lo_sw128(sbase + SM_W1), w2 = desc_lo_sw128(sbase + SM_W2), w3 = desc_lo_sw128(sbase + SM_W3);
         const int d = 1 << (b % p.nd);
         // ---- GEMM3: D13 = ReLU(h) W1_b, K = 256 in eight 32-channel chunks, issued as the epilogue produces them
         mbar_wait_bounded(&bars[B_W1], pw1); pw1 ^= 1u;
+        CH_STAMP(16);
         {
-          uint32_t acc = 0;
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) {
             mbar_wait_bounded(&bars[B_A3 + cc], ph); tc_fence_after();
+            if (cc == 0) CH_STAMP(17);
+            if (cc == 3) CH_STAMP(23);
+            if (cc == 7) CH_STAMP(18);
 #pragma unroll
-            for (int part = 0; part < NPART; ++part) {
-              const uint32_t a0 = COL_A3 + 32 * (cc & 3) + (part == 1 ? 16 : 0);
-              const uint32_t w0 = sbase + SM_W1 + (part == 2 ? W1_PART : 0) + (cc >> 1) * 8192 + (cc & 1) * 64;
-              mma_ts_elect_k<2>(COL_D13, a0, make_smem_desc_sw128(w0), id64, acc);
-              acc = 1;
-            }
-            if (cc < 4) mma_commit_elect(&bars[B_FREE + cc]);      // ring slot cc may be overwritten by chunk cc + 4
+            for (int part = 0; part < NPART; ++part)
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)      // chunk cc = K16 steps 2cc, 2cc + 1: half of the 64-wide K chunk cc >> 1
+                mma_ts_lo<DESC_HI_SW128>(z + COL_D13, z + COL_A3 + 32 * (cc & 3) + (part == 1 ? 16 : 0) + 8 * ks,
+                                         w1 + (((part == 2 ? W1_PART : 0) + (cc >> 1) * 8192 + (cc & 1) * 64 + ks * 32) >> 4), id64,
+                                         (cc | part | ks) != 0, e);
+            if (cc < 4) mma_commit_lo(&bars[B_FREE + cc], e);      // ring slot cc may be overwritten by chunk cc + 4
           }
-          mma_commit_elect(&bars[B_D3]);
+          mma_commit_lo(&bars[B_D3], e);
         }
         // ---- GEMM1: D13 = [c1(t-2d) | c1(t-d) | c1(t)] W2_b, A and B in shared memory; tap kc starts (2 - kc) d rows early
         mbar_wait_bounded(&bars[B_W2], ph);
         mbar_wait_bounded(&bars[B_C1], ph); tc_fence_after();
+        CH_STAMP(19);
         {
-          uint32_t acc = 0;
+          const uint32_t c1 = desc_lo_noswz(sbase + SM_C1 + HALO * 16, C1_UNIT);      // tap 2 (no shift); taps 1, 0 start d, 2d rows earlier
+          // The SS-mode MMAs are bound by shared-memory reads, so the two products with the same A operand (c1_hi W2_hi, c1_hi W2_lo)
+          // are adjacent and share one fetch of it through the A collector.
 #pragma unroll
-          for (int part = 0; part < NPART; ++part) {
-            const uint32_t c1b = sbase + SM_C1 + (part == 1 ? C1_PLANE : 0), w0 = sbase + SM_W2 + (part == 2 ? W2_PART : 0);
+          for (int kc = 0; kc < 3; ++kc) {
+            const uint32_t a_tap = c1 - (uint32_t)((2 - kc) * d);
 #pragma unroll
-            for (int kc = 0; kc < 3; ++kc) {
-              const uint32_t a_addr = c1b + (uint32_t)(HALO - (2 - kc) * d) * 16;
-              mma_ss_elect_k4<2 * C1_UNIT / 16>(COL_D13, make_smem_desc_noswz(a_addr, C1_UNIT, 128), make_smem_desc_sw128(w0 + kc * 8192), id64, acc);
-              acc = 1;
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t a_hi = a_tap + ks * (2 * C1_UNIT / 16), b_hi = w2 + ((kc * 8192 + ks * 32) >> 4);
+              if (SPLIT) {
+                mma_ss_lo<A_HI, DESC_HI_SW128, 1>(z + COL_D13, a_hi, b_hi, id64, (kc | ks) != 0, e);
+                mma_ss_lo<A_HI, DESC_HI_SW128, 2>(z + COL_D13, a_hi, b_hi + (W2_PART >> 4), id64, 1u, e);
+                mma_ss_lo<A_HI, DESC_HI_SW128, 0>(z + COL_D13, a_hi + C1_PLANE / 16, b_hi, id64, 1u, e);
+              } else {
+                mma_ss_lo<A_HI, DESC_HI_SW128, 0>(z + COL_D13, a_hi, b_hi, id64, (kc | ks) != 0, e);
+              }
             }
           }
-          mma_commit_elect(&bars[B_D1]);
+          mma_commit_lo(&bars[B_D1], e);
+          CH_STAMP(20);
         }
         // ---- GEMM2: H += LN(ReLU(c2)) W3_b, K = 64, four 64-column groups committed one by one
         mbar_wait_bounded(&bars[B_W3], ph);
         mbar_wait_bounded(&bars[B_A2], ph); tc_fence_after();
+        CH_STAMP(21);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
 #pragma unroll
-          for (int part = 0; part < NPART; ++part) {
-            const uint32_t a0 = part == 1 ? COL_A2_LO : COL_A2_HI, w0 = sbase + SM_W3 + (part == 2 ? W3_PART : 0) + g * 8192;
-            mma_ts_elect_k<4>(COL_H + 64 * g, a0, make_smem_desc_sw128(w0), id64, 1u);
-          }
-          mma_commit_elect(&bars[B_D2 + g]);
+          for (int part = 0; part < NPART; ++part)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma_ts_lo<DESC_HI_SW128>(z + COL_H + 64 * g, z + (part == 1 ? COL_A2_LO : COL_A2_HI) + 8 * ks,
+                                       w3 + (((part == 2 ? W3_PART : 0) + g * 8192 + ks * 32) >> 4), id64, 1u, e);
+          mma_commit_lo(&bars[B_D2 + g], e);
         }
+        CH_STAMP(22);
       }
       mbar_wait_bounded(&bars[B_W1], pw1);      // the end-of-tile aux record: keeps this warp's view of the barrier in step
     } else if (warp == 17) {
@@ -338,12 +378,14 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
         tmem_wait_st();
         if (!has_prev && halo_mine) *reinterpret_cast<uint4*>(halo_dst) = make_uint4(0, 0, 0, 0);      // causal zero padding
       }
-      float sc = 1.0f;      // power-of-two operand scale of the row (see the header)
+      float sc = p.sc0;      // power-of-two operand scale of the row (see the header)
       for (int b = 0; b < nb; ++b, ++it) {
         const uint32_t ph = it & 1u;
-        const float* auxa = reinterpret_cast<const float*>(smem + SM_AUXA + (b & 1) * 768);
+        const float* auxa = reinterpret_cast<const float*>(smem + SM_AUXA + (b & 1) * (AUXA_FLOATS * 4));
+        CH_STAMP(0);
         // ---- P2: r3 = ReLU(H + B3cum_b) * sc -> A3 ring (un-normalised fp16 hi | lo), row sums for the deferred LayerNorm
         mbar_wait_bounded(&bars[B_W1], pw1); pw1 ^= 1u;      // aux record of block b
+        CH_STAMP(1);
         float2 s1v = make_float2(0.0f, 0.0f), s2v = make_float2(0.0f, 0.0f);
         const float2 scv = make_float2(sc, sc);
 #pragma unroll
@@ -351,8 +393,10 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
           const int cc = qd + 4 * i;
           if (b > 0) mbar_wait_bounded(&bars[B_D2 + (cc >> 1)], pd2);      // GEMM2 of the previous block has written these columns
           tc_fence_after();
+          if (i == 0) CH_STAMP(2); else CH_STAMP(6);
           float v[32];
           tmem_ld32(lane_addr + COL_H + 32 * cc, v); tmem_wait_ld();
+          if (i == 0) CH_STAMP(3);
           const float4* bc = reinterpret_cast<const float4*>(sB3 + 32 * cc);
           uint32_t hi[16], lo[16];
 #pragma unroll
@@ -367,10 +411,12 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
             to_h2<SPLIT>(r0.x, r0.y, hi[2 * q], lo[2 * q]);
             to_h2<SPLIT>(r1.x, r1.y, hi[2 * q + 1], lo[2 * q + 1]);
           }
+          if (i == 0) CH_STAMP(4);
           if (i == 1) { mbar_wait_bounded(&bars[B_FREE + qd], ph); tc_fence_after(); }      // the MMAs of chunk qd have read ring slot qd
           tmem_st16(lane_addr + COL_A3 + 32 * qd, hi);
           if (SPLIT) tmem_st16(lane_addr + COL_A3 + 32 * qd + 16, lo);
           tmem_wait_st(); warp_arrive(&bars[B_A3 + cc]);
+          if (i == 0) CH_STAMP(5); else CH_STAMP(7);
         }
         if (b > 0) pd2 ^= 1u;
         float mu3, inv3;
@@ -379,19 +425,22 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
           ln_merge(red + (mrg & 1) * (NSPLIT * TILE), row, qd, 64.0f, m1, fmaxf(s2 - s1 * m1, 0.0f), 1e-6f * sc * sc, mu3, inv3);
           ++mrg;
         }
+        CH_STAMP(8);
         // ---- P3: c1 = LN(ReLU(inv3 (D13 - mu3 colsum(W1)) + b1)) -> shared memory rows 32.., rows 96..127 also to the halo buffer
         mbar_wait_bounded(&bars[B_DEP], ph);
         uint4 hal = make_uint4(0, 0, 0, 0);
         if (has_prev && halo_mine) hal = __ldcg(reinterpret_cast<const uint4*>(halo_in + (size_t)b * 4096));
+        CH_STAMP(9);
         mbar_wait_bounded(&bars[B_D3], ph); tc_fence_after();
+        CH_STAMP(10);
         {
           float a[16];
           tmem_ld16(lane_addr + COL_D13 + 16 * qd, a); tmem_wait_ld();
-          const float nim3 = -inv3 * mu3;
+          const float inv3w = inv3 * auxa[192], nim3 = -inv3w * mu3;      // auxa[192] = 1 / s1: W1 is stored as W1 * s1
           float s = 0.0f;
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            a[k] = relu(fmaf(inv3, a[k], fmaf(nim3, auxa[64 + 16 * qd + k], auxa[16 * qd + k])));
+            a[k] = relu(fmaf(inv3w, a[k], fmaf(nim3, auxa[64 + 16 * qd + k], auxa[16 * qd + k])));
             s += a[k];
           }
           const float mean_i = s * (1.0f / 16.0f);
@@ -401,8 +450,10 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
           float mean, inv;
           ln_merge(red + (mrg & 1) * (NSPLIT * TILE), row, qd, 16.0f, mean_i, q2, 1e-6f, mean, inv);
           ++mrg;
+          CH_STAMP(14);
           const float off = -mean * inv;
           unsigned char* c1w = smem + SM_C1 + (2 * qd) * C1_UNIT + (HALO + row) * 16;
+          uint4 vh[2], vl[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             uint32_t hi[4], lo[4];
@@ -411,28 +462,38 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
               const float x0 = valid ? fmaf(a[8 * e + 2 * k], inv, off) : 0.0f, x1 = valid ? fmaf(a[8 * e + 2 * k + 1], inv, off) : 0.0f;
               to_h2<SPLIT>(x0, x1, hi[k], lo[k]);
             }
-            const uint4 vh = make_uint4(hi[0], hi[1], hi[2], hi[3]), vl = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-            *reinterpret_cast<uint4*>(c1w + e * C1_UNIT) = vh;
-            if (SPLIT) *reinterpret_cast<uint4*>(c1w + C1_PLANE + e * C1_UNIT) = vl;
-            if (has_next && row >= TILE - HALO) {
-              __half* ho = halo_out + (size_t)b * 4096 + ((size_t)(2 * qd + e) * HALO + (row - (TILE - HALO))) * 8;
-              *reinterpret_cast<uint4*>(ho) = vh;
-              if (SPLIT) *reinterpret_cast<uint4*>(ho + 8 * HALO * 8) = vl;
-            }
+            vh[e] = make_uint4(hi[0], hi[1], hi[2], hi[3]); vl[e] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(c1w + e * C1_UNIT) = vh[e];
+            if (SPLIT) *reinterpret_cast<uint4*>(c1w + C1_PLANE + e * C1_UNIT) = vl[e];
           }
           if (has_prev && halo_mine) *reinterpret_cast<uint4*>(halo_dst) = hal;
           fence_proxy_async();      // generic-proxy writes of the c1 tile -> visible to the tensor core's reads
+          CH_STAMP(15);
           warp_arrive(&bars[B_C1]);
-          if (lane == 0) mbar_arrive(&bars[B_PUB]);      // after the __syncwarp of warp_arrive: this warp's halo rows are written
+          // the rows the next tile of the utterance needs travel to the halo record while GEMM1 runs
+          if (has_next && row >= TILE - HALO) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              __half* ho = halo_out + (size_t)b * 4096 + ((size_t)(2 * qd + e) * HALO + (row - (TILE - HALO))) * 8;
+              *reinterpret_cast<uint4*>(ho) = vh[e];
+              if (SPLIT) *reinterpret_cast<uint4*>(ho + 8 * HALO * 8) = vl[e];
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[B_PUB]);      // this warp's halo rows are written
         }
+        CH_STAMP(11);
         // ---- P1: A2 = LN(ReLU(D13 + b2)) as fp16 hi | lo (normalised here: GEMM2 accumulates into H)
         mbar_wait_bounded(&bars[B_D1], ph); tc_fence_after();
+        CH_STAMP(12);
         {
           float a[16];
           tmem_ld16(lane_addr + COL_D13 + 16 * qd, a); tmem_wait_ld();
           float s = 0.0f;
 #pragma unroll
-          for (int k = 0; k < 16; ++k) { a[k] = relu(a[k] + auxa[128 + 16 * qd + k]); s += a[k]; }
+          const float is2 = auxa[193];      // W2 is stored as W2 * s2
+#pragma unroll
+          for (int k = 0; k < 16; ++k) { a[k] = relu(fmaf(a[k], is2, auxa[128 + 16 * qd + k])); s += a[k]; }
           const float mean_i = s * (1.0f / 16.0f);
           float q2 = 0.0f;
 #pragma unroll
@@ -440,6 +501,7 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
           float mean, inv;
           ln_merge(red + (mrg & 1) * (NSPLIT * TILE), row, qd, 16.0f, mean_i, q2, 1e-6f, mean, inv);
           ++mrg;
+          inv *= auxa[194];      // W3 is stored as W3 * s3 and GEMM2 lands in H: the operand carries 1 / s3 (s3 takes half of W3's exponent)
           const float off = -mean * inv;
           uint32_t hi[8], lo[8];
 #pragma unroll
@@ -448,6 +510,7 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
           if (SPLIT) tmem_st8(lane_addr + COL_A2_LO + 8 * qd, lo);
           tmem_wait_st(); warp_arrive(&bars[B_A2]);
         }
+        CH_STAMP(13);
         // operand scale of the next block: the exponent of this block's 1 / std (true scale = inv3 * sc)
         sc = __uint_as_float(__float_as_uint(fminf(fmaxf(inv3 * sc, 1e-30f), 1e30f)) & 0x7F800000u);
       }
@@ -468,8 +531,6 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
         }
       }
       tc_fence_before();
-    } else {
-      it += nb;      // warp 19: idle
     }
     __syncthreads();      // tile end: the next item is known, B3cum / TMEM / the c1 tile are quiescent
     if (warp == 17) {
@@ -518,12 +579,23 @@ int make_weight_map(void* out, const void* dev, int K, size_t rows, int box_rows
   return DXI_OK;
 }
 
-// W [K][N] fp32 (Keras layout flattened) -> [N][K] fp16 hi and lo (K contiguous); colsum over the effective weights.
-static void pack_nk(__half* hi, __half* lo, int N, int K, const float* W, bool split, float* colsum) {
+// Weight range guard: the exact power of two that brings max |W| next to 1 (half = true: next to sqrt(max |W|), for a matrix whose
+// product cannot be rescaled afterwards, so the other half of the exponent goes to the other operand).  The matrices are stored as
+// W * s in fp16 hi | lo and the epilogues multiply by 1 / s, so fp32 weights of any magnitude keep their ~21 significant bits.
+float weight_pow2_scale(const float* W, size_t n, bool half) {
+  float m = 0.0f;
+  for (size_t i = 0; i < n; ++i) m = fmaxf(m, fabsf(W[i]));
+  if (!(m > 1e-30f) || !(m < 1e30f)) return 1.0f;
+  const double e = rint(log2((double)m));
+  return (float)exp2(-(half ? rint(e / 2) : e));
+}
+
+// W [K][N] fp32 (Keras layout flattened) -> [N][K] fp16 hi and lo of W * scale (K contiguous); colsum over the effective weights.
+static void pack_nk(__half* hi, __half* lo, int N, int K, const float* W, bool split, float* colsum, float scale) {
   for (int n = 0; n < N; ++n) {
     double cs = 0.0;
     for (int k = 0; k < K; ++k) {
-      const float w = W[(size_t)k * N + n];
+      const float w = W[(size_t)k * N + n] * scale;
       const __half h = __float2half_rn(w);
       const __half l = __float2half_rn(w - __half2float(h));
       hi[(size_t)n * K + k] = h;
@@ -532,6 +604,17 @@ static void pack_nk(__half* hi, __half* lo, int N, int K, const float* W, bool s
     }
     if (colsum) colsum[n] = (float)cs;
   }
+}
+
+// Power of two next to 1 / rms(gamma) of the first layer's LayerNorm: its output ReLU(LN(z) * gamma) is what the first block's
+// un-normalised operands are made of, so this is their range guard before any row statistic exists.
+float resnet_first_operand_scale(const dxi_net& net) {
+  const std::vector<float>* g = net.host_tensor(1, "gamma");
+  double s2 = 0.0;
+  for (float v : *g) s2 += (double)v * v;
+  const double rms = sqrt(s2 / (double)g->size());
+  if (!(rms > 1e-30) || !(rms < 1e30)) return 1.0f;
+  return (float)exp2(-rint(log2(rms)));
 }
 
 bool resnet_chain_supported(const dxi_net& net) {
@@ -559,9 +642,14 @@ int resnet_chain_prepare(dxi_net& net, cudaStream_t st) {
     for (int k = 0; k < 256; ++k) a[AUX_B3 + k] = (float)b3cum[k];
     if (b == nb) break;
     const int li = 2 + 3 * b;
-    pack_nk(w1 + (size_t)b * 2 * 64 * 256, w1 + ((size_t)b * 2 + 1) * 64 * 256, 64, 256, net.host_tensor(li, "kernel")->data(), split, a + 64);
-    pack_nk(w2 + (size_t)b * 2 * 64 * 192, w2 + ((size_t)b * 2 + 1) * 64 * 192, 64, 192, net.host_tensor(li + 1, "kernel")->data(), split, nullptr);
-    pack_nk(w3 + (size_t)b * 2 * 256 * 64, w3 + ((size_t)b * 2 + 1) * 256 * 64, 256, 64, net.host_tensor(li + 2, "kernel")->data(), split, nullptr);
+    const float* k1 = net.host_tensor(li, "kernel")->data();
+    const float* k2 = net.host_tensor(li + 1, "kernel")->data();
+    const float* k3 = net.host_tensor(li + 2, "kernel")->data();
+    const float s1 = weight_pow2_scale(k1, 256 * 64, false), s2 = weight_pow2_scale(k2, 192 * 64, false), s3 = weight_pow2_scale(k3, 64 * 256, true);
+    pack_nk(w1 + (size_t)b * 2 * 64 * 256, w1 + ((size_t)b * 2 + 1) * 64 * 256, 64, 256, k1, split, a + 64, s1);
+    pack_nk(w2 + (size_t)b * 2 * 64 * 192, w2 + ((size_t)b * 2 + 1) * 64 * 192, 64, 192, k2, split, nullptr, s2);
+    pack_nk(w3 + (size_t)b * 2 * 256 * 64, w3 + ((size_t)b * 2 + 1) * 256 * 64, 256, 64, k3, split, nullptr, s3);
+    a[192] = 1.0f / s1; a[193] = 1.0f / s2; a[194] = 1.0f / s3;
     memcpy(a, net.host_tensor(li, "bias")->data(), 64 * 4);
     memcpy(a + 128, net.host_tensor(li + 1, "bias")->data(), 64 * 4);
     const float* b3 = net.host_tensor(li + 2, "bias")->data();
@@ -602,6 +690,7 @@ int resnet_chain_blocks(const dxi_net& net, float* h, const float2* stem_stats, 
   a.nd = 0;
   for (int m = c.max_d_rate; m > 0; m >>= 1) ++a.nd;
   a.zero = 0;
+  a.sc0 = resnet_first_operand_scale(net);
   const int grid = a.n_items < n_sm ? a.n_items : n_sm;
   CUtensorMap tm[3];
   memcpy(tm, net.chain_tm, sizeof(tm));
@@ -615,3 +704,13 @@ int resnet_chain_blocks(const dxi_net& net, float* h, const float2* stem_stats, 
 }
 
 }  // namespace dxi
+
+#ifdef DXI_ENABLE_DEBUG
+// Tuning build: the epilogue thread 0 and the MMA warp of the CTA that processes work item `item` of subsequent forwards write
+// clock64 stamps into dev_buf (int64 [n_blocks * 32]); nullptr switches it off.
+extern "C" DXI_API int dxi_debug_chain_clocks(long long* dev_buf, int item) {
+  if (cudaMemcpyToSymbol(dxi::g_chain_dbg, &dev_buf, sizeof(dev_buf)) != cudaSuccess) return DXI_E_CUDA;
+  if (cudaMemcpyToSymbol(dxi::g_chain_dbg_item, &item, sizeof(item)) != cudaSuccess) return DXI_E_CUDA;
+  return DXI_OK;
+}
+#endif

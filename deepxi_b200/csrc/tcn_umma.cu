@@ -51,8 +51,8 @@ constexpr int IMG_W2 = 0;                 // [192 -> 64] : 3 K-chunks x [64 rows
 constexpr int IMG_W3 = 24576;             // [ 64 -> 256]: 1 K-chunk  x [256 rows x 128 B]
 constexpr int IMG_W1 = 57344;             // [256 -> 64] : 4 K-chunks x [64 rows x 128 B]
 constexpr int IMG_PART = 90112;           // bytes of one precision part (hi, then lo)
-constexpr int IMG_BIAS = 2 * IMG_PART;    // fp32: b2[64], b3[256], b1'[64], colsum(W3)[256], colsum(W1')[64]
-constexpr int OFF_B2 = 0, OFF_B3 = 64, OFF_B1 = 320, OFF_CS3 = 384, OFF_CS1 = 640, N_AUX = 704;
+constexpr int IMG_BIAS = 2 * IMG_PART;    // fp32: b2[64], b3[256], b1'[64], colsum(W3)[256], colsum(W1')[64], 1/s1, 1/s2, 1/s3 (the matrices are stored as W * s, see weight_pow2_scale)
+constexpr int OFF_B2 = 0, OFF_B3 = 64, OFF_B1 = 320, OFF_CS3 = 384, OFF_CS1 = 640, OFF_IS = 704, N_AUX = 708;      // OFF_IS: 1/s1, 1/s2, 1/s3 (weight scales)
 constexpr int IMG_BYTES = IMG_BIAS + N_AUX * 4;
 
 // TMEM column map
@@ -73,6 +73,9 @@ struct StageArgs {
   int reverse;                   // walk this CTA's tiles last-to-first: consecutive stages alternate, so each starts on what the previous one left in L2
   const float2* stem_stats;     // stage 0 only: per-row partial statistics of the stem pre-activation (8 parts of 32 channels);
                                 // the row is then LayerNorm(gamma) + ReLU'd on load (tcn.py:176-179), gamma in the b3 slot
+  const float* sc_in;           // per-row power-of-two operand scale left by the previous stage (nullptr in stage 0: 1.0)
+  float sc0;                    // stage 0: power of two next to 1 / rms(gamma) of the first layer
+  float* sc_out;                // ... and the one this stage leaves for the next: the exponent of the row's 1 / std (fp16 range guard, see P2)
   int zero;                     // always 0 (see the MMA warp's descriptor arithmetic)
   int wait_val;                 // with flags: a tile of this stage may start once flags[.] >= wait_val for it and its neighbours
   int* flags;                   // flags[tile] = number of stages that have published the tile (zeroed by the host before the stem); nullptr:
@@ -121,7 +124,7 @@ __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
 // LayerNorm statistics of one row split between NSPLIT threads (n values each): every thread contributes
 // (mean_i, M2_i = sum of squared deviations from mean_i); Chan's formula merges them.  Returns mean and
 // 1/sqrt(biased variance + 1e-6) of the whole row.
-__device__ __forceinline__ void ln_merge(float2* red, int row, int qd, float n, float mean_i, float m2_i, float& mean, float& inv) {
+__device__ __forceinline__ void ln_merge(float2* red, int row, int qd, float n, float mean_i, float m2_i, float& mean, float& inv, float eps = 1e-6f) {
   red[qd * TILE + row] = make_float2(mean_i, m2_i);
   quarter_barrier(row >> 5);
   float2 pt[NSPLIT];
@@ -135,7 +138,7 @@ __device__ __forceinline__ void ln_merge(float2* red, int row, int qd, float n, 
 #pragma unroll
   for (int i = 0; i < NSPLIT; ++i) { const float d = pt[i].x - m; m2 += pt[i].y + n * d * d; }
   mean = m;
-  inv = rsqrtf(m2 / (n * NSPLIT) + 1e-6f);
+  inv = rsqrtf(m2 / (n * NSPLIT) + eps);
 }
 
 template <bool SPLIT>
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
         tmem_ld16(lane_addr + COL_D1 + 16 * qd, a); tmem_wait_ld();
         float s = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { a[j] = relu(a[j] + sAux[OFF_B2 + 16 * qd + j]); s += a[j]; }
+        for (int j = 0; j < 16; ++j) { a[j] = relu(fmaf(a[j], sAux[OFF_IS + 1], sAux[OFF_B2 + 16 * qd + j])); s += a[j]; }
         {
           uint32_t hi[8], lo[8];
 #pragma unroll
@@ -395,6 +398,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
 #pragma unroll
         for (int j = 0; j < 16; ++j) { const float d = a[j] - mean_i; q2 = fmaf(d, d, q2); }
         ln_merge(red[0], row, qd, 16.0f, mean_i, q2, mu2, inv2);
+        inv2 *= sAux[OFF_IS + 2];      // W3 is stored as W3 * s3
       }
       DXI_STAMP(3);
       // ---- P2: h_new = h + b3 + inv2 (acc2 - mu2 colsum(W3)); r3 = ReLU(h_new) -> A3 in place, chunk by chunk
@@ -416,6 +420,10 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
       }
       float2 s1v = make_float2(0.0f, 0.0f), s2v = make_float2(0.0f, 0.0f);     // sums of r and r^2 over this thread's 64 channels
       const float nim = -inv2 * mu2;
+      // fp16 range guard: the MMAs consume the UN-normalised ReLU(h) as fp16 hi | lo, so the row is pre-scaled by an exact power of
+      // two taken from its 1 / std one block earlier (the residual stream changes slowly); LayerNorm is scale invariant, the epsilon
+      // is scaled by sc^2, so the result does not change -- but |h| of 1e-4 or 1e5 no longer leaves fp16's normal range.
+      const float sc = !p.has_front ? 1.0f : (p.sc_in ? __ldcg(p.sc_in + (size_t)tile * TILE + row) : p.sc0);
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int cc = qd + 4 * i;
@@ -470,7 +478,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float2 r = make_float2(relu(v[2 * j]), relu(v[2 * j + 1]));
+            const float2 r = __fmul2_rn(make_float2(relu(v[2 * j]), relu(v[2 * j + 1])), make_float2(sc, sc));
             s1v = __fadd2_rn(s1v, r);
             s2v = __ffma2_rn(r, r, s2v);
             to_h2<SPLIT>(r.x, r.y, hi[j], lo[j]);
@@ -485,7 +493,9 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
       float mu3 = 0.0f, inv3 = 0.0f;
       if (p.has_front) {
         const float s1 = s1v.x + s1v.y, s2 = s2v.x + s2v.y, m1 = s1 * (1.0f / 64.0f);
-        ln_merge(red[1], row, qd, 64.0f, m1, fmaxf(s2 - s1 * m1, 0.0f), mu3, inv3);
+        ln_merge(red[1], row, qd, 64.0f, m1, fmaxf(s2 - s1 * m1, 0.0f), mu3, inv3, 1e-6f * sc * sc);
+        if (qd == 0 && p.sc_out)
+          p.sc_out[(size_t)tile * TILE + row] = __uint_as_float(__float_as_uint(fminf(fmaxf(inv3 * sc, 1e-30f), 1e30f)) & 0x7F800000u);
       }
       DXI_STAMP(6);
       // ---- the next tile's c1 taps travel to TMEM while this tile's GEMM3 drains
@@ -500,11 +510,11 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
         float a[16];
         tmem_ld16(lane_addr + COL_D3 + 16 * qd, a); tmem_wait_ld();
         if (has_next) warp_arrive(&bar_a1);      // every D3 read is done: GEMM1 / A2 of the next tile may reuse the columns
-        const float nim3 = -inv3 * mu3;
+        const float inv3w = inv3 * sAux[OFF_IS], nim3 = -inv3w * mu3;      // W1 is stored as W1 * s1
         float s = 0.0f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          a[j] = relu(fmaf(inv3, a[j], fmaf(nim3, sAux[OFF_CS1 + 16 * qd + j], sAux[OFF_B1 + 16 * qd + j])));
+          a[j] = relu(fmaf(inv3w, a[j], fmaf(nim3, sAux[OFF_CS1 + 16 * qd + j], sAux[OFF_B1 + 16 * qd + j])));
           s += a[j];
         }
         const float mean_i = s * (1.0f / 16.0f);
@@ -557,7 +567,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
 // ---------------------------------------------------------------------------------------------------
 constexpr int STEM_PART = 4 * 128 * 128;             // one precision part: 4 K-chunks x [128 rows x 128 B]
 constexpr int STEM_AUX = 2 * STEM_PART;              // fp32: b0[128], W0[256][128 half]
-constexpr int STEM_IMG_BYTES = STEM_AUX + 256 * 4;
+constexpr int STEM_IMG_BYTES = STEM_AUX + 260 * 4;      // b0[128], W0[256][half 128], 1 / s0 (+ pad)
 constexpr int STEM_STAGE_LD = TILE + 1;              // transposed input staging [64 cols][129]
 constexpr int HEAD_W = 4 * 256 * 128;                // hi only: 4 K-chunks x [256 rows x 128 B]
 constexpr int HEAD_IMG_BYTES = HEAD_W + (260 + 256) * 4;   // fp32: bo[257 (+3 pad)], Wo[:, 256]
@@ -663,7 +673,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) stem_umma_kernel(const StemA
       float s = 0.0f;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        z[j] = valid ? z[j] + fmaf(x256, sAux[128 + 32 * qd + j], sAux[32 * qd + j]) : 0.0f;
+        z[j] = valid ? fmaf(z[j], sAux[256], fmaf(x256, sAux[128 + 32 * qd + j], sAux[32 * qd + j])) : 0.0f;      // sAux[256] = 1 / s0
         s += z[j];
       }
       const float mean_i = s * (1.0f / 32.0f);
@@ -694,7 +704,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) head_umma_kernel(const HeadA
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar_w, bar_a, bar_d[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float dot[NSPLIT * TILE];
+  __shared__ float dot[NSPLIT * TILE], rmax[NSPLIT * TILE];
   unsigned char* sW = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const float* sBias = reinterpret_cast<const float*>(sW + HEAD_W);          // [260]
   const float* sLast = sBias + 260;                                           // Wo[:, 256]
@@ -756,21 +766,32 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) head_umma_kernel(const HeadA
       const int t = t0 + row;
       const bool valid = t < p.T;
       const float* hrow = p.h + (size_t)tile * (TILE * 256) + row * 4 + (size_t)(16 * qd) * (TILE * 4);
-      // ---- A operand: h (raw residual sum, tcn.py:158-159) as fp16 hi | lo; column 256 as an fp32 dot product
+      // ---- A operand: h (raw residual sum, tcn.py:158-159) as fp16 hi | lo; column 256 as an fp32 dot product.
+      // fp16 range guard: the row is scaled by an exact power of two that brings its largest magnitude into [1, 2) before the
+      // split and the accumulator is scaled back, so a residual stream of 1e-4 or 1e5 neither underflows nor overflows fp16.
+      float4 hv[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) hv[q] = *reinterpret_cast<const float4*>(hrow + (size_t)q * (TILE * 4));
+      float mx = 0.0f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) mx = fmaxf(fmaxf(mx, fmaxf(fabsf(hv[q].x), fabsf(hv[q].y))), fmaxf(fabsf(hv[q].z), fabsf(hv[q].w)));
+      rmax[qd * TILE + row] = mx;
+      epi_barrier();
+      mx = fmaxf(fmaxf(rmax[row], rmax[TILE + row]), fmaxf(rmax[2 * TILE + row], rmax[3 * TILE + row]));
+      const uint32_t ex = min(max((__float_as_uint(mx) >> 23) & 0xFFu, 1u), 253u);      // biased exponent of the row maximum (1 if the row is zero)
+      const float sc = __uint_as_float((254u - ex) << 23), isc = __uint_as_float(ex << 23) * sBias[257];      // 2^-(ex-127); its inverse times 1 / s_o (Wo is stored as Wo * s_o)
       float d256 = 0.0f;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        float4 hv[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) hv[q] = *reinterpret_cast<const float4*>(hrow + (size_t)(4 * g + q) * (TILE * 4));
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+          const float4 h4 = hv[4 * g + q];
           const float* wl = sLast + 64 * qd + 16 * g + 4 * q;
-          d256 = fmaf(hv[q].x, wl[0], d256); d256 = fmaf(hv[q].y, wl[1], d256);
-          d256 = fmaf(hv[q].z, wl[2], d256); d256 = fmaf(hv[q].w, wl[3], d256);
-          split_h2(hv[q].x, hv[q].y, hi[2 * q], lo[2 * q]);
-          split_h2(hv[q].z, hv[q].w, hi[2 * q + 1], lo[2 * q + 1]);
+          d256 = fmaf(h4.x, wl[0], d256); d256 = fmaf(h4.y, wl[1], d256);
+          d256 = fmaf(h4.z, wl[2], d256); d256 = fmaf(h4.w, wl[3], d256);
+          split_h2(h4.x * sc, h4.y * sc, hi[2 * q], lo[2 * q]);
+          split_h2(h4.z * sc, h4.w * sc, hi[2 * q + 1], lo[2 * q + 1]);
         }
         tmem_st8(lane_addr + COL_A_HI + 32 * qd + 8 * g, hi);
         tmem_st8(lane_addr + COL_A_LO + 32 * qd + 8 * g, lo);
@@ -792,7 +813,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) head_umma_kernel(const HeadA
         tc_fence_before();
         float* st = stage + ((size_t)qd * TILE + row) * HEAD_STAGE_LD;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) st[j] = 1.0f / (1.0f + expf(-(z[j] + sBias[128 * nh + 32 * qd + j])));
+        for (int j = 0; j < 32; ++j) st[j] = 1.0f / (1.0f + expf(-fmaf(z[j], isc, sBias[128 * nh + 32 * qd + j])));
         epi_barrier();
         for (int i = tid; i < TILE * 128; i += EPI_THREADS) {
           const int r = i >> 7, c = i & 127;
@@ -814,13 +835,13 @@ __global__ void __launch_bounds__(STAGE_THREADS, 1) head_umma_kernel(const HeadA
 // Packs W [K][N] (fp32) as fp16 hi / lo UMMA B images and returns the column sums of the EFFECTIVE weights
 // (hi, or hi + lo) in colsum[N]: that is what the deferred normalisation has to subtract.
 static void pack_b_sw128(unsigned char* hi, unsigned char* lo, int N, int K, const float* W /* [K][N] */, bool split,
-                         float* colsum) {
+                         float* colsum, float scale = 1.0f) {
   std::vector<double> cs(N, 0.0);
   for (int n = 0; n < N; ++n)
     for (int k = 0; k < K; ++k) {
       const int c = k >> 6, kk = k & 63, u = kk >> 3, e = kk & 7;
       const size_t off = (size_t)c * N * 128 + (size_t)(n >> 3) * 1024 + (n & 7) * 128 + ((u ^ (n & 7)) * 16) + e * 2;
-      const float w = W[(size_t)k * N + n];
+      const float w = W[(size_t)k * N + n] * scale;
       const __half h = __float2half_rn(w);
       const __half l = __float2half_rn(w - __half2float(h));
       memcpy(hi + off, &h, 2);
@@ -847,14 +868,21 @@ int resnet_umma_prepare(dxi_net& net, cudaStream_t st) {
     const bool split = c.precision == DXI_PREC_F16X3;
     if (s >= 1) {
       const int li = 2 + 3 * (s - 1);
-      pack_b_sw128(base + IMG_W2, base + IMG_PART + IMG_W2, 64, 192, net.host_tensor(li + 1, "kernel")->data(), split, nullptr);        // [3*64][64]
-      pack_b_sw128(base + IMG_W3, base + IMG_PART + IMG_W3, 256, 64, net.host_tensor(li + 2, "kernel")->data(), split, aux + OFF_CS3);  // [64][256]
+      const float* k2 = net.host_tensor(li + 1, "kernel")->data();
+      const float* k3 = net.host_tensor(li + 2, "kernel")->data();
+      const float s2 = weight_pow2_scale(k2, 192 * 64, false), s3 = weight_pow2_scale(k3, 64 * 256, false);
+      pack_b_sw128(base + IMG_W2, base + IMG_PART + IMG_W2, 64, 192, k2, split, nullptr, s2);        // [3*64][64]
+      pack_b_sw128(base + IMG_W3, base + IMG_PART + IMG_W3, 256, 64, k3, split, aux + OFF_CS3, s3);  // [64][256]
+      aux[OFF_IS + 1] = 1.0f / s2; aux[OFF_IS + 2] = 1.0f / s3;
       memcpy(aux + OFF_B2, net.host_tensor(li + 1, "bias")->data(), 64 * 4);
       memcpy(aux + OFF_B3, net.host_tensor(li + 2, "bias")->data(), 256 * 4);
     }
     if (s < c.n_blocks) {
       const int li = 2 + 3 * s;
-      pack_b_sw128(base + IMG_W1, base + IMG_PART + IMG_W1, 64, 256, net.host_tensor(li, "kernel")->data(), split, aux + OFF_CS1);      // [256][64]
+      const float* k1 = net.host_tensor(li, "kernel")->data();
+      const float s1 = weight_pow2_scale(k1, 256 * 64, false);
+      pack_b_sw128(base + IMG_W1, base + IMG_PART + IMG_W1, 64, 256, k1, split, aux + OFF_CS1, s1);      // [256][64]
+      aux[OFF_IS] = 1.0f / s1;
       memcpy(aux + OFF_B1, net.host_tensor(li, "bias")->data(), 64 * 4);
     }
   }
@@ -870,9 +898,11 @@ int resnet_umma_prepare(dxi_net& net, cudaStream_t st) {
       unsigned char* base = img.data() + off_stem + half * stem_stride;
       for (int k = 0; k < 256; ++k)
         for (int n = 0; n < 128; ++n) sub[(size_t)k * 128 + n] = W0[(size_t)k * 256 + 128 * half + n];
-      pack_b_sw128(base, base + STEM_PART, 128, 256, sub.data(), true, nullptr);
+      const float s0 = weight_pow2_scale(W0, (size_t)256 * 256, false);
+      pack_b_sw128(base, base + STEM_PART, 128, 256, sub.data(), true, nullptr, s0);
       float* aux = reinterpret_cast<float*>(base + STEM_AUX);
       for (int n = 0; n < 128; ++n) { aux[n] = b0[128 * half + n]; aux[128 + n] = W0[(size_t)256 * 256 + 128 * half + n]; }
+      aux[256] = 1.0f / s0;
     }
     // stage 0 applies the stem's LayerNorm scale: gamma rides in its (otherwise unused) b3 slot
     memcpy(reinterpret_cast<float*>(img.data() + IMG_BIAS) + OFF_B3, net.host_tensor(1, "gamma")->data(), 256 * 4);
@@ -884,9 +914,11 @@ int resnet_umma_prepare(dxi_net& net, cudaStream_t st) {
     for (int k = 0; k < 256; ++k)
       for (int n = 0; n < 256; ++n) sq[(size_t)k * 256 + n] = Wo[(size_t)k * 257 + n];
     unsigned char* hb = img.data() + off_head;
-    pack_b_sw128(hb, scratch.data(), 256, 256, sq.data(), false, nullptr);
+    const float so = weight_pow2_scale(sq.data(), sq.size(), false);
+    pack_b_sw128(hb, scratch.data(), 256, 256, sq.data(), false, nullptr, so);
     float* aux = reinterpret_cast<float*>(hb + HEAD_W);
     for (int n = 0; n < 257; ++n) aux[n] = bo[n];
+    aux[257] = 1.0f / so;
     for (int k = 0; k < 256; ++k) aux[260 + k] = Wo[(size_t)k * 257 + 256];
   }
   net.umma_stage_offset = {off_stem, off_stem + stem_stride, off_head};
@@ -910,7 +942,8 @@ int64_t resnet_umma_workspace_bytes(const dxi_net& net, int B, int T) {
   const size_t c1_bytes = align_up((size_t)B * 2 * 8 * Ts * 16, 256);
   const size_t stats_bytes = (size_t)B * tiles * TILE * 8 * sizeof(float2);
   const size_t flag_bytes = align_up((size_t)B * tiles * sizeof(int), 256);
-  const size_t chain_bytes = resnet_chain_supported(net) ? 256 + resnet_chain_extra_workspace(net, B, tiles) : 0;
+  // behind the stem statistics: the depth-first path's flags / halo records, or the stage-per-launch path's per-row operand scales
+  const size_t chain_bytes = 256 + (resnet_chain_supported(net) ? resnet_chain_extra_workspace(net, B, tiles) : 2 * (size_t)B * tiles * TILE * sizeof(float));
   return (int64_t)(256 + h_bytes + 2 * c1_bytes + flag_bytes + stats_bytes + chain_bytes);
 }
 
@@ -981,6 +1014,10 @@ static int resnet_umma_group(const dxi_net& net, const float* mag, int B, int T,
     a.dbg_cta = (dbg && g_dbg_stage == 255 && g_dbg_clocks) ? g_dbg_clocks + (size_t)s * grid * 8 : nullptr;      // stage 255: CTA timelines of all stages
     a.dbg_flags = g_dbg_flags;
     a.flags = (no_flags || (dbg && g_dbg_stop_after >= 0)) ? nullptr : flags;
+    float* row_scale = reinterpret_cast<float*>(chain_ws);      // [2][n_tiles * 128], alternating between stages
+    a.sc_in = s >= 1 ? row_scale + (size_t)((s + 1) & 1) * n_tiles * TILE : nullptr;
+    a.sc_out = row_scale + (size_t)(s & 1) * n_tiles * TILE;
+    a.sc0 = resnet_first_operand_scale(net);
     a.wait_val = s;               // stage s-1 has published a tile when its counter reaches s
     const int d = s >= 1 ? 1 << ((s - 1) % nd) : 1;
     if (c.padding == DXI_PAD_CAUSAL) { a.shift0 = 2 * d; a.shift1 = d; a.shift2 = 0; }       // tap j reads t-(2-j)d

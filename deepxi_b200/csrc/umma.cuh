@@ -250,6 +250,53 @@ __device__ __forceinline__ void mma_ss_elect_k4(uint32_t tmem_d, uint64_t adesc,
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "n"(A_STEP), "n"(2 * A_STEP), "n"(3 * A_STEP)
       : "memory");
 }
+// ---- issue path with the election hoisted and 32-bit descriptor words ---------------------------------------------------
+// A kernel whose MMA warp issues many small (N = 64) MMAs is bound by that warp's instruction stream, not by the tensor pipe:
+// with 64-bit descriptors formed per MMA ptxas emits ~13 SASS instructions per UTCHMMA (64-bit adds in vector registers, R2UR
+// moves, a VOTEU per election).  Here the leader is elected ONCE (`e` = elect_leader(), non-zero in one lane), the high descriptor
+// word is a compile-time constant and the low word is base + immediate, which ptxas keeps in uniform registers (UIADD3): 3-5
+// instructions per UTCHMMA.  All lanes execute the calls convergently; only the leader issues.
+__device__ __forceinline__ uint32_t elect_leader() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(pred));
+  return pred;
+}
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO 1024, version 1, SWIZZLE_128B
+__host__ __device__ constexpr uint32_t desc_hi_noswz(uint32_t sbo) { return (sbo >> 4) | (1u << 14); }
+// low descriptor word of a 128-byte-swizzled operand at shared address `a` (LBO field 1) / of a no-swizzle operand
+__device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t a) { return ((a & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_lo_noswz(uint32_t a, uint32_t lbo) { return ((a & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16); }
+template <uint32_t B_HI>
+__device__ __forceinline__ void mma_ts_lo(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t idesc, uint32_t accumulate, uint32_t e) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 bd;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\tmov.b64 bd, {%2, %6};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(e), "n"(B_HI)
+      : "memory");
+}
+// COLL: use of the A collector buffer.  0 = default (A is fetched and discarded), 1 = fill (fetched and kept for the next MMA),
+// 2 = lastuse (the A operand the previous MMA kept is reused, not fetched again): two adjacent MMAs with the same A operand read
+// it from shared memory once, which is what bounds an SS-mode N = 64 MMA (4 KB of A + 2 KB of B per 32 tensor cycles).
+template <uint32_t A_HI, uint32_t B_HI, int COLL = 0>
+__device__ __forceinline__ void mma_ss_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate, uint32_t e) {
+#define DXI_MMA_SS_LO(MOD)                                                                                                              \
+  asm volatile(                                                                                                                         \
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 ad, bd;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"                                 \
+      "mov.b64 ad, {%1, %6};\n\tmov.b64 bd, {%2, %7};\n\t"                                                                              \
+      "@q tcgen05.mma.cta_group::1.kind::f16" MOD " [%0], ad, bd, %3, p;\n\t}" ::"r"(tmem_d),                                             \
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(e), "n"(A_HI), "n"(B_HI)                                                   \
+      : "memory")
+  if (COLL == 1) DXI_MMA_SS_LO(".collector::a::fill");
+  else if (COLL == 2) DXI_MMA_SS_LO(".collector::a::lastuse");
+  else DXI_MMA_SS_LO("");
+#undef DXI_MMA_SS_LO
+}
+__device__ __forceinline__ void mma_commit_lo(uint64_t* bar, uint32_t e) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)), "r"(e)
+      : "memory");
+}
 __device__ __forceinline__ void mma_ss_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"

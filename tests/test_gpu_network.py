@@ -336,6 +336,31 @@ def test_infer_loads_a_written_checkpoint(tmp_path):
     assert np.array_equal(ya, y2.cpu().numpy()[0, :(nfr[0] + 1) * 256])
 
 
+def test_depth_first_and_stage_per_launch_paths_agree(tmp_path, xi_stats):
+    """padding='causal' runs the depth-first kernel (tcn_chain.cu: residual tile resident in tensor memory, GEMM2 accumulating into
+    it); DXI_TCN_STAGED=1 (read once per process) selects the stage-per-launch kernel on the same weights.  Two formulations of the
+    same arithmetic: they must agree far inside the 0.1 dB budget on a batch with several rounds of work items and ragged lengths."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mu, sg = xi_stats['resnet-1.1c/mu'], xi_stats['resnet-1.1c/sigma']
+    outs = []
+    for staged in (False, True):
+        env = dict(os.environ)
+        env.pop('DXI_TCN_STAGED', None)
+        if staged:
+            env['DXI_TCN_STAGED'] = '1'
+        f = str(tmp_path / ('staged.npy' if staged else 'chain.npy'))
+        r = subprocess.run([sys.executable, os.path.join(root, 'scripts', 'flags_check.py'), f, '40', '100000', 'causal'], env=env,
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(np.load(f))
+    a = cdfmap.normal_cdf_inverse_db(outs[0].astype(np.float64), mu, sg)
+    b = cdfmap.normal_cdf_inverse_db(outs[1].astype(np.float64), mu, sg)
+    m = np.isfinite(a) & np.isfinite(b) & (np.abs(b) < 40)
+    d = np.abs(a - b)[m]
+    assert np.median(d) < 5e-3 and d.max() < 5e-2, (np.median(d), d.max())
+
+
 def test_tile_level_stage_dependencies_are_bit_exact(tmp_path):
     """The stage launches of the tcgen05 ResNetV2 path are chained by per-tile flags; with DXI_TCN_NO_FLAGS=1 every
     stage waits for its whole predecessor instead.  The switch is read once per process, so each mode runs in its own process
@@ -348,6 +373,7 @@ def test_tile_level_stage_dependencies_are_bit_exact(tmp_path):
         for mode in ('flags', 'noflags'):
             env = dict(os.environ)
             env.pop('DXI_TCN_NO_FLAGS', None)
+            env['DXI_TCN_STAGED'] = '1'          # 'causal' otherwise takes the depth-first kernel (tcn_chain.cu), which has no stage launches
             if mode == 'noflags':
                 env['DXI_TCN_NO_FLAGS'] = '1'
             f = str(tmp_path / ('%s_%s.npy' % (pad, mode)))
