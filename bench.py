@@ -12,9 +12,13 @@ shards them with no collective on the data path ("weak" scaling: 256 utterances 
 
 Prints ONE JSON line (rank 0).  `value`: device-resident inputs, CUDA-event timed, max over ranks.
 `e2e`: the same metric through the public API (DeepXi.infer_batch) with pinned HOST buffers, H2D and
-D2H copies inside the timed region.  `roofline`: the dominant kernel (tcn_stage_kernel, tcgen05) against
-the measured bf16 peak of MEASURED_PEAKS.json.  `cpu_baseline`: the oracle (CPU restatement of the
-reference path; TensorFlow cannot be installed here) on a bounded sample, all host cores.
+D2H copies inside the timed region; `e2e.pcie_ceiling_gbs` is a duplex pinned-copy measurement taken by all ranks at
+once inside the run, `e2e.frac_of_pcie_bound` the e2e rate against the bound that ceiling implies.  `roofline`: the
+dominant kernel (tcn_chain_kernel: the 40 residual blocks, tcgen05 / TMEM) against the measured bf16 peak of
+MEASURED_PEAKS.json.  `configs`: the other BASELINE.json configs measured in the same run (C1 latency, C3 MHANet,
+the 1024-utterance shard of C5) and `sustained`: the same step looped for >= 3 s with its clock record.
+`cpu_baseline`: the oracle (CPU restatement of the reference path; TensorFlow cannot be installed here) on a
+bounded sample, all host cores.
 """
 import argparse
 import json
@@ -36,8 +40,14 @@ UTTS_PER_GPU = 256
 FLOP_PER_FRAME_STAGES = 40 * 2 * (256 * 64 + 3 * 64 * 64 + 64 * 256)     # the 40 residual blocks (tensor cores)
 FLOP_PER_FRAME_TOTAL = 3867648                                           # whole ResNetV2
 STFT_BYTES_PER_FRAME = 512 + 2 * 257 * 4                                 # int16 in, mag + phase out
-TCN_STAGE_BYTES_PER_FRAME = 2 * 1024 + 256 + 256                         # per stage: h read + write (fp32), c1 write, c1 read (once)
-NCU_TCN_STAGE_TRAFFIC = 385.43e6      # dram__bytes_read.sum + dram__bytes_write.sum of one tcn_stage_kernel<true> launch (231.75 + 153.68 MB), profiles/r01_prof_tcn_stage_final.csv
+# tcn_chain_kernel, algorithmic HBM bytes per frame: stem pre-activation in (1024) + its row statistics (64) + residual sum out (1024)
+# + per block the 32 halo rows of c1 (fp16 hi + lo) a tile writes for, and reads from, its neighbour in the utterance (2 x 8 KB per
+# 128 frames = 128 B per frame and block).  The fp32 residual stream itself never leaves the SM.
+TCN_CHAIN_BYTES_PER_FRAME = 1024 + 64 + 1024 + 40 * 128
+# dram__bytes_read.sum + dram__bytes_write.sum of the one tcn_chain_kernel<true> launch of this workload, from the committed
+# ncu --set full capture (profiles/r02_prof_tcn_chain.csv); a citation, NOT measured in the run
+NCU_TCN_CHAIN_TRAFFIC = None
+MHA_KW = dict(d_model=256, n_blocks=5, n_heads=8, warmup_steps=40000, max_len=2048, causal=1, outp_act='Sigmoid')
 RES_KW = dict(d_model=256, n_blocks=40, d_f=64, k=3, max_d_rate=16, unit_type='ReLU->LN->W+b', outp_act='Sigmoid')
 
 
@@ -46,8 +56,8 @@ def measured_peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return d.get('hbm_gbs', 6650.0), d.get('bf16_tflops_sustained', d.get('bf16_tflops', 1590.0)), 'measured'
-    return 6650.0, 1590.0, 'fallback'
+        return d.get('hbm_gbs', 6650.0), d.get('bf16_tflops', 1590.0), d.get('bf16_tflops_sustained', d.get('bf16_tflops', 1590.0)), 'measured'
+    return 6650.0, 1590.0, 1590.0, 'fallback'
 
 
 class ClockSampler:
@@ -78,31 +88,41 @@ class ClockSampler:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.05)
         self.proc.terminate()
-        inside = [ln for t, ln in self.lines if any(a <= t <= b + 0.01 for a, b in windows)]
-        window = 'timed regions (device-timed steps + e2e steps)'
+        return self.summarise(self.lines, windows)
+
+    @staticmethod
+    def summarise(lines, windows):
+        inside = [ln for t, ln in lines if any(a <= t <= b + 0.01 for a, b in windows)]
+        window = 'timed regions'
         if not inside:      # a timed region shorter than one sampling period: the samples of the same load just around it
             lo = min((a for a, _ in windows), default=0.0) - 0.5
-            inside = [ln for t, ln in self.lines if t >= lo]
+            hi = max((b for _, b in windows), default=0.0) + 0.05
+            inside = [ln for t, ln in lines if lo <= t <= hi]
             window = 'no sample fell inside the timed regions: samples from 0.5 s before them (warm-up steps, same load) to their end'
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for ln in inside:
             f = [x.strip() for x in ln.split(',')]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
                 if v.lower().startswith('active'):
                     reasons.add(name)
         busy = [s for s in sm if s > 0]
-        return {'sm_mhz': float(np.median(busy)) if busy else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': sorted(reasons), 'samples': len(sm), 'window': window}
+        return {'sm_mhz': float(np.median(busy)) if busy else None, 'sm_min_mhz': min(busy) if busy else None, 'sm_max_mhz': max(mx) if mx else None,
+                'power_w_max': max(pw) if pw else None, 'reasons': sorted(reasons), 'samples': len(sm), 'window': window}
+
+
+WORKLOAD = ('ResNet-1.1c (ResNetV2 40 blocks causal, random-init weights of the checkpoint shapes) + MMSE-LSA, %d utt x %d s '
+            '@16 kHz per GPU, STFT 512/256, int16 waveform in -> enhanced waveform out')
 
 
 def run_reference(args, rank, world):
-    """CPU arm: the oracle port of the reference path on this box's host cores (rank 0 only)."""
+    """CPU arm: the oracle port of the reference path on this box's host cores (rank 0 only).  The metric is a rate (audio
+    seconds per second), so each step times a BOUNDED SAMPLE of the workload: `config.sample` says how many utterances."""
     if rank != 0:
         return
     import torch
@@ -122,13 +142,14 @@ def run_reference(args, rank, world):
         pipeline.infer(x, lens, w, mu, sigma, out_type='y', gtype='mmse-lsa')
     dt = (time.perf_counter() - t0) / args.steps
     v = n_utt * SECONDS / dt
-    sample = '%d x %d s utterances per step (ResNet-1.1c + MMSE-LSA, y out)' % (n_utt, SECONDS)
+    sample = ('%d of the %d utterances x %d s per step (the oracle is a per-utterance loop: its rate does not depend on the batch '
+              'size); ResNet-1.1c + MMSE-LSA, int16 in -> waveform out' % (n_utt, args.utts, SECONDS))
     line = {'impl': 'reference', 'metric': 'audio-seconds enhanced per second (ResNet-1.1c, MMSE-LSA)', 'value': v,
             'unit': 'audio-s/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'ResNet-1.1c + MMSE-LSA, %d utt x %d s @16 kHz per GPU, STFT 512/256, int16 in -> wav out'
-                                   % (UTTS_PER_GPU, SECONDS), 'arm': 'CPU restatement of the reference path (oracle/, numpy + '
-                       'torch-CPU + scipy); the TF2 reference cannot be installed or imported here'},
+            'config': {'workload': WORKLOAD % (args.utts, SECONDS), 'sample': sample, 'utterances_timed_per_step': n_utt,
+                       'arm': 'CPU restatement of the reference path (oracle/, numpy + torch-CPU + scipy); the TF2 reference cannot '
+                              'be installed or imported here'},
             'cpu_baseline': {'value': v, 'unit': 'audio-s/s', 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': v, 'unit': 'audio-s/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -162,7 +183,7 @@ def cpu_baseline(n_utt=8):
 def bind_to_gpu_numa_node(local_rank):
     """Pins this process (and therefore the pinned host buffers it allocates next: first touch) to the CPUs of the NUMA node
     the GPU hangs off, so that the e2e arm's host<->device copies of the N ranks do not cross the socket interconnect.
-    Best effort: returns a short description, or None when the topology cannot be read."""
+    Best effort: returns a short description of what was done or why nothing could be."""
     try:
         import torch
         pr = torch.cuda.get_device_properties(local_rank)
@@ -170,7 +191,7 @@ def bind_to_gpu_numa_node(local_rank):
         with open('/sys/bus/pci/devices/%s/numa_node' % bdf) as f:
             node = int(f.read().strip())
         if node < 0:
-            return None
+            return 'not bound: the VM reports no NUMA node for GPU %s' % bdf
         with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
             cpus = set()
             for part in f.read().strip().split(','):
@@ -178,11 +199,42 @@ def bind_to_gpu_numa_node(local_rank):
                 cpus.update(range(int(lo), int(hi or lo) + 1))
         cpus &= os.sched_getaffinity(0)
         if not cpus:
-            return None
+            return 'not bound: no allowed cpu on numa node %d' % node
         os.sched_setaffinity(0, cpus)
         return 'numa node %d (%d cpus)' % (node, len(cpus))
-    except Exception:
-        return None
+    except Exception as e:
+        return 'not bound: %s' % type(e).__name__
+
+
+def pcie_ceiling(torch, x_host, y_host, dev, barrier, seconds=0.2):
+    """Duplex pinned-copy rate of this rank while ALL ranks copy at once: the same two buffers the e2e arm moves, H2D on one
+    stream and D2H on another, back to back for `seconds`.  Returns (h2d GB/s, d2h GB/s)."""
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    xd = torch.empty_like(x_host, device=dev)
+    yd = torch.empty_like(y_host, device=dev)
+    for _ in range(2):
+        with torch.cuda.stream(s_in):
+            xd.copy_(x_host, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            y_host.copy_(yd, non_blocking=True)
+    torch.cuda.synchronize()
+    barrier()
+    n = 0
+    a0, a1, b0, b1 = (torch.cuda.Event(enable_timing=True) for _ in range(4))
+    a0.record(s_in); b0.record(s_out)
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(4):
+            with torch.cuda.stream(s_in):
+                xd.copy_(x_host, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                y_host.copy_(yd, non_blocking=True)
+        n += 4
+        s_in.synchronize(); s_out.synchronize()
+    a1.record(s_in); b1.record(s_out)
+    torch.cuda.synchronize()
+    return (n * x_host.numel() * x_host.element_size() / (a0.elapsed_time(a1) * 1e-3) / 1e9,
+            n * y_host.numel() * y_host.element_size() / (b0.elapsed_time(b1) * 1e-3) / 1e9)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -193,7 +245,7 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
-    numa = bind_to_gpu_numa_node(local_rank) if not os.environ.get('DXI_BENCH_NO_NUMA') else None
+    numa = bind_to_gpu_numa_node(local_rank) if not os.environ.get('DXI_BENCH_NO_NUMA') else 'not bound: DXI_BENCH_NO_NUMA'
     if world > 1 and not dist.is_initialized():
         # NCCL prints a version banner on stdout when the communicator is created; stdout must carry exactly
         # ONE JSON line, so fd 1 points at stderr until the first collective has run.
@@ -224,6 +276,7 @@ def run_ours(args, rank, world, local_rank):
     lens = [L] * B
     x_dev = [x_host.to(dev), x_host.to(dev).roll(1, 0)]          # two input buffers, alternated
     it = dx.inp_tgt
+    KEYS = ('stft', 'tcn_chain', 'tcn_stage', 'tcn_stem', 'tcn_head', 'enhance')
 
     def step(i):
         inp, pha, nfr = it.observation_batch(x_dev[i & 1], lens)
@@ -237,7 +290,7 @@ def run_ours(args, rank, world, local_rank):
         y = step(i)
     torch.cuda.synchronize()
     _lib.profile_enable(True)
-    for k in ('stft', 'tcn_stage', 'tcn_stem', 'tcn_head', 'enhance'):
+    for k in KEYS:
         _lib.profile_read(k)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(); torch.cuda.synchronize()
@@ -252,7 +305,7 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     launches = _lib.launch_count()
     ms = e0.elapsed_time(e1)
-    prof = {k: _lib.profile_read(k) for k in ('stft', 'tcn_stage', 'tcn_stem', 'tcn_head', 'enhance')}
+    prof = {k: _lib.profile_read(k) for k in KEYS}
     _lib.profile_enable(False)
     assert torch.isfinite(y).all(), 'non-finite samples in the enhanced waveform'
 
@@ -275,36 +328,68 @@ def run_ours(args, rank, world, local_rank):
     pipe.drain()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop([(win_dev0, win_dev1), (win_e2e0, time.time())]) if rank == 0 else None
+    win_e2e1 = time.time()
     if os.environ.get('DXI_BENCH_DEBUG'):
         sys.stderr.write('rank %d e2e submit marks %s total %.4f\n' % (rank, ['%.4f' % m for m in marks], e2e_s))
     barrier()
     assert int(y_hosts[0].abs().max()) > 0
+    # ---- what the host <-> device links of this box give when every rank copies at once (the e2e arm's ceiling)
+    h2d_gbs, d2h_gbs = pcie_ceiling(torch, x_host, y_hosts[0], dev, barrier)
+    barrier()
 
-    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # ---- sustained: the same device-resident step looped for >= 3 s (the 10-step region above is a burst of ~30 ms)
+    sustained = None
+    win_sus = None
+    if not args.no_sustained:
+        n_sus = max(args.steps, int(args.sustain_seconds / max(ms / args.steps * 1e-3, 1e-4)) + 1)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier(); torch.cuda.synchronize()
+        ws0 = time.time()
+        s0.record()
+        for i in range(n_sus):
+            y = step(i)
+        s1.record()
+        torch.cuda.synchronize()
+        win_sus = (ws0, time.time())
+        sustained = (n_sus, s0.elapsed_time(s1))
+        barrier()
+
+    t = torch.tensor([ms, e2e_s * 1e3, -h2d_gbs, -d2h_gbs, sustained[1] if sustained else 0.0], dtype=torch.float64, device=dev)
+    tsum = torch.tensor([h2d_gbs, d2h_gbs], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    ms, e2e_ms, h2d_min, d2h_min, sus_ms = float(t[0]), float(t[1]), -float(t[2]), -float(t[3]), float(t[4])
+
+    # ---- the other BASELINE.json configs, in the same run (single-GPU runs only: they are per-GPU figures)
+    configs = extra_configs(torch, dx, it, dev, args) if (world == 1 and not args.no_extra_configs) else None
+    clocks = None
+    if rank == 0:
+        clocks = sampler.stop([(win_dev0, win_dev1), (win_e2e0, win_e2e1)])
+        if win_sus:
+            clocks_sus = ClockSampler.summarise(sampler.lines, [win_sus])
     if rank != 0:
         return
     audio_s = world * B * SECONDS
     value = audio_s * args.steps / (ms / 1e3)
-    hbm_peak, tf_peak, peak_src = measured_peaks()
+    hbm_peak, tf_burst, tf_sustained, peak_src = measured_peaks()
     frames = B * T
-    st_ms, st_n = prof['tcn_stage']
+    chain = prof['tcn_chain'][1] > 0
+    st_ms, st_n = prof['tcn_chain'] if chain else prof['tcn_stage']
     st_ms_per_launch = st_ms / max(st_n, 1)
-    st_per_step = st_n / max(args.steps, 1)          # 41 (one launch per stage) or the number of utterance groups (chained kernel)
+    st_per_step = st_n / max(args.steps, 1)          # 1 (depth-first kernel) or 41 (one launch per stage)
     flops_per_launch = frames * FLOP_PER_FRAME_STAGES / max(st_per_step, 1)
     achieved_tf = flops_per_launch / (st_ms_per_launch * 1e-3) / 1e12 if st_n else None
-    # the same launches seen from the memory side: per frame and stage the residual stream is read and written (2 x 1 KB fp32) and
-    # c1 is written once (fp16 hi + lo, 256 B) and fetched from HBM once (256 B; its other two taps are L2 hits)
-    st_bytes_per_launch = frames * TCN_STAGE_BYTES_PER_FRAME * 41.0 / max(st_per_step, 1)
-    st_gbs = st_bytes_per_launch / (st_ms_per_launch * 1e-3) / 1e9 if st_n else None
-    # dram__bytes_read + dram__bytes_write of one launch from the committed ncu --set full capture (C2 shape, one launch per stage)
-    traffic = NCU_TCN_STAGE_TRAFFIC if (frames == 160000 and abs(st_per_step - 41) < 0.5 and args.precision == 'f16x3') else None
+    chain_bytes = frames * TCN_CHAIN_BYTES_PER_FRAME
     stft_ms, stft_n = prof['stft']
     stft_gbs = frames * STFT_BYTES_PER_FRAME / (stft_ms / max(stft_n, 1) * 1e-3) / 1e9 if stft_n else None
     enh_ms, enh_n = prof['enhance']
+    enh_gbs = (frames * (3 * 1028 + 1024) / (enh_ms / max(enh_n, 1) * 1e-3) / 1e9) if enh_n else None
+    e2e_value = audio_s * args.steps / (e2e_ms / 1e3)
+    # e2e bound the links imply: a step moves B*L*2 bytes in and B*(T+1)*512 bytes out per rank, the two directions run concurrently
+    h2d_bytes, d2h_bytes = B * L * 2, B * (T + 1) * 256 * 2
+    link_s = max(h2d_bytes / (h2d_min * 1e9), d2h_bytes / (d2h_min * 1e9)) if min(h2d_min, d2h_min) > 0 else None
+    pcie_bound = (world * B * SECONDS / max(link_s, ms / args.steps * 1e-3)) if link_s else None
     line = {
         'metric': 'audio-seconds enhanced per second (ResNet-1.1c, MMSE-LSA)', 'value': value, 'unit': 'audio-s/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps,
@@ -312,40 +397,101 @@ def run_ours(args, rank, world, local_rank):
         'dtype': {'f16x3': 'f16x3 (fp16 hi/lo split tensor-core operands, fp32 accumulate; fp32 elsewhere)',
                   'f16': 'f16 tensor-core operands, fp32 accumulate', 'f32': 'f32'}[args.precision],
         'data': 'synthetic',
-        'config': {'workload': 'ResNet-1.1c (ResNetV2 40 blocks causal, random-init weights of the checkpoint shapes) + '
-                               'MMSE-LSA, %d utt x %d s @16 kHz per GPU, STFT 512/256, int16 waveform in -> f32 waveform out'
-                               % (B, SECONDS),
+        'config': {'workload': WORKLOAD % (B, SECONDS),
                    'utterances_per_gpu': B, 'frames_per_gpu': frames, 'precision': args.precision,
                    'sharding': 'utterances split across ranks, no data-path collective',
                    'l2': 'per-step working set %.2f GB per GPU (two alternating input buffers) exceeds the 126 MB L2'
                          % ((B * L * 2 + 3 * frames * 257 * 4 + frames * 1024 + B * (T + 1) * 1024) / 1e9)},
         'realtime_factor_per_gpu': value / world,
         'clocks': clocks,
-        'e2e': {'value': audio_s * args.steps / (e2e_ms / 1e3), 'unit': 'audio-s/s',
-                'h2d_bytes_per_step': B * L * 2, 'd2h_bytes_per_step': B * (T + 1) * 256 * 2,
+        'e2e': {'value': e2e_value, 'unit': 'audio-s/s',
+                'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
                 'api': 'HostPipeline(DeepXi).submit(pinned int16 in, lens, pinned int16 out): H2D, DeepXi.infer_batch and D2H on three event-chained streams, 3 batches in flight',
-                'host_binding': numa},
+                'host_binding': numa,
+                'pcie_ceiling_gbs': {'h2d_per_gpu_min': h2d_min, 'd2h_per_gpu_min': d2h_min, 'h2d_all_gpus': float(tsum[0]), 'd2h_all_gpus': float(tsum[1]),
+                                     'how': '0.2 s of back-to-back duplex copies of the same pinned buffers, all ranks at once, CUDA events'},
+                'pcie_bound': pcie_bound, 'frac_of_pcie_bound': (e2e_value / pcie_bound) if pcie_bound else None,
+                'note': 'bound = audio per step / max(link time of a step at the measured duplex rates, device time of a step)'},
         'gpu_launches': launches,
-        'roofline': {'kernel': 'tcn_stage_kernel (tcgen05 / TMEM, %g launches per step)' % st_per_step, 'bound': 'tensor',
-                     'achieved': achieved_tf, 'peak': tf_peak, 'unit': 'TFLOP/s',
-                     'frac': (achieved_tf / tf_peak) if achieved_tf else None, 'traffic': traffic,
-                     'traffic_source': 'profiles/r01_prof_tcn_stage_final.csv (bytes per launch; algorithmic %.0f)' % st_bytes_per_launch,
-                     'hbm_view': {'bound': 'hbm', 'achieved': st_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
-                                  'frac': (st_gbs / hbm_peak) if st_gbs else None, 'bytes_per_frame_and_stage': TCN_STAGE_BYTES_PER_FRAME,
-                                  'note': 'one stage per launch, chained tile by tile through flags: the kernel streams the fp32 residual '
-                                          'through HBM at loaded-latency speed; this is the bound that binds today, the tensor figure is the target'},
-                     'peak_source': peak_src + ' bf16 sustained (MEASURED_PEAKS.json)',
+        'roofline': {'kernel': ('tcn_chain_kernel (the 40 residual blocks depth first, tcgen05 / TMEM, %g launch per step)' if chain else
+                                'tcn_stage_kernel (tcgen05 / TMEM, %g launches per step)') % st_per_step, 'bound': 'tensor',
+                     'achieved': achieved_tf, 'peak': tf_burst, 'unit': 'TFLOP/s',
+                     'frac': (achieved_tf / tf_burst) if achieved_tf else None,
+                     'frac_of_sustained_peak': (achieved_tf / tf_sustained) if achieved_tf else None,
+                     'traffic': NCU_TCN_CHAIN_TRAFFIC if (chain and frames == 160000 and args.precision == 'f16x3') else None,
+                     'traffic_source': 'profiles/r02_prof_tcn_chain.csv (dram bytes of the launch under ncu --set full; a citation, not measured in this run); '
+                                       'algorithmic %.0f bytes per launch' % chain_bytes,
+                     'peak_source': peak_src + ' bf16 burst (MEASURED_PEAKS.json bf16_tflops): the timed region is %.0f ms; sustained %.1f' % (ms, tf_sustained),
                      'algorithmic_flop_per_launch': flops_per_launch, 'ms_per_launch': st_ms_per_launch,
                      'share_of_step': st_ms / ms if ms else None,
-                     'note': 'useful FLOPs only: in f16x3 mode the tensor cores execute 3x this'},
+                     'note': 'useful FLOPs only: in f16x3 mode the tensor cores execute 3x this (ceiling of the useful fraction: 0.33); the '
+                             'kernel keeps one tile per SM and is bound by the serial chain GEMM -> epilogue -> GEMM of a block, see DESIGN.md'},
         'kernels_ms_per_step': {k: (v[0] / args.steps) for k, v in prof.items()},
         'stft': {'bound': 'hbm', 'achieved': stft_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
                  'frac': (stft_gbs / hbm_peak) if stft_gbs else None, 'bytes_per_frame': STFT_BYTES_PER_FRAME},
-        'enhance_gbs': (frames * (3 * 1028 + 1024) / (enh_ms / max(enh_n, 1) * 1e-3) / 1e9) if enh_n else None,
+        'enhance': {'bound': 'hbm', 'achieved': enh_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': (enh_gbs / hbm_peak) if enh_gbs else None,
+                    'bytes_per_frame': 3 * 1028 + 1024},
+        'enhance_gbs': enh_gbs,
     }
+    if sustained:
+        line['sustained'] = {'value': audio_s * sustained[0] / (sus_ms / 1e3), 'unit': 'audio-s/s', 'steps': sustained[0],
+                             'seconds': sus_ms / 1e3, 'ms_per_step': sus_ms / sustained[0], 'clocks': clocks_sus}
+    if configs:
+        line['configs'] = configs
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline(args.ref_utts)
     print(json.dumps(line), flush=True)
+
+
+def extra_configs(torch, dx, it, dev, args):
+    """BASELINE.json configs other than the headline one, device-resident inputs, CUDA events (each a few tens of ms)."""
+    from deepxi_b200 import synth, weights
+    from deepxi_b200.model import DeepXi
+    out = {}
+
+    def timed(fn, reps, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    # C1: one 4 s utterance, batch 1 (latency of the whole path, int16 in -> waveform out)
+    x1 = torch.from_numpy(synth.noisy_speech(1, 4 * F_S, seed=7)).to(dev)
+    ms1 = timed(lambda: dx.infer_batch(x1, [4 * F_S], 'y', 'mmse-lsa'), 20, 3)
+    out['C1'] = {'workload': 'ResNet-1.1c + MMSE-LSA, 1 utterance x 4 s, batch 1', 'ms_per_call': ms1, 'realtime_factor': 4.0 / (ms1 * 1e-3)}
+    # C5: the per-GPU shard of the 8192-utterance corpus at 8 GPUs (1024 utterances x 10 s in one call)
+    B5, L = 1024, SECONDS * F_S
+    base = synth.noisy_speech(32, L, seed=99)
+    x5 = torch.from_numpy(np.tile(base, (B5 // 32, 1))).to(dev)
+    lens5 = [L] * B5
+    ms5 = timed(lambda: dx.infer_batch(x5, lens5, 'y', 'mmse-lsa'), 3, 1)
+    out['C5_shard'] = {'workload': 'ResNet-1.1c + MMSE-LSA, 1024 utt x 10 s (one GPU\'s shard of the 8192-utterance corpus at 8 GPUs)',
+                       'ms_per_step': ms5, 'value': B5 * SECONDS / (ms5 * 1e-3), 'unit': 'audio-s/s'}
+    del x5
+    # C3: MHANet-1.1c, 64 utterances x 30 s
+    dm = DeepXi(512, 256, 512, F_S, 'MagXi', 'MHANetV3', ver='mhanet-1.1c', map_type='DBNormalCDF', map_params=None,
+                precision=args.precision, **MHA_KW)
+    dm.set_weights(weights.synthetic_mhanetv3(0))
+    B3, L3 = 64, 30 * F_S
+    x3 = torch.from_numpy(np.tile(synth.noisy_speech(16, L3, seed=98), (4, 1))).to(dev)
+    lens3 = [L3] * B3
+    ms3 = timed(lambda: dm.infer_batch(x3, lens3, 'y', 'mmse-lsa'), 3, 1)
+    T3 = -(-L3 // 256)
+    inp3, _, _ = dm.inp_tgt.observation_batch(x3, lens3)
+    ms3n = timed(lambda: dm.network(inp3), 3, 1)
+    mha_flop = B3 * T3 * (2 * 257 * 256 + 5 * (2 * 256 * 768 + 2 * 256 * 256 + 2 * 256 * 1024 * 2 + 4 * T3 * 256) + 2 * 256 * 257)
+    hbm_peak, tf_burst, tf_sustained, _ = measured_peaks()
+    out['C3'] = {'workload': 'MHANet-1.1c (MHANetV3, 5 blocks, 8 heads, mask as shipped) + MMSE-LSA, 64 utt x 30 s',
+                 'ms_per_step': ms3, 'value': B3 * 30 / (ms3 * 1e-3), 'unit': 'audio-s/s', 'network_ms': ms3n,
+                 'roofline': {'bound': 'tensor', 'achieved': mha_flop / (ms3n * 1e-3) / 1e12, 'peak': tf_burst, 'unit': 'TFLOP/s',
+                              'frac': mha_flop / (ms3n * 1e-3) / 1e12 / tf_burst, 'note': 'whole network forward, useful FLOPs (f16x3 executes 3x)'}}
+    return out
 
 
 def main():
@@ -359,6 +505,9 @@ def main():
     ap.add_argument('--utts', type=int, default=UTTS_PER_GPU, help='utterances per GPU')
     ap.add_argument('--ref-utts', type=int, default=8, help='utterances per step of the CPU arm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-sustained', action='store_true')
+    ap.add_argument('--no-extra-configs', action='store_true')
+    ap.add_argument('--sustain-seconds', type=float, default=3.0)
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
