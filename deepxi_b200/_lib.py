@@ -21,9 +21,9 @@ MASK_MODES = {'none': 0, 'causal+pad': 1}
 
 # every symbol include/deepxi_b200.h declares
 SYMBOLS = ['dxi_last_error', 'dxi_version', 'dxi_device_check', 'dxi_stft', 'dxi_istft', 'dxi_map_gain', 'dxi_gfunc',
-           'dxi_cdf_map', 'dxi_enhance', 'dxi_net_create', 'dxi_net_load', 'dxi_net_finalize',
+           'dxi_cdf_map', 'dxi_deepmmse', 'dxi_enhance', 'dxi_net_create', 'dxi_net_load', 'dxi_net_finalize',
            'dxi_net_workspace_bytes', 'dxi_net_forward', 'dxi_net_destroy', 'dxi_launch_count',
-           'dxi_launch_count_reset', 'dxi_selftest_umma', 'dxi_profile_enable', 'dxi_profile_read', 'dxi_debug_tcn_clocks', 'dxi_debug_tmem_bw', 'dxi_debug_tcn_stop_after',
+           'dxi_launch_count_reset', 'dxi_selftest_umma', 'dxi_profile_enable', 'dxi_profile_read',
            'dxi_mix_workspace_bytes', 'dxi_mix', 'dxi_xi_map', 'dxi_xi_db_moments', 'dxi_subband_ibm']
 
 
@@ -57,6 +57,8 @@ def load():
     lib.dxi_map_gain.argtypes = [vp, vp, vp, i64, i32, i32, vp, vp, vp, vp]
     lib.dxi_gfunc.argtypes = [vp, vp, i64, i32, vp, vp]
     lib.dxi_cdf_map.argtypes = [vp, vp, vp, i64, i32, vp, vp]
+    lib.dxi_deepmmse.argtypes = [vp, vp, vp, vp, i64, i32, vp, vp]
+    lib.dxi_deepmmse.restype = i32
     lib.dxi_enhance.argtypes = [vp, vp, vp, vp, vp, i32, vp, i32, i32, vp, vp, i64, vp]
     lib.dxi_net_create.argtypes = [ctypes.POINTER(vp), i32, ctypes.POINTER(NetCfg)]
     lib.dxi_net_load.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(i64), i32]
@@ -73,12 +75,15 @@ def load():
     lib.dxi_profile_enable.restype = None
     lib.dxi_profile_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     lib.dxi_profile_read.restype = i32
-    lib.dxi_debug_tcn_clocks.argtypes = [vp, i32]
-    lib.dxi_debug_tcn_clocks.restype = None
-    lib.dxi_debug_tmem_bw.argtypes = [i32, i32, i32, vp, vp]
-    lib.dxi_debug_tmem_bw.restype = i32
-    lib.dxi_debug_tcn_stop_after.argtypes = [i32]
-    lib.dxi_debug_tcn_stop_after.restype = None
+    if hasattr(lib, 'dxi_debug_tcn_clocks'):      # tuning build only (include/deepxi_b200_debug.h)
+        lib.dxi_debug_tcn_clocks.argtypes = [vp, i32]
+        lib.dxi_debug_tcn_clocks.restype = None
+        lib.dxi_debug_tmem_bw.argtypes = [i32, i32, i32, vp, vp]
+        lib.dxi_debug_tmem_bw.restype = i32
+        lib.dxi_debug_tcn_stop_after.argtypes = [i32]
+        lib.dxi_debug_tcn_stop_after.restype = None
+        lib.dxi_debug_chain_clocks.argtypes = [vp, i32]
+        lib.dxi_debug_chain_clocks.restype = i32
     lib.dxi_mix_workspace_bytes.argtypes = [i32]
     lib.dxi_mix_workspace_bytes.restype = i64
     lib.dxi_mix.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, i64, vp, vp, vp, i64, vp, vp]
@@ -87,7 +92,7 @@ def load():
     lib.dxi_subband_ibm.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp]
     for name in ('dxi_mix', 'dxi_xi_map', 'dxi_xi_db_moments', 'dxi_subband_ibm'):
         getattr(lib, name).restype = i32
-    for name in ('dxi_stft', 'dxi_istft', 'dxi_map_gain', 'dxi_gfunc', 'dxi_cdf_map', 'dxi_enhance', 'dxi_net_create',
+    for name in ('dxi_stft', 'dxi_istft', 'dxi_map_gain', 'dxi_gfunc', 'dxi_cdf_map', 'dxi_deepmmse', 'dxi_enhance', 'dxi_net_create',
                  'dxi_net_load', 'dxi_net_finalize', 'dxi_net_forward', 'dxi_net_destroy', 'dxi_selftest_umma'):
         getattr(lib, name).restype = i32
     _lib = lib

@@ -9,7 +9,8 @@ template <int UNROLL>
 __global__ void __launch_bounds__(256) map_gain_kernel(const float* __restrict__ xbar, const float* __restrict__ mu,
                                                        const float* __restrict__ sigma, int64_t n, int n_bins,
                                                        int gtype, float* __restrict__ xi_out,
-                                                       float* __restrict__ g_out, uint8_t* __restrict__ ibm_out) {
+                                                       float* __restrict__ g_out, uint8_t* __restrict__ ibm_out,
+                                                       const float* __restrict__ mag_sq = nullptr) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * UNROLL) {
     float xb[UNROLL];
@@ -25,7 +26,11 @@ __global__ void __launch_bounds__(256) map_gain_kernel(const float* __restrict__
       int k = (int)(i % n_bins);
       float xi = xi_from_xbar(xb[u], __ldg(mu + k), __ldg(sigma + k));
       if (xi_out) __stcs(xi_out + i, xi);
-      if (g_out) __stcs(g_out + i, gfunc_eval(gtype, xi, __fadd_rn(xi, 1.0f)));   // gamma_hat = xi_hat + 1 (inp_tgt.py:212)
+      if (g_out) {
+        const float g = gfunc_eval(gtype, xi, __fadd_rn(xi, 1.0f));   // gamma_hat = xi_hat + 1 (inp_tgt.py:212)
+        if (mag_sq) { const float m = __ldcs(mag_sq + i); __stcs(g_out + i, __fmul_rn(__fmul_rn(m, m), g)); }      // |X|^2 G (model.py:314-318)
+        else __stcs(g_out + i, g);
+      }
       if (ibm_out) ibm_out[i] = xi > 1.0f ? 1 : 0;
     }
   }
@@ -76,6 +81,19 @@ extern "C" DXI_API int dxi_map_gain(const float* xbar, const float* mu, const fl
   if (n == 0) return DXI_OK;
   ProfScope prof("map_gain", as_stream(stream), 1);
   map_gain_kernel<4><<<grid_for(n, 4), 256, 0, as_stream(stream)>>>(xbar, mu, sigma, n, n_bins, gtype, xi_hat, gain, ibm);
+  DXI_LAUNCHED("map_gain_kernel");
+  return DXI_OK;
+}
+
+extern "C" DXI_API int dxi_deepmmse(const float* mag, const float* xbar, const float* mu, const float* sigma, int64_t n_rows, int n_bins,
+                            float* d_psd, void* stream) {
+  if (int rc = check_device()) return rc;
+  DXI_REQUIRE(mag && xbar && mu && sigma && d_psd, "dxi_deepmmse: null argument");
+  DXI_REQUIRE(n_rows >= 0 && n_bins > 0, "dxi_deepmmse: bad shape");
+  int64_t n = n_rows * n_bins;
+  if (n == 0) return DXI_OK;
+  ProfScope prof("map_gain", as_stream(stream), 1);
+  map_gain_kernel<4><<<grid_for(n, 4), 256, 0, as_stream(stream)>>>(xbar, mu, sigma, n, n_bins, DXI_G_DEEPMMSE, nullptr, d_psd, nullptr, mag);
   DXI_LAUNCHED("map_gain_kernel");
   return DXI_OK;
 }

@@ -115,6 +115,11 @@ extern "C" DXI_API int dxi_net_load(dxi_net_t* h, const char* tensor_name, const
 extern "C" DXI_API int dxi_net_finalize(dxi_net_t* h, void* stream) {
   if (int rc = check_device()) return rc;
   DXI_REQUIRE(h, "dxi_net_finalize: null handle");
+  {
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (dev != h->device) { set_error("dxi_net_finalize: handle belongs to device %d, current device is %d", h->device, dev); return DXI_E_STATE; }
+  }
   auto exp = expected_shapes(h->kind, h->cfg);
   for (auto& kv : exp)
     if (!h->host.count(kv.first)) { set_error("dxi_net_finalize: tensor '%s' was not loaded", kv.first.c_str()); return DXI_E_STATE; }
@@ -171,6 +176,11 @@ extern "C" DXI_API int dxi_net_forward(dxi_net_t* h, const float* mag, int B, in
   DXI_REQUIRE(h && mag && xbar, "dxi_net_forward: null argument");
   DXI_REQUIRE(B >= 0 && Tmax >= 0, "dxi_net_forward: bad shape");
   if (!h->finalized) { set_error("dxi_net_forward: call dxi_net_finalize first"); return DXI_E_STATE; }
+  {   // the handle's weights live on the device that was current at creation: refuse anything else instead of faulting
+    int dev = -1;
+    cudaGetDevice(&dev);
+    if (dev != h->device) { set_error("dxi_net_forward: handle belongs to device %d, current device is %d", h->device, dev); return DXI_E_STATE; }
+  }
   if (B == 0 || Tmax == 0) return DXI_OK;
   DXI_REQUIRE(workspace, "dxi_net_forward: null workspace");
   cudaStream_t st = as_stream(stream);

@@ -80,10 +80,21 @@ struct StageArgs {
   int wait_val;                 // with flags: a tile of this stage may start once flags[.] >= wait_val for it and its neighbours
   int* flags;                   // flags[tile] = number of stages that have published the tile (zeroed by the host before the stem); nullptr:
                                 // every stage waits for the whole previous launch (griddepcontrol.wait) instead
-  int dbg_flags;                // tuning experiments only: 1 = skip residual loads, 2 = skip residual stores, 4 = skip c1 tap loads
-  long long* dbg_cta;           // optional: per-CTA timeline of this launch in globaltimer ns (8 slots per CTA), see scripts/tcn_timeline.py
-  long long* dbg;               // optional: clock64 stamps of the epilogue phases (16 per tile), see dxi_debug_tcn_clocks
+#ifdef DXI_ENABLE_DEBUG         // tuning build only (DXI_DEBUG_BUILD=1 python -m deepxi_b200.build): none of this exists in the product library
+  int dbg_flags;                // tuning experiments: 1 = skip residual loads, 2 = skip residual stores, 4 = skip c1 tap loads
+  long long* dbg_cta;           // per-CTA timeline of this launch in globaltimer ns (8 slots per CTA), see scripts/tcn_timeline.py
+  long long* dbg;               // clock64 stamps of the epilogue phases (16 per tile), see dxi_debug_tcn_clocks
+#endif
 };
+#ifdef DXI_ENABLE_DEBUG
+#define DBG_CTA (p.dbg_cta)
+#define DBG_FLAGS (p.dbg_flags)
+#define DBG_STAMPS (p.dbg)
+#else
+#define DBG_CTA (static_cast<long long*>(nullptr))
+#define DBG_FLAGS 0
+#define DBG_STAMPS (static_cast<long long*>(nullptr))
+#endif
 
 __device__ __forceinline__ float relu(float x) { return fmaxf(x, 0.0f); }
 
@@ -151,8 +162,8 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
   const float* sAux = reinterpret_cast<const float*>(sW + IMG_BIAS);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // (debug) per-CTA timeline slots: the pointer is re-formed from the kernel parameters at every use instead of living in registers
-#define tl (p.dbg_cta + (size_t)blockIdx.x * 8)
-  if (p.dbg_cta && tid == 0) {
+#define tl (DBG_CTA + (size_t)blockIdx.x * 8)
+  if (DBG_CTA && tid == 0) {
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     tl[0] = globaltimer_ns(); tl[6] = smid;
@@ -232,16 +243,21 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
       const int j = t % p.tiles_per_utt, dj = lane - 1;
       if (lane < 3 && j + dj >= 0 && j + dj < p.tiles_per_utt) {
         const int* f = p.flags + t + dj;
-        while (ld_acquire_gpu(f) < p.wait_val) {}
+        if (ld_acquire_gpu(f) < p.wait_val) {      // bounded: a broken co-residency argument must fail the launch, not hang the GPU
+          const long long t_spin = clock64();
+          uint32_t spins = 0;
+          while (ld_acquire_gpu(f) < p.wait_val)
+            if ((++spins & 255u) == 0 && clock64() - t_spin > SPIN_LIMIT_CYCLES) __trap();
+        }
       }
       __syncwarp();
       if (elect_one()) mbar_arrive(&bar_dep);
       __syncwarp();
     };
-    if (p.dbg_cta && lane == 0) tl[1] = globaltimer_ns();
+    if (DBG_CTA && lane == 0) tl[1] = globaltimer_ns();
     if (dep_flags) { if (n_r > 0) await(tile_first); }
     else asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (p.dbg_cta && lane == 0) tl[2] = globaltimer_ns();
+    if (DBG_CTA && lane == 0) tl[2] = globaltimer_ns();
     for (int r = 0; r < n_r; ++r) {
       const int tile = tile_at(r);
       // The shared-memory descriptors are recomputed per tile (a handful of uniform-datapath adds) instead of being kept as ~100
@@ -324,8 +340,8 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
     uint32_t ph = 0, pdep = 0;
     // one arrival per warp: tcgen05.wait is warp-wide, so once it returns every lane's TMEM traffic is done
     auto warp_arrive = [&](uint64_t* bar) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar); };
-    const bool stamp = p.dbg != nullptr && tid == 0;
-#define DXI_STAMP(k) do { if (stamp) p.dbg[(size_t)tile * 16 + (k)] = clock64(); } while (0)
+    const bool stamp = DBG_STAMPS != nullptr && tid == 0;
+#define DXI_STAMP(k) do { if (stamp) DBG_STAMPS[(size_t)tile * 16 + (k)] = clock64(); } while (0)
 
     // c1 taps of a tile -> TMEM [320,512): this thread moves units 2qd, 2qd+1 of every (tap, plane)
     auto load_a1 = [&](int tile_) {
@@ -340,7 +356,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
         for (int plane = 0; plane < (SPLIT ? 2 : 1); ++plane)
 #pragma unroll
           for (int u = 0; u < 2; ++u)
-            qv[j][plane][u] = (p.dbg_flags & 4) ? make_uint4(0, 0, 0, 0) : __ldcg(reinterpret_cast<const uint4*>(cb + ((size_t)(plane * 8 + 2 * qd + u) * p.Ts + r_in) * 8));
+            qv[j][plane][u] = (DBG_FLAGS & 4) ? make_uint4(0, 0, 0, 0) : __ldcg(reinterpret_cast<const uint4*>(cb + ((size_t)(plane * 8 + 2 * qd + u) * p.Ts + r_in) * 8));
       }
 #pragma unroll
       for (int j = 0; j < 3; ++j)
@@ -358,7 +374,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
     auto dep_wait = [&]() { if (dep_flags) { mbar_wait(&bar_dep, pdep); pdep ^= 1; } };
     if (!dep_flags) asm volatile("griddepcontrol.wait;" ::: "memory");      // the previous launch's h / c1 are complete and visible
     if (p.has_back && n_r > 0) { dep_wait(); load_a1(tile_first); warp_arrive(&bar_a1); }
-    if (p.dbg_cta && tid == 0) { tl[3] = globaltimer_ns(); tl[7] = n_r; }
+    if (DBG_CTA && tid == 0) { tl[3] = globaltimer_ns(); tl[7] = n_r; }
     for (int r = 0; r < n_r; ++r) {
       const int tile = tile_at(r);
       const int b = tile / p.tiles_per_utt, t0 = (tile - b * p.tiles_per_utt) * TILE;
@@ -371,7 +387,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
       float4 hv[8];
       auto load_h = [&](int cc_) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) hv[q] = (p.dbg_flags & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(reinterpret_cast<const float4*>(hrow + (size_t)(cc_ * 8 + q) * (TILE * 4)));
+        for (int q = 0; q < 8; ++q) hv[q] = (DBG_FLAGS & 1) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcg(reinterpret_cast<const float4*>(hrow + (size_t)(cc_ * 8 + q) * (TILE * 4)));
       };
       load_h(qd);
       float mu2 = 0.0f, inv2 = 0.0f;
@@ -468,7 +484,7 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.0f;
         }
-        if ((p.has_back || p.stem_stats) && !(p.dbg_flags & 2)) {
+        if ((p.has_back || p.stem_stats) && !(DBG_FLAGS & 2)) {
 #pragma unroll
           for (int q = 0; q < 8; ++q)
             *reinterpret_cast<float4*>(hrow + (size_t)(cc * 8 + q) * (TILE * 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -545,11 +561,11 @@ __global__ void __launch_bounds__(TCN_THREADS, 1) tcn_stage_kernel(const StageAr
       ph ^= 1;
     }
 #undef DXI_STAMP
-    if (p.dbg_cta && tid == 0) tl[4] = globaltimer_ns();
+    if (DBG_CTA && tid == 0) tl[4] = globaltimer_ns();
   }
   tc_fence_before();
   __syncthreads();
-  if (p.dbg_cta && tid == 0) tl[5] = globaltimer_ns();
+  if (DBG_CTA && tid == 0) tl[5] = globaltimer_ns();
 #undef tl
   if (warp == EPI_WARPS) tmem_dealloc(0, 512);
 }
@@ -932,8 +948,12 @@ int resnet_umma_prepare(dxi_net& net, cudaStream_t st) {
 }
 
 static bool env_flag(const char* name) { const char* v = getenv(name); return v && *v && *v != '0'; }
+#ifdef DXI_ENABLE_DEBUG
 static thread_local long long* g_dbg_clocks = nullptr;
 static thread_local int g_dbg_stage = -1, g_dbg_flags = 0, g_dbg_stop_after = -1;
+#else
+constexpr int g_dbg_stop_after = -1;
+#endif
 
 int64_t resnet_umma_workspace_bytes(const dxi_net& net, int B, int T) {
   const int tiles = (T + TILE - 1) / TILE;
@@ -1010,9 +1030,11 @@ static int resnet_umma_group(const dxi_net& net, const float* mag, int B, int T,
     a.T = T; a.tiles_per_utt = tiles; a.n_tiles = n_tiles; a.Ts = Ts;
     a.has_back = s >= 1; a.has_front = s < c.n_blocks;
     a.reverse = (s & 1) == 0 && !env_flag("DXI_TCN_NO_REVERSE");      // the stem leaves the last tiles in L2, the output layer starts on the first
+#ifdef DXI_ENABLE_DEBUG
     a.dbg = (dbg && s == g_dbg_stage) ? g_dbg_clocks : nullptr;
     a.dbg_cta = (dbg && g_dbg_stage == 255 && g_dbg_clocks) ? g_dbg_clocks + (size_t)s * grid * 8 : nullptr;      // stage 255: CTA timelines of all stages
     a.dbg_flags = g_dbg_flags;
+#endif
     a.flags = (no_flags || (dbg && g_dbg_stop_after >= 0)) ? nullptr : flags;
     float* row_scale = reinterpret_cast<float*>(chain_ws);      // [2][n_tiles * 128], alternating between stages
     a.sc_in = s >= 1 ? row_scale + (size_t)((s + 1) & 1) * n_tiles * TILE : nullptr;
@@ -1057,6 +1079,7 @@ int resnet_umma_forward(const dxi_net& net, const float* mag, int B, int T, floa
 
 }  // namespace dxi
 
+#ifdef DXI_ENABLE_DEBUG
 // Debug aid: the epilogue of stage `stage` of the following forward calls (this thread) writes 16 clock64
 // stamps per tile into dev_buf[n_tiles * 16]; pass nullptr to switch it off.
 extern "C" DXI_API void dxi_debug_tcn_clocks(long long* dev_buf, int stage) {
@@ -1068,3 +1091,4 @@ extern "C" DXI_API void dxi_debug_tcn_clocks(long long* dev_buf, int stage) {
 // Debug aid: run only the stem and stages 0..stage of subsequent forwards of this thread (-1 = everything), so
 // that the residual / c1 buffers in the caller's workspace can be inspected between stages.
 extern "C" DXI_API void dxi_debug_tcn_stop_after(int stage) { dxi::g_dbg_stop_after = stage; }
+#endif

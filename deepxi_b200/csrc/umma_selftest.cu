@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __grid_constan
 }
 
 
+#ifdef DXI_ENABLE_DEBUG
 // TMEM port micro-benchmark: `warps` warps (multiple of 4) each run `rounds` x (tcgen05.ld|st .32x32b.x32) on their
 // lane quarter; out[0] = cycles for the whole CTA (max over warps).  mode 0 = loads, 1 = stores, 2 = load + store.
 __global__ void __launch_bounds__(1024) tmem_bw_kernel(int mode, int rounds, long long* out) {
@@ -160,6 +161,8 @@ __global__ void __launch_bounds__(1024) tmem_bw_kernel(int mode, int rounds, lon
   if (warp == 0) tmem_dealloc(slot, 512);
 }
 
+#endif
+
 }  // namespace dxi
 
 using namespace dxi;
@@ -167,6 +170,7 @@ using namespace dxi;
 namespace dxi { int make_weight_map(void* out, const void* dev, int K, size_t rows, int box_rows); }
 static int selftest_weight_map(CUtensorMap* tm, const void* b, int K, int N) { return dxi::make_weight_map(tm, b, K, (size_t)N, N); }
 
+#ifdef DXI_ENABLE_DEBUG
 extern "C" DXI_API int dxi_debug_tmem_bw(int mode, int warps, int rounds, long long* dev_out, void* stream) {
   if (int rc = check_device()) return rc;
   DXI_REQUIRE(warps >= 4 && warps <= 32 && warps % 4 == 0 && rounds > 0 && dev_out, "dxi_debug_tmem_bw: bad argument");
@@ -174,6 +178,7 @@ extern "C" DXI_API int dxi_debug_tmem_bw(int mode, int warps, int rounds, long l
   DXI_LAUNCHED("tmem_bw_kernel");
   return DXI_OK;
 }
+#endif
 
 extern "C" DXI_API int dxi_selftest_umma(const void* a_f16, const void* b_f16, int N, int K, int variant, float* d_out,
                                  void* stream) {

@@ -161,6 +161,19 @@ class MagXi(MagTgt):
         _, G, _, was_np = self._map_gain(xi_bar_hat, gtype, want_gain=True)
         return ret(G, was_np)
 
+    def deepmmse(self, x_STMS, xi_bar_hat):
+        """Noise PSD estimate of out_type 'deepmmse' (model.py:314-318): |X|^2 * gfunc(xi_hat, xi_hat + 1, 'deepmmse'), one kernel."""
+        mag, was_np = to_dev(x_STMS, torch.float32)
+        xb, _ = to_dev(xi_bar_hat, torch.float32)
+        if mag.shape != xb.shape or mag.shape[-1] != self.n_outp:
+            raise ValueError('x_STMS and xi_bar_hat must share the shape [..., T, %d]' % self.n_outp)
+        mu, sigma = self.xi_map._stats_dev(xb.device)
+        out = torch.empty_like(xb)
+        if xb.numel():
+            _lib.check(_lib.load().dxi_deepmmse(_lib.ptr(mag), _lib.ptr(xb), _lib.ptr(mu), _lib.ptr(sigma), xb.numel() // self.n_outp,
+                                                self.n_outp, _lib.ptr(out), _lib.stream_ptr(xb.device)))
+        return ret(out, was_np)
+
     def ibm_hat(self, xi_bar_hat):
         """xi_hat > 1 as bool (model.py:319-322)."""
         _, _, ibm, was_np = self._map_gain(xi_bar_hat, None, want_ibm=True)
@@ -271,16 +284,17 @@ class MagGain(MagTgt):
         X, _ = self._stft(xo, lens)
         return X, gfunc(self.xi(S, D), self.gamma(X, D), self.gain), nfr
 
-    def enhanced_speech(self, x_STMS, x_STPS, G_hat, gtype=None):
-        """inp_tgt.py:503-519: the network output IS the gain (thresholded at 0.5 for 'ibm')."""
+    def enhanced_speech(self, x_STMS, x_STPS, G_hat, gtype=None, n_frames=None, int16=False):
+        """inp_tgt.py:503-519: the network output IS the gain (thresholded at 0.5 for 'ibm').  Batched [B, T, 257] inputs take the
+        per-utterance n_frames; int16=True applies the save_wav rule (utils.py:28) in the synthesis kernel."""
         mag, was_np = to_dev(x_STMS, torch.float32)
         G, _ = to_dev(G_hat, torch.float32)
         if self.gain == 'ibm':
             G = (G > 0.5).to(torch.float32)
-        return ret(_synthesis_with_gain(self, mag, x_STPS, G), was_np)
+        return ret(_synthesis_with_gain(self, mag, x_STPS, G, n_frames, int16), was_np)
 
 
-def _synthesis_with_gain(it, mag, x_STPS, G):
+def _synthesis_with_gain(it, mag, x_STPS, G, n_frames=None, int16=False):
     """(|X| G) e^{j phase} -> waveform through dxi_istft (the gain multiply is fused into the synthesis kernel)."""
     pha, _ = to_dev(x_STPS, torch.float32)
     G, _ = to_dev(G, torch.float32)
@@ -291,8 +305,12 @@ def _synthesis_with_gain(it, mag, x_STPS, G):
         mag, pha, G = mag[None], pha[None], G[None]
     B, T, _ = mag.shape
     n_out = (T + 1) * it.N_s
-    y = torch.empty((B, n_out), dtype=torch.float32, device=mag.device)
+    y = torch.empty((B, n_out), dtype=torch.int16 if int16 else torch.float32, device=mag.device)
+    nf = None
+    if n_frames is not None:
+        nf = torch.as_tensor(np.asarray(n_frames, np.int32)).to(mag.device, non_blocking=True)
     if B and T:
-        _lib.check(_lib.load().dxi_istft(_lib.ptr(mag.contiguous()), _lib.ptr(G.contiguous()), _lib.ptr(pha.contiguous()), None, B, T,
-                                         _lib.ptr(y), None, n_out, _lib.stream_ptr(mag.device)))
+        _lib.check(_lib.load().dxi_istft(_lib.ptr(mag.contiguous()), _lib.ptr(G.contiguous()), _lib.ptr(pha.contiguous()),
+                                         _lib.ptr(nf, torch.int32, allow_none=True), B, T,
+                                         None if int16 else _lib.ptr(y), _lib.ptr(y) if int16 else None, n_out, _lib.stream_ptr(mag.device)))
     return y[0] if squeeze else y

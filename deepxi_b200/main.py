@@ -24,6 +24,8 @@ def network_kwargs(args):
     else:
         kw = {}
     kw = {k: v for k, v in kw.items() if v is not None}
+    if args.inp_tgt_type == 'MagGain':
+        kw['gain'] = args.gain[0] if isinstance(args.gain, list) else args.gain      # the gain the network was trained to estimate (inp_tgt.py:51-52)
     kw['precision'] = args.precision or ('f32' if args.network_type in ('ResNet', 'ResNetV3') else 'f16x3')
     return kw
 
@@ -41,7 +43,7 @@ def main(argv=None):
         raise NotImplementedError('--train / --test / --spect_dist / --prelim are outside the inference hot path (SURVEY 2)')
     if not args.infer:
         return 0
-    test_x, test_x_len, _, test_x_base_names = Batch(args.test_x_path)                       # main.py:45-46
+    test_x, test_x_len, _, test_x_base_names = Batch(args.test_x_path, f_s=args.f_s)                       # main.py:45-46
     print('Version: %s.' % args.ver)
     map_type = args.map_type[0] if isinstance(args.map_type, list) else args.map_type
     map_params = args.map_params[0] if isinstance(args.map_params, list) and args.map_params and isinstance(args.map_params[0], list) else None

@@ -33,7 +33,22 @@ class DeepXi:
         self.min_snr, self.max_snr = min_snr, max_snr
         self.snr_levels = list(range(min_snr, max_snr + 1, snr_inter))
         self.ver = ver
+        if inp_tgt_type not in ('MagXi', 'MagGain'):
+            # MagXiGamma (514 outputs) and the fork's other targets have no committed checkpoint; the target classes themselves
+            # (inp_tgt.MagXiGamma ...) are available for the training-target side
+            raise NotImplementedError('DeepXi drives the MagXi and MagGain targets; %r has no committed model' % inp_tgt_type)
         self.inp_tgt = inp_tgt_selector(inp_tgt_type, N_d, N_s, K, f_s, **kwargs)
+        self._init_rest(sample_dir, ver, reset_inp_tgt, N_d, N_s, K, network_type, kwargs)
+
+    def _init_rest(self, sample_dir, ver, reset_inp_tgt, N_d, N_s, K, network_type, kwargs):
+        if self.inp_tgt_type == 'MagGain':      # the network estimates the gain itself: no CDF statistics (inp_tgt.py:471-519)
+            net_kwargs = dict(kwargs)
+            for k in ('map_type', 'map_params', 'stats'):
+                net_kwargs.pop(k, None)
+            self.network = network_selector(network_type, None, self.inp_tgt.n_outp, **net_kwargs)
+            self.model = self.network
+            self._weights_epoch = None
+            return
         # statistics: data/<ver>_inp_tgt.p when present (model.py:90-93), else the packaged values
         p = os.path.join(sample_dir, ver + '_inp_tgt.p') if sample_dir else None
         if p and os.path.exists(p) and not reset_inp_tgt:
@@ -84,6 +99,10 @@ class DeepXi:
         it = self.inp_tgt
         inp, pha, n_frames = it.observation_batch(test_x, test_x_len)
         xbar = self.network(inp)
+        if self.inp_tgt_type == 'MagGain':      # the network output IS the gain (inp_tgt.py:500-519); only the waveform is defined
+            if out_type != 'y':
+                raise ValueError('Invalid output type.')
+            return it.enhanced_speech(inp, pha, xbar, n_frames=n_frames, int16=int16), n_frames
         if out_type == 'y':
             out = it.enhanced_speech(inp, pha, xbar, gain, n_frames=n_frames, int16=int16)
         elif out_type == 'xi_hat':
@@ -96,14 +115,18 @@ class DeepXi:
             out = it.ibm_hat(xbar)
         elif out_type == 'subband_ibm_hat':      # (xi_hat H^T) > 1 with the mel filter bank (model.py:255-258, :323-328)
             out = it.subband(it.xi_hat(xbar), n_filters)[1]
-        else:  # deepmmse: |X|^2 * G_deepmmse(xi_hat, xi_hat + 1)   (model.py:314-318)
-            out = inp * inp * it.gain_hat(xbar, 'deepmmse')
+        else:  # deepmmse: |X|^2 * G_deepmmse(xi_hat, xi_hat + 1)   (model.py:314-318), one kernel
+            out = it.deepmmse(inp, xbar)
         return out, n_frames
 
     def infer(self, test_x, test_x_len, test_x_base_names, test_epoch, model_path='model', out_type='y',
               gain='mmse-lsa', out_path='out', n_filters=40, saved_data_path=None):
         """Deep Xi inference; the specified out_type is saved (model.py:224-332)."""
         out_path_base = out_path
+        if saved_data_path is not None:
+            # model.py:298-300 hands the .mat contents to the target's enhanced_speech as (supplementary, saved_data); only targets
+            # that are out of scope here consume it (MagXi / MagGain take the phase alone)
+            raise NotImplementedError('saved_data_path is only consumed by targets without committed models')
         if not isinstance(test_epoch, list): test_epoch = [test_epoch]
         if not isinstance(gain, list): gain = [gain]
         for e in test_epoch:
@@ -112,7 +135,9 @@ class DeepXi:
                 out_path = out_path_base + '/' + self.ver + '/' + 'e' + str(e)
                 if out_type == 'xi_hat': out_path = out_path + '/xi_hat'
                 elif out_type == 'gamma_hat': out_path = out_path + '/gamma_hat'
-                elif out_type == 'y': out_path = out_path + '/y/' + g
+                elif out_type == 'y':
+                    if self.inp_tgt_type in ('MagGain', 'MagMag'): out_path = out_path + '/y'      # model.py:269-271
+                    else: out_path = out_path + '/y/' + g
                 elif out_type == 'deepmmse': out_path = out_path + '/deepmmse'
                 elif out_type == 'ibm_hat': out_path = out_path + '/ibm_hat'
                 elif out_type == 'subband_ibm_hat': out_path = out_path + '/subband_ibm_hat'

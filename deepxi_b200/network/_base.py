@@ -62,8 +62,9 @@ class DeviceNetwork:
             ws = self._ws.get(key)
             if ws is None or ws.numel() < need:
                 ws = self._ws[key] = torch.empty(need, dtype=torch.uint8, device=x.device)
-            _lib.check(_lib.load().dxi_net_forward(self._h, _lib.ptr(x), B, T, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
-                                                   _lib.stream_ptr(x.device)))
+            with torch.cuda.device(x.device):      # the C side launches on the current device; the handle checks it is its own
+                _lib.check(_lib.load().dxi_net_forward(self._h, _lib.ptr(x), B, T, _lib.ptr(out), _lib.ptr(ws), ws.numel(),
+                                                       _lib.stream_ptr(x.device)))
         return ret(out[0] if squeeze else out, was_np)
 
     predict = __call__

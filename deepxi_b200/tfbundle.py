@@ -259,5 +259,8 @@ def save_tensors(prefix, tensors):
 
 
 def save_keras_weights(prefix, weights):
-    """{'layer_with_weights-<i>/<var>': ndarray} -> a bundle keras_weights() (and Keras' load_weights) can read."""
+    """{'layer_with_weights-<i>/<var>': ndarray} -> a bundle with the checkpoint's own keys ('<name>/.ATTRIBUTES/VARIABLE_VALUE') that
+    keras_weights() / load_tensors() of this module read back (crc-verified).  It is a valid tensor bundle for name-keyed readers
+    (tf.train.load_checkpoint), but it carries NO '_CHECKPOINTABLE_OBJECT_GRAPH' entry, so Keras' object-based model.load_weights
+    (deepxi/model.py:279) cannot restore from it: the writer exists to round-trip this repo's weights, not to feed TensorFlow."""
     save_tensors(prefix, {n + '/.ATTRIBUTES/VARIABLE_VALUE': v for n, v in weights.items()})

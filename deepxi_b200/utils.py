@@ -22,14 +22,32 @@ def save_wav(path, wav, f_s):
         f.writeframes(wav.astype('<i2').tobytes())
 
 
-def read_wav(path):
-    """Returns (int16 waveform, f_s) of a mono PCM16 file (upstream utils.py:43-45 semantics)."""
+def read_wav(path, rule='reference', f_s=16000):
+    """Returns (int16 waveform, f_s) of a PCM16 wav file.
+
+    rule='reference' (default) is the ACTIVE branch of deepxi/utils.py:46-49: librosa.load(path, sr=16000, mono=True, float32)
+    -> audio * 32767 -> astype(int16), i.e. for a 16 kHz PCM16 file trunc((x / 32768) * 32767) in float32 -- almost every non-zero
+    sample moves 1 LSB towards zero -- and the mean of the channels for a multi-channel file.  librosa's resampler is not
+    available here, so a file whose rate is not `f_s` is refused instead of being silently processed at the wrong rate.
+    rule='pcm' returns the stored samples unchanged (the commented-out soundfile branch, utils.py:41-45; mono only)."""
     with wave.open(str(path), 'rb') as f:
-        if f.getsampwidth() != 2 or f.getnchannels() != 1:
-            raise ValueError('%s: only mono PCM16 wav files are supported' % path)
-        f_s = f.getframerate()
+        if f.getsampwidth() != 2:
+            raise ValueError('%s: only PCM16 wav files are supported' % path)
+        rate, n_ch = f.getframerate(), f.getnchannels()
         wav = np.frombuffer(f.readframes(f.getnframes()), dtype='<i2').astype(np.int16)
-    return wav, f_s
+    if rule == 'pcm':
+        if n_ch != 1:
+            raise ValueError('%s: only mono files are supported with rule="pcm"' % path)
+        return wav, rate
+    if rule != 'reference':
+        raise ValueError('rule must be "reference" or "pcm"')
+    if rate != f_s:
+        raise ValueError('%s is sampled at %d Hz; the reference resamples to %d Hz with librosa, which is not available: '
+                         'resample the file first' % (path, rate, f_s))
+    audio = wav.astype(np.float32) / np.float32(32768.0)              # soundfile / librosa PCM16 -> float32
+    if n_ch > 1:
+        audio = audio.reshape(-1, n_ch).mean(axis=1, dtype=np.float32)      # librosa.to_mono
+    return (audio * np.float32(32767.0)).astype(np.int16), f_s
 
 
 def save_mat(path, data, name):

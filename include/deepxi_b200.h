@@ -108,6 +108,11 @@ DXI_API int dxi_istft(const float* mag, const float* gain, const float* phase, c
 DXI_API int dxi_map_gain(const float* xbar, const float* mu, const float* sigma, int64_t n_rows, int n_bins,
                  int gtype, float* xi_hat, float* gain, uint8_t* ibm, void* stream);
 
+/* out_type 'deepmmse' of DeepXi.infer (deepxi/model.py:314-318): d_psd = |X|^2 * gfunc(xi_hat, xi_hat + 1, 'deepmmse') with
+ * xi_hat the inverse map of xbar, in one pass.  mag, xbar, d_psd: [n_rows, n_bins]. */
+DXI_API int dxi_deepmmse(const float* mag, const float* xbar, const float* mu, const float* sigma, int64_t n_rows, int n_bins,
+                 float* d_psd, void* stream);
+
 /* gfunc(xi, gamma, gtype) element-wise (deepxi/gain.py:168-191); gamma may be NULL for the
  * xi-only gains (wf, srwf, cwf, irm, ibm). */
 DXI_API int dxi_gfunc(const float* xi, const float* gamma, int64_t n, int gtype, float* G, void* stream);
@@ -213,17 +218,6 @@ DXI_API void dxi_launch_count_reset(void);
  * the number of launches they covered, and clears the group.  Per calling thread. */
 DXI_API void dxi_profile_enable(int on);
 DXI_API int dxi_profile_read(const char* key, double* total_ms, int64_t* launches);
-
-/* Debug aid for kernel tuning: the epilogue of stage `stage` of subsequent dxi_net_forward calls from this
- * thread writes 16 clock64 stamps per tile into dev_buf (int64 [n_tiles * 16]); NULL switches it off. */
-DXI_API void dxi_debug_tcn_clocks(long long* dev_buf, int stage);
-
-/* Debug aid: subsequent dxi_net_forward calls of this thread run only the stem and stages 0..stage (-1: all). */
-DXI_API void dxi_debug_tcn_stop_after(int stage);
-
-/* Tuning aid: cycles for `warps` warps x `rounds` x 4 KB tcgen05.ld (mode 0) / st (mode 1) / both (mode 2) on one SM;
- * dev_out[0] = cycles. */
-DXI_API int dxi_debug_tmem_bw(int mode, int warps, int rounds, long long* dev_out, void* stream);
 
 /* Self test of the tcgen05 / TMEM building blocks: D[128,N] = A[128,K] * B[K,N] with fp16 operands
  * (A from tensor memory, B from shared memory) written to `d_out` (float32 [128,N]).

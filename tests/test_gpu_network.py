@@ -383,3 +383,42 @@ def test_tile_level_stage_dependencies_are_bit_exact(tmp_path):
             outs.append(np.load(f))
         assert outs[0].shape == outs[1].shape and np.array_equal(outs[0], outs[1])
         assert np.isfinite(outs[0]).all() and outs[0].min() >= 0.0 and outs[0].max() <= 1.0
+
+
+def test_deepmmse_and_maggain_through_deepxi(xi_stats, tmp_path):
+    """out_type 'deepmmse' (model.py:314-318) in one kernel against the oracle; the MagGain target through DeepXi.infer_batch / infer
+    (the network output is the gain, inp_tgt.py:503-519) with the reference's '/y' output directory (model.py:269-271);
+    saved_data_path and targets without committed models raise."""
+    mu, sg = xi_stats['resnet-1.1c/mu'], xi_stats['resnet-1.1c/sigma']
+    w = weights.synthetic_resnetv2(0)
+    lens = [16000, 9000]
+    x = synth.noisy_speech(2, 16000, seed=45)
+    dx = DeepXi(512, 256, 512, 16000, 'MagXi', 'ResNetV2', ver='resnet-1.1c', map_type='DBNormalCDF', map_params=None,
+                padding='causal', precision='f32', **RES_KW)
+    dx.set_weights(w)
+    d, nfr = dx.infer_batch(x, lens, 'deepmmse')
+    inp, _, _ = dx.observation_batch(x, lens)
+    xbar = dx.network(inp).cpu().numpy()
+    xi = cdfmap.normal_cdf_inverse(xbar, mu, sg)
+    from oracle import gain as ogain
+    ref = np.square(inp.cpu().numpy()) * ogain.gfunc(xi, xi + np.float32(1.0), 'deepmmse')
+    got = d.cpu().numpy()
+    for i, n in enumerate(nfr):
+        assert np.allclose(got[i, :n], ref[i, :n], rtol=1e-4, atol=1e-12)
+    with pytest.raises(NotImplementedError):
+        dx.infer(x, lens, ['a', 'b'], test_epoch=1, out_path=str(tmp_path), saved_data_path=str(tmp_path))
+    with pytest.raises(NotImplementedError):
+        DeepXi(512, 256, 512, 16000, 'MagXiGamma', 'ResNetV2', ver='x', map_type=['DBNormalCDF', 'DBNormalCDF'], map_params=[None, None], **RES_KW)
+    dg = DeepXi(512, 256, 512, 16000, 'MagGain', 'ResNetV2', ver='maggain', gain='srwf', padding='causal', precision='f32', **RES_KW)
+    dg.set_weights(w)
+    y, nfr = dg.infer_batch(x, lens, 'y')
+    G = dg.network(inp).cpu().numpy()
+    for i, n in enumerate(nfr):
+        ref_y = osig.polar_synthesis(inp.cpu().numpy()[i, :n] * G[i, :n], dx.observation_batch(x, lens)[1].cpu().numpy()[i, :n])
+        got_y = y.cpu().numpy()[i, :(n + 1) * 256]
+        snr = 10 * np.log10(np.sum(ref_y.astype(np.float64) ** 2) / np.sum((got_y - ref_y).astype(np.float64) ** 2))
+        assert snr > 90.0, snr
+    with pytest.raises(ValueError, match='Invalid output type.'):
+        dg.infer_batch(x, lens, 'xi_hat')
+    dg.infer(x, lens, ['a', 'b'], test_epoch=7, out_path=str(tmp_path), out_type='y', gain='srwf')
+    assert (tmp_path / 'maggain' / 'e7' / 'y' / 'a.wav').exists()

@@ -199,29 +199,30 @@ def test_checkpoint_writer_round_trip(tmp_path, golden_dir):
         weights.load_checkpoint(str(model_path), 199)
 
 
-def test_committed_bench_lines_keep_the_contract():
-    """The JSON lines committed under profiles/ (written by bench.py on a B200) carry every key of the bench contract, and the
-    reference arm's line the keys of its variant; guards the contract against edits of bench.py's line assembly."""
-    import json
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    ours = json.load(open(os.path.join(root, 'profiles', 'r01_bench_f16x3_final.json')))
-    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
-              'dtype', 'data', 'config', 'clocks', 'e2e', 'gpu_launches', 'roofline', 'cpu_baseline'):
-        assert k in ours, k
-    assert ours['unit'] == 'audio-s/s' and ours['higher_is_better'] is True and ours['scaling'] == 'weak' and ours['vs_baseline'] is None
-    assert 'workload' in ours['config'] and 'model' not in ours['config'] and ours['data'] == 'synthetic'
-    assert set(('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step')) <= set(ours['e2e'])
-    assert ours['e2e']['h2d_bytes_per_step'] > 0 and ours['e2e']['d2h_bytes_per_step'] > 0 and ours['e2e']['value'] != ours['value']
-    assert set(('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic')) <= set(ours['roofline'])
-    assert abs(ours['roofline']['frac'] - ours['roofline']['achieved'] / ours['roofline']['peak']) < 1e-9
-    assert set(('value', 'unit', 'cores', 'kind', 'sample')) <= set(ours['cpu_baseline']) and ours['cpu_baseline']['kind'] == 'port'
-    assert ours['gpu_launches'] == 46 * ours['steps']          # stft, 2 x stem, 41 x stage, output layer, enhancement
-    assert ours['n_gpus'] == 1 and abs(ours['value'] - 256 * 10 * ours['steps'] / (ours['ms_per_step'] * ours['steps'] / 1e3)) < 1e-3 * ours['value']
-    assert set(('sm_mhz', 'sm_max_mhz', 'reasons')) <= set(ours['clocks'])
-    ref = json.load(open(os.path.join(root, 'profiles', 'r01_bench_reference.json')))
-    assert ref['impl'] == 'reference' and ref['metric'] == ours['metric'] and ref['unit'] == ours['unit']
-    assert ref['e2e'] == {'value': ref['value'], 'unit': ref['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
-    assert ref['cpu_baseline']['value'] == ref['value'] and ref['cpu_baseline']['kind'] == 'port'
-    for n, f in ((2, 'r01_bench_f16x3_n2_final.json'), (8, 'r01_bench_f16x3_n8_final.json')):
-        d = json.load(open(os.path.join(root, 'profiles', f)))
-        assert d['n_gpus'] == n and d['scaling'] == 'weak' and d['value'] > 0.9 * n * ours['value'] * 0.95
+def test_read_wav_follows_the_reference_rule(tmp_path):
+    """deepxi/utils.py:46-49 (the active branch): librosa.load(sr=16000, mono=True) -> * 32767 -> astype(int16).  For a 16 kHz PCM16
+    file that is trunc((x / 32768) * 32767) in float32; stereo files are averaged; another rate would be resampled by librosa,
+    which is absent here, so it raises instead of being processed at the wrong rate."""
+    import wave
+    from deepxi_b200 import utils, se_batch
+    x = np.array([0, 1, -1, 2, 1000, -1000, 32767, -32768, 12345, -23456], np.int16)
+    utils.save_wav(str(tmp_path / 'a.wav'), x, 16000)
+    got, fs = utils.read_wav(str(tmp_path / 'a.wav'))
+    want = ((x.astype(np.float32) / np.float32(32768.0)) * np.float32(32767.0)).astype(np.int16)
+    assert fs == 16000 and got.dtype == np.int16 and np.array_equal(got, want)
+    assert np.array_equal(want, [0, 0, 0, 1, 999, -999, 32766, -32767, 12344, -23455])
+    raw, _ = utils.read_wav(str(tmp_path / 'a.wav'), rule='pcm')
+    assert np.array_equal(raw, x)
+    utils.save_wav(str(tmp_path / 'b.wav'), x, 44100)
+    with pytest.raises(ValueError, match='44100'):
+        utils.read_wav(str(tmp_path / 'b.wav'))
+    (tmp_path / 'd').mkdir()
+    utils.save_wav(str(tmp_path / 'd' / 'u.wav'), x, 8000)
+    with pytest.raises(ValueError, match='8000'):
+        se_batch.Batch(str(tmp_path / 'd'), f_s=16000)
+    with wave.open(str(tmp_path / 's.wav'), 'wb') as f:      # stereo: librosa.to_mono = mean of the channels
+        f.setnchannels(2); f.setsampwidth(2); f.setframerate(16000)
+        f.writeframes(np.stack([x, x[::-1]], axis=1).astype('<i2').tobytes())
+    st, _ = utils.read_wav(str(tmp_path / 's.wav'))
+    m = (x.astype(np.float32) / np.float32(32768.0) + x[::-1].astype(np.float32) / np.float32(32768.0)) / np.float32(2)
+    assert np.array_equal(st, (m * np.float32(32767.0)).astype(np.int16))

@@ -74,3 +74,16 @@ def test_two_rank_gloo_equals_single_process():
     assert tmax == 2.0 and sorted(merged) == list(range(len(lens)))
     for i in range(len(lens)):
         assert np.array_equal(merged[i], single[i])
+
+
+@pytest.mark.gpu
+def test_two_gpus_equal_one_gpu_bit_for_bit():
+    """shard.infer_sharded over the CUDA path on 2 GPUs (one process per GPU, NCCL only gathers the outputs) must give the
+    bits of the single-GPU run.  Needs two devices: skipped on a one-GPU box (run it with `gpurun --gpus 2`, scripts/shard_check.py)."""
+    import subprocess, sys, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                        '--master-port', '29611', os.path.join(root, 'scripts', 'shard_check.py')], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'mismatching utterances: []' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
