@@ -336,6 +336,11 @@ def run_ours(args, rank, world, local_rank):
     # ---- what the host <-> device links of this box give when every rank copies at once (the e2e arm's ceiling)
     h2d_gbs, d2h_gbs = pcie_ceiling(torch, x_host, y_hosts[0], dev, barrier)
     barrier()
+    # the same with a write-combined input buffer (what a serving loop that only fills its input batches can use)
+    from deepxi_b200 import hostmem
+    x_wc = hostmem.pinned_copy(x_host, write_combined=True)
+    h2d_wc_gbs, d2h_wc_gbs = pcie_ceiling(torch, x_wc, y_hosts[0], dev, barrier)
+    barrier()
 
     # ---- sustained: the same device-resident step looped for >= 3 s (the 10-step region above is a burst of ~30 ms)
     sustained = None
@@ -354,12 +359,13 @@ def run_ours(args, rank, world, local_rank):
         sustained = (n_sus, s0.elapsed_time(s1))
         barrier()
 
-    t = torch.tensor([ms, e2e_s * 1e3, -h2d_gbs, -d2h_gbs, sustained[1] if sustained else 0.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, e2e_s * 1e3, -h2d_gbs, -d2h_gbs, sustained[1] if sustained else 0.0, -h2d_wc_gbs, -d2h_wc_gbs], dtype=torch.float64, device=dev)
     tsum = torch.tensor([h2d_gbs, d2h_gbs], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
     ms, e2e_ms, h2d_min, d2h_min, sus_ms = float(t[0]), float(t[1]), -float(t[2]), -float(t[3]), float(t[4])
+    h2d_wc_min, d2h_wc_min = -float(t[5]), -float(t[6])
 
     # ---- the other BASELINE.json configs, in the same run (single-GPU runs only: they are per-GPU figures)
     configs = extra_configs(torch, dx, it, dev, args) if (world == 1 and not args.no_extra_configs) else None
@@ -409,6 +415,7 @@ def run_ours(args, rank, world, local_rank):
                 'api': 'HostPipeline(DeepXi).submit(pinned int16 in, lens, pinned int16 out): H2D, DeepXi.infer_batch and D2H on three event-chained streams, 3 batches in flight',
                 'host_binding': numa,
                 'pcie_ceiling_gbs': {'h2d_per_gpu_min': h2d_min, 'd2h_per_gpu_min': d2h_min, 'h2d_all_gpus': float(tsum[0]), 'd2h_all_gpus': float(tsum[1]),
+                                     'with_write_combined_input': {'h2d_per_gpu_min': h2d_wc_min, 'd2h_per_gpu_min': d2h_wc_min},
                                      'how': '0.2 s of back-to-back duplex copies of the same pinned buffers, all ranks at once, CUDA events'},
                 'pcie_bound': pcie_bound, 'frac_of_pcie_bound': (e2e_value / pcie_bound) if pcie_bound else None,
                 'note': 'bound = audio per step / max(link time of a step at the measured duplex rates, device time of a step)'},

@@ -20,7 +20,7 @@ PADDINGS = {'causal': 0, 'same': 1}
 MASK_MODES = {'none': 0, 'causal+pad': 1}
 
 # every symbol include/deepxi_b200.h declares
-SYMBOLS = ['dxi_last_error', 'dxi_version', 'dxi_device_check', 'dxi_stft', 'dxi_istft', 'dxi_map_gain', 'dxi_gfunc',
+SYMBOLS = ['dxi_last_error', 'dxi_host_alloc', 'dxi_host_free', 'dxi_version', 'dxi_device_check', 'dxi_stft', 'dxi_istft', 'dxi_map_gain', 'dxi_gfunc',
            'dxi_cdf_map', 'dxi_deepmmse', 'dxi_enhance', 'dxi_net_create', 'dxi_net_load', 'dxi_net_finalize',
            'dxi_net_workspace_bytes', 'dxi_net_forward', 'dxi_net_destroy', 'dxi_launch_count',
            'dxi_launch_count_reset', 'dxi_selftest_umma', 'dxi_profile_enable', 'dxi_profile_read',
@@ -51,6 +51,10 @@ def load():
     lib.dxi_last_error.restype = ctypes.c_char_p
     lib.dxi_last_error.argtypes = []
     lib.dxi_version.restype = i32
+    lib.dxi_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t, i32]
+    lib.dxi_host_alloc.restype = i32
+    lib.dxi_host_free.argtypes = [vp]
+    lib.dxi_host_free.restype = i32
     lib.dxi_device_check.restype = i32
     lib.dxi_stft.argtypes = [vp, i32, vp, i32, i64, i32, vp, vp, vp]
     lib.dxi_istft.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, i64, vp]

@@ -84,6 +84,20 @@ int dxi_profile_read(const char* key, double* total_ms, int64_t* launches) {
   if (launches) *launches = n;
   return DXI_OK;
 }
+// Pinned host buffers for the serving loop.  write_combined = 1 (cudaHostAllocWriteCombined): memory the HOST only writes
+// sequentially and the device reads (the noisy-speech input batches): not snooped during the DMA, slow for the host to read back.
+int dxi_host_alloc(void** ptr, size_t bytes, int write_combined) {
+  if (!ptr || bytes == 0) { dxi::set_error("dxi_host_alloc: bad argument"); return DXI_E_INVALID; }
+  cudaError_t e = cudaHostAlloc(ptr, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+  if (e != cudaSuccess) return dxi::cuda_fail(e, "cudaHostAlloc");
+  return DXI_OK;
+}
+int dxi_host_free(void* ptr) {
+  if (!ptr) return DXI_OK;
+  cudaError_t e = cudaFreeHost(ptr);
+  if (e != cudaSuccess) return dxi::cuda_fail(e, "cudaFreeHost");
+  return DXI_OK;
+}
 const char* dxi_last_error(void) { return dxi::g_err; }
 int dxi_version(void) { return 100; }
 int dxi_device_check(void) { return dxi::check_device(); }

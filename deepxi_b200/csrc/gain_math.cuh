@@ -4,6 +4,7 @@
 // chain to a few ulp:  deepxi/map.py:373-390 (NormalCDF.inverse), :62-85 (db / db_inverse),
 // deepxi/gain.py:13-166 (mmse_stsa, mmse_lsa, wf, srwf, cwf, irm, ibm, deepmmse).
 #pragma once
+#include <cmath>
 #include "common.cuh"
 
 namespace dxi {
@@ -202,6 +203,59 @@ __device__ __forceinline__ float lsa_gain_from_xbar_fast(float xbar, float mu, f
   const float xi = fmaxf(fast_ex2(0.33219281f * xdb), 1e-12f);
   const float wf = xi * fast_rcp(1.0f + xi);
   return wf * fast_ex2(0.72134752f * expint_e1_fast(xi));
+}
+
+// ---- table form of the same gain -------------------------------------------------------------------------------------
+// With gamma_hat = xi_hat + 1 the MMSE-LSA gain is a function of xi_hat alone, smooth and monotone in dB:
+//   g(t) = log2 G,  G = xi / (1 + xi) * exp(E1(xi) / 2),  xi = 10^(t / 10).
+// g is tabulated as piecewise cubics (Hermite data from the analytic derivative, float64 on the host) on [LSA_TAB_LO, LSA_TAB_HI] dB
+// in steps of 0.5 dB: |2^cubic / G - 1| < 1e-7.  Below the table g follows its asymptote t log2(10)/20 - gamma_E / (2 ln 2)
+// (error < 1e-10 at -100 dB); above it G = 1 - O(1e-6).  One LDS.128 + 3 FMA + ex2 replace the E1 branches, two ex2 and an rcp.
+constexpr int LSA_TAB_N = 320;
+constexpr float LSA_TAB_LO = -100.0f, LSA_TAB_HI = 60.0f, LSA_TAB_INV_H = 2.0f;
+
+// Host: the LSA_TAB_N cubics c0 + c1 f + c2 f^2 + c3 f^3, f in [0, 1) the position inside the interval.
+static inline void lsa_table_build(float4* tab) {
+  const double h = 1.0 / LSA_TAB_INV_H, ln2 = 0.69314718055994531, ln10 = 2.3025850929940457;
+  auto gval = [&](double t, double& g, double& d) {
+    const double xi = pow(10.0, t / 10.0);
+    const double e1 = -std::expint(-xi);
+    g = (log(xi) - log1p(xi) + 0.5 * e1) / ln2;
+    d = (xi * ln10 / 10.0) * (1.0 / xi - 1.0 / (1.0 + xi) - 0.5 * exp(-xi) / xi) / ln2 * h;      // dg/dt * h
+  };
+  for (int i = 0; i < LSA_TAB_N; ++i) {
+    double g0, d0, g1, d1;
+    gval(LSA_TAB_LO + i * h, g0, d0);
+    gval(LSA_TAB_LO + (i + 1) * h, g1, d1);
+    tab[i] = make_float4((float)g0, (float)d0, (float)(3.0 * (g1 - g0) - 2.0 * d0 - d1), (float)(2.0 * (g0 - g1) + d0 + d1));
+  }
+}
+
+// The exact-order chain for the arguments the table form does not take (erfinv = +-inf, NaN: x_bar on or outside the open unit
+// interval).  Out of line on purpose: it contains a double-precision erfinv / pow and would otherwise be inlined into every unrolled
+// copy of the hot loop (3000 of the kernel's 4500 instructions, far beyond the instruction cache).
+#ifdef __CUDACC__
+#define DXI_NOINLINE __noinline__
+#else
+#define DXI_NOINLINE __attribute__((noinline))
+#endif
+static __device__ DXI_NOINLINE float lsa_gain_exact_slow(float xbar, float mu, float sigma) {
+  const float xi = xi_from_xbar(xbar, mu, sigma);
+  return gain_mmse_lsa(xi, __fadd_rn(xi, 1.0f));
+}
+
+// s2 = sigma * f32(sqrt(2)); tab: the LSA_TAB_N cubics (shared memory in the kernel).
+__device__ __forceinline__ float lsa_gain_from_xbar_tab(float xbar, float mu, float s2, float sigma, const float4* tab) {
+  const float arg = fmaf(2.0f, xbar, -1.0f);
+  if (!(fabsf(arg) < 1.0f)) return lsa_gain_exact_slow(xbar, mu, sigma);
+  const float t = fmaf(s2, erfinv_fast(arg), mu);                                   // xi_hat in dB
+  const float pos = fminf(fmaxf(fmaf(t, LSA_TAB_INV_H, -LSA_TAB_LO * LSA_TAB_INV_H), 0.0f), (float)LSA_TAB_N - 0.001f);
+  const int i = (int)pos;
+  const float f = pos - (float)i;
+  const float4 c = tab[i];
+  float g = fmaf(fmaf(fmaf(c.w, f, c.z), f, c.y), f, c.x);
+  if (t < LSA_TAB_LO) g = fmaf(fmaxf(t, -120.0f), 0.16609640f, -0.41636583f);      // xi is clamped at 1e-12 (gain.py:60)
+  return fast_ex2(g);
 }
 
 }  // namespace dxi

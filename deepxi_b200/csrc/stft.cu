@@ -22,6 +22,7 @@ __device__ float d_win[N_D];          // analysis window
 __device__ float d_swin[N_D];         // synthesis window / 256 (irfft scaling folded in)
 __device__ float2 d_tw256[256];       // e^{-2 pi j m / 256}
 __device__ float2 d_tw512[NBINS];     // e^{-2 pi j k / 512}, k = 0..256
+__device__ float4 d_lsa_tab[LSA_TAB_N];   // piecewise cubics of log2 G_LSA(xi_hat [dB]) (gain_math.cuh)
 
 static std::mutex g_tab_mutex;
 static bool g_tab_ready[64] = {};
@@ -49,6 +50,9 @@ static int ensure_tables(cudaStream_t stream) {
   DXI_CUDA(cudaMemcpyToSymbolAsync(d_swin, swin, sizeof(swin), 0, cudaMemcpyHostToDevice, stream));
   DXI_CUDA(cudaMemcpyToSymbolAsync(d_tw256, tw256, sizeof(tw256), 0, cudaMemcpyHostToDevice, stream));
   DXI_CUDA(cudaMemcpyToSymbolAsync(d_tw512, tw512, sizeof(tw512), 0, cudaMemcpyHostToDevice, stream));
+  static float4 lsa_tab[LSA_TAB_N];
+  lsa_table_build(lsa_tab);
+  DXI_CUDA(cudaMemcpyToSymbolAsync(d_lsa_tab, lsa_tab, sizeof(lsa_tab), 0, cudaMemcpyHostToDevice, stream));
   DXI_CUDA(cudaStreamSynchronize(stream));   // one-time: the host tables above are static scratch
   if (dev < 64) g_tab_ready[dev] = true;
   return DXI_OK;
@@ -191,10 +195,11 @@ __global__ void __launch_bounds__(256, 4) stft_kernel(const void* __restrict__ w
 // Synthesis
 // ----------------------------------------------------------------------------------------------
 constexpr int HOPS_PER_STRIP = 64;   // a strip recomputes one leading frame: 1/64 redundant work
+constexpr int ISTFT_CTAS_PER_SM = 4;  // 47 KB of shared memory and 64 registers per thread: the kernel is issue / latency bound, not HBM bound
 
 struct IstftSmem {
-  float2 buf[FR * FFT_FRAME_SLOTS];   // per frame: 257 spectrum values, then the FFT exchange
-  float fr[FR * N_D];                 // windowed time-domain frames
+  float2 buf[FR * FFT_FRAME_SLOTS];   // per frame: 257 spectrum values, then the FFT exchange, then (as 512 floats) the windowed time-domain frame
+  float4 lsa[LSA_TAB_N];              // MMSE-LSA gain table (MODE 2)
   float carry[N_S];                   // second half of the last frame of the previous pass
   float swin[N_D];
   float2 tw256[256];
@@ -204,7 +209,7 @@ struct IstftSmem {
 // MODE 0: gain tensor (nullable); MODE 1: fused inverse map + gain from xbar (inp_tgt.py:198-214), exact-order math, any gain
 // type; MODE 2: the same for MMSE-LSA through the MUFU-based path of gain_math.cuh (lsa_gain_from_xbar_fast)
 template <int MODE>
-__global__ void __launch_bounds__(256, 3) istft_kernel(const float* __restrict__ mag, const float* __restrict__ gain_or_xbar,
+__global__ void __launch_bounds__(256, ISTFT_CTAS_PER_SM) istft_kernel(const float* __restrict__ mag, const float* __restrict__ gain_or_xbar,
                                                     const float* __restrict__ phase, const float* __restrict__ mu,
                                                     const float* __restrict__ sigma, int gtype,
                                                     const int32_t* __restrict__ n_frames, int B, int Tmax,
@@ -216,10 +221,13 @@ __global__ void __launch_bounds__(256, 3) istft_kernel(const float* __restrict__
   for (int i = tid; i < N_D; i += 256) sm.swin[i] = d_swin[i];
   sm.tw256[tid] = d_tw256[tid];
   for (int i = tid; i < NBINS; i += 256) sm.tw512[i] = d_tw512[i];
+  if (MODE == 2)
+    for (int i = tid; i < LSA_TAB_N; i += 256) sm.lsa[i] = d_lsa_tab[i];
   __syncthreads();
 
   const int f = tid >> 4, lane16 = tid & 15;
   const int total = B * strips_per_utt;
+  auto frame_of = [&](int fi) { return reinterpret_cast<float*>(sm.buf + fi * FFT_FRAME_SLOTS); };      // windowed frame fi (512 floats)
   for (int s = blockIdx.x; s < total; s += gridDim.x) {
     const int b = s / strips_per_utt;
     const int hs = (s - b * strips_per_utt) * HOPS_PER_STRIP;      // first hop of the strip
@@ -245,7 +253,7 @@ __global__ void __launch_bounds__(256, 3) istft_kernel(const float* __restrict__
               const float xi = xi_from_xbar(gx, muv, sgv);
               m = __fmul_rn(m, gfunc_eval(gtype, xi, __fadd_rn(xi, 1.0f)));
             } else {
-              m *= lsa_gain_from_xbar_fast(gx, muv, s2v, sgv);
+              m *= lsa_gain_from_xbar_tab(gx, muv, s2v, sgv, sm.lsa);
             }
             float sn, cs;
             __sincosf(p, &sn, &cs);                                        // |p| <= pi: abs error < 5e-7
@@ -302,15 +310,17 @@ __global__ void __launch_bounds__(256, 3) istft_kernel(const float* __restrict__
       __syncwarp();
       if (f < nf) fft256_pass1<1>(v, fb, sm.tw256, lane16);
       __syncwarp();
+      if (f < nf) fft256_pass2<1>(v, fb, lane16);
+      __syncwarp();      // both frames of the warp have taken the exchange into registers: their buffers now receive the windowed frames
       if (f < nf) {
-        fft256_pass2<1>(v, fb, lane16);
         // z[m] = x[2m] + j x[2m+1], m = lane16 + 16 k2; synthesis window (x 1/256 folded in)
+        float* fr = frame_of(f);
 #pragma unroll
         for (int k2 = 0; k2 < 16; ++k2) {
           const int n = 2 * (lane16 + 16 * k2);
           float2 z = v[fft16_pos(k2)];
           float2 w = *reinterpret_cast<const float2*>(&sm.swin[n]);
-          *reinterpret_cast<float2*>(&sm.fr[f * N_D + n]) = make_float2(z.x * w.x, z.y * w.y);
+          *reinterpret_cast<float2*>(&fr[n]) = make_float2(z.x * w.x, z.y * w.y);
         }
       }
       __syncthreads();
@@ -319,13 +329,13 @@ __global__ void __launch_bounds__(256, 3) istft_kernel(const float* __restrict__
       for (int i = tid + first * N_S; i < nf * N_S; i += 256) {
         const int fi = i >> 8, n = i & 255;
         const int t = f0 + fi;
-        float y = sm.fr[fi * N_D + n] + (fi > 0 ? sm.fr[(fi - 1) * N_D + N_S + n] : sm.carry[n]);
+        float y = frame_of(fi)[n] + (fi > 0 ? frame_of(fi - 1)[N_S + n] : sm.carry[n]);
         const int64_t o = (int64_t)t * N_S + n;
         if (of) __stcs(of + o, y);
         if (oi) oi[o] = (int16_t)__float2int_rz(y * 32768.0f);   // utils.py:28 truncation
       }
       __syncthreads();
-      sm.carry[tid] = sm.fr[(nf - 1) * N_D + N_S + tid];
+      sm.carry[tid] = frame_of(nf - 1)[N_S + tid];
       __syncthreads();
     }
   }
@@ -340,7 +350,7 @@ static int istft_launch(int mode, const float* mag, const float* g_or_xbar, cons
   if (int rc = ensure_tables(st)) return rc;
   const int strips = (Tmax + 1 + HOPS_PER_STRIP - 1) / HOPS_PER_STRIP;
   const int64_t total = (int64_t)B * strips;
-  const int grid = (int)(total < 148 * 3 ? total : 148 * 3);
+  const int grid = (int)(total < 148 * ISTFT_CTAS_PER_SM ? total : 148 * ISTFT_CTAS_PER_SM);
   const size_t smem = sizeof(IstftSmem);
   ProfScope prof(mode == 0 ? "istft" : "enhance", st, 1);
   if (mode == 0) {

@@ -88,8 +88,10 @@ struct ChainArgs {
 __device__ long long* g_chain_dbg = nullptr;
 __device__ int g_chain_dbg_item = -1;
 #define CH_STAMP(k) do { if (dbgp) dbgp[b * 32 + (k)] = clock64(); } while (0)
+#define CH_TILE_STAMP(k) do { if (dbgp) dbgp[(k)] = clock64(); } while (0)      // tile-level stamps live in block 0's unused slots 24..31
 #else
 #define CH_STAMP(k) do { } while (0)
+#define CH_TILE_STAMP(k) do { } while (0)
 #endif
 
 __device__ __forceinline__ float relu(float x) { return fmaxf(x, 0.0f); }
@@ -342,6 +344,7 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
       const __half* halo_in = p.halo + ((size_t)(u * 2 + ((j + 1) & 1)) * nb) * 4096 + tid * 8;        // written by tile j - 1
       __half* halo_out = p.halo + ((size_t)(u * 2 + (j & 1)) * nb) * 4096;
 
+      CH_TILE_STAMP(24);
       // ---- tile prologue: H <- ReLU(LayerNorm(z) * gamma) of the stem pre-activation z (tcn.py:176-179); rows beyond T are zero
       {
         const float2* sp = p.stem_stats + ((size_t)tile * TILE + row) * 8;
@@ -378,6 +381,7 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
         tmem_wait_st();
         if (!has_prev && halo_mine) *reinterpret_cast<uint4*>(halo_dst) = make_uint4(0, 0, 0, 0);      // causal zero padding
       }
+      CH_TILE_STAMP(25);
       float sc = p.sc0;      // power-of-two operand scale of the row (see the header)
       for (int b = 0; b < nb; ++b, ++it) {
         const uint32_t ph = it & 1u;
@@ -490,7 +494,6 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
           float a[16];
           tmem_ld16(lane_addr + COL_D13 + 16 * qd, a); tmem_wait_ld();
           float s = 0.0f;
-#pragma unroll
           const float is2 = auxa[193];      // W2 is stored as W2 * s2
 #pragma unroll
           for (int k = 0; k < 16; ++k) { a[k] = relu(fmaf(a[k], is2, auxa[128 + 16 * qd + k])); s += a[k]; }
@@ -515,7 +518,9 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
         sc = __uint_as_float(__float_as_uint(fminf(fmaxf(inv3 * sc, 1e-30f), 1e30f)) & 0x7F800000u);
       }
       // ---- tile end: residual sum after the last block = H + B3cum_nb -> tiled buffer for the output layer
+      CH_TILE_STAMP(26);
       mbar_wait_bounded(&bars[B_W1], pw1);
+      CH_TILE_STAMP(27);
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int cc = qd + 4 * i;
@@ -530,9 +535,13 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
               valid ? make_float4(v[4 * q] + bq.x, v[4 * q + 1] + bq.y, v[4 * q + 2] + bq.z, v[4 * q + 3] + bq.w) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      CH_TILE_STAMP(28);
       tc_fence_before();
     }
     __syncthreads();      // tile end: the next item is known, B3cum / TMEM / the c1 tile are quiescent
+#ifdef DXI_ENABLE_DEBUG
+    if (dbgp && tid == 0) dbgp[29] = clock64();
+#endif
     if (warp == 17) {
       const int next = s_item[(n + 1) & 1];
       if (next < p.n_items && elect_one()) issue_w1(0);

@@ -72,6 +72,10 @@ extern "C" {
 #define DXI_MASK_CAUSAL_PAD  1   /* the mask attention.py:355-385 builds */
 
 DXI_API const char* dxi_last_error(void);
+/* Pinned host memory for the host <-> device copies of a serving loop (deepxi_b200.model.HostPipeline; the reference's counterpart
+ * is the numpy batch of deepxi/se_batch.py:12-55).  write_combined: for buffers the host only fills and the device reads. */
+DXI_API int dxi_host_alloc(void** ptr, size_t bytes, int write_combined);
+DXI_API int dxi_host_free(void* ptr);
 DXI_API int dxi_version(void);
 /* 0 when the current CUDA device can run the library (compute capability 10.x). */
 DXI_API int dxi_device_check(void);

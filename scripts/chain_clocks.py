@@ -52,3 +52,7 @@ print('  mma  %-26s +%6.0f' % ('-> next W1 wait passed', (s[2:40, 16] - s[1:39, 
 print('  GEMM3 tail: A3 chunk 7 ready (mma) -> GEMM3 done (epi): %.0f' % (blk[:, 10] - blk[:, 18]).mean())
 print('  GEMM1: c1 ready (mma) -> GEMM1 done (epi): %.0f' % (blk[:, 12] - blk[:, 19]).mean())
 print('  GEMM2: A2 ready (mma) -> first group seen by P2.0 of the next block (epi): %.0f' % (s[2:40, 2] - s[1:39, 21]).mean())
+t = s[0]
+print('  tile: prologue (stats + z load + LN + TMEM store) %d, blocks %d, wait final aux %d, read-out + store %d, tile-end barrier %d  => tile %d cycles'
+      % (t[25] - t[24], t[26] - t[25], t[27] - t[26], t[28] - t[27], t[29] - t[28], t[29] - t[24]))
+print('  first block of the tile: start -> aux landed %d (W1 of block 0 is re-loaded after the tile-end barrier)' % (s[0][1] - s[0][0]))

@@ -129,4 +129,14 @@ void host_lsa_from_xbar_fast(const float* xbar, const float* mu, const float* si
     for (int k = 0; k < bins; ++k)
       G[r * bins + k] = lsa_gain_from_xbar_fast(xbar[r * bins + k], mu[k], __fmul_rn(sigma[k], 1.41421354f), sigma[k]);
 }
+
+// the table form of the same chain (what the fused enhancement kernel runs)
+void host_lsa_from_xbar_tab(const float* xbar, const float* mu, const float* sigma, int rows, int bins, float* G) {
+  static float4 tab[LSA_TAB_N];
+  static bool ready = false;
+  if (!ready) { lsa_table_build(tab); ready = true; }
+  for (int r = 0; r < rows; ++r)
+    for (int k = 0; k < bins; ++k)
+      G[r * bins + k] = lsa_gain_from_xbar_tab(xbar[r * bins + k], mu[k], __fmul_rn(sigma[k], 1.41421354f), sigma[k], tab);
+}
 }

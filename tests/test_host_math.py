@@ -136,3 +136,8 @@ def test_fast_lsa_path_math(hostlib, xi_stats):
     ok = np.isfinite(Gref)
     assert ok.mean() > 0.99
     assert np.allclose(G[ok], Gref[ok], rtol=2e-5, atol=1e-30)      # > 90 dB on the waveform
+    # the table form the kernel runs (piecewise cubics of log2 G over xi_hat in dB): the same bound
+    Gt = np.zeros_like(xb)
+    hostlib.host_lsa_from_xbar_tab(P(xb), P(mu), P(sg), xb.shape[0], 257, P(Gt))
+    assert np.allclose(Gt[ok], Gref[ok], rtol=2e-5, atol=1e-30)
+    assert np.abs(Gt[ok] / np.maximum(G[ok], 1e-30) - 1).max() < 1e-5
