@@ -40,10 +40,10 @@ UTTS_PER_GPU = 256
 FLOP_PER_FRAME_STAGES = 40 * 2 * (256 * 64 + 3 * 64 * 64 + 64 * 256)     # the 40 residual blocks (tensor cores)
 FLOP_PER_FRAME_TOTAL = 3867648                                           # whole ResNetV2
 STFT_BYTES_PER_FRAME = 512 + 2 * 257 * 4                                 # int16 in, mag + phase out
-# tcn_chain_kernel, algorithmic HBM bytes per frame: stem pre-activation in (1024) + its row statistics (64) + residual sum out (1024)
-# + per block the 32 halo rows of c1 (fp16 hi + lo) a tile writes for, and reads from, its neighbour in the utterance (2 x 8 KB per
-# 128 frames = 128 B per frame and block).  The fp32 residual stream itself never leaves the SM.
-TCN_CHAIN_BYTES_PER_FRAME = 1024 + 64 + 1024 + 40 * 128
+# tcn_chain_kernel (whole network in one launch), algorithmic HBM bytes per frame: |X| in (1028) + x_bar out (1028) + per block the 32
+# halo rows of c1 (fp16 hi + lo) a tile writes for, and reads from, its neighbour in the utterance (2 x 8 KB per 128 frames = 128 B per
+# frame and block).  The fp32 residual stream itself never leaves the SM.
+TCN_CHAIN_BYTES_PER_FRAME = 1028 + 1028 + 40 * 128
 # dram__bytes_read.sum + dram__bytes_write.sum of the one tcn_chain_kernel<true> launch of this workload, from the committed
 # ncu --set full capture (profiles/r02_prof_tcn_chain.csv); a citation, NOT measured in the run
 NCU_TCN_CHAIN_TRAFFIC = None
@@ -384,7 +384,8 @@ def run_ours(args, rank, world, local_rank):
     st_ms, st_n = prof['tcn_chain'] if chain else prof['tcn_stage']
     st_ms_per_launch = st_ms / max(st_n, 1)
     st_per_step = st_n / max(args.steps, 1)          # 1 (depth-first kernel) or 41 (one launch per stage)
-    flops_per_launch = frames * FLOP_PER_FRAME_STAGES / max(st_per_step, 1)
+    fused = chain and prof['tcn_stem'][1] == 0      # first and output layer inside the same launch: the whole network's FLOPs
+    flops_per_launch = frames * (FLOP_PER_FRAME_TOTAL if fused else FLOP_PER_FRAME_STAGES) / max(st_per_step, 1)
     achieved_tf = flops_per_launch / (st_ms_per_launch * 1e-3) / 1e12 if st_n else None
     chain_bytes = frames * TCN_CHAIN_BYTES_PER_FRAME
     stft_ms, stft_n = prof['stft']
@@ -420,7 +421,8 @@ def run_ours(args, rank, world, local_rank):
                 'pcie_bound': pcie_bound, 'frac_of_pcie_bound': (e2e_value / pcie_bound) if pcie_bound else None,
                 'note': 'bound = audio per step / max(link time of a step at the measured duplex rates, device time of a step)'},
         'gpu_launches': launches,
-        'roofline': {'kernel': ('tcn_chain_kernel (the 40 residual blocks depth first, tcgen05 / TMEM, %g launch per step)' if chain else
+        'roofline': {'kernel': ('tcn_chain_kernel (first layer + 40 residual blocks + output layer in one launch, depth first, tcgen05 / TMEM, %g launch per step)' if fused else
+                                'tcn_chain_kernel (the 40 residual blocks depth first, tcgen05 / TMEM, %g launch per step)' if chain else
                                 'tcn_stage_kernel (tcgen05 / TMEM, %g launches per step)') % st_per_step, 'bound': 'tensor',
                      'achieved': achieved_tf, 'peak': tf_burst, 'unit': 'TFLOP/s',
                      'frac': (achieved_tf / tf_burst) if achieved_tf else None,

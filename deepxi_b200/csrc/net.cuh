@@ -22,7 +22,8 @@ struct dxi_net {
   // depth-first ResNetV2 path (tcn_chain.cu): plain fp16 hi/lo weight matrices + aux records, and the tensor maps over them
   void* d_chain = nullptr;
   size_t chain_aux_offset = 0;
-  alignas(64) unsigned char chain_tm[3][128] = {};
+  size_t chain_stem_aux_offset = 0, chain_head_aux_offset = 0;
+  alignas(64) unsigned char chain_tm[5][128] = {};      // W1, W2, W3 of the blocks; first layer; output layer
 
   const float* dev_tensor(int layer, const char* var) const {
     char name[96];
@@ -52,6 +53,8 @@ float weight_pow2_scale(const float* W, size_t n, bool half);
 int resnet_chain_prepare(dxi_net& net, cudaStream_t st);
 size_t resnet_chain_extra_workspace(const dxi_net& net, int B, int tiles);
 int resnet_chain_blocks(const dxi_net& net, float* h, const float2* stem_stats, int B, int T, void* extra, int n_sm, cudaStream_t st);
+bool resnet_chain_fused(const dxi_net& net);
+int resnet_chain_network(const dxi_net& net, const float* mag, float* xbar, int B, int T, void* extra, int n_sm, cudaStream_t st);
 int64_t mhanet_workspace_bytes(const dxi_net& net, int B, int T);
 int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xbar, void* ws, size_t ws_bytes,
                    cudaStream_t st);

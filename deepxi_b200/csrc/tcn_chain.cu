@@ -61,13 +61,25 @@ constexpr int SM_AUXA = SM_C1 + 2 * C1_PLANE;              // [2 slots][AUXA_FLO
 constexpr int SM_B3 = SM_AUXA + 2 * AUXA_FLOATS * 4;               // B3cum[256] fp32 (single buffer)
 constexpr int SM_RED = SM_B3 + 1024;                       // LayerNorm partials [2][4][128] float2
 constexpr int SM_BAR = SM_RED + 2 * NSPLIT * TILE * 8;
-enum { B_W1 = 0, B_W2, B_W3, B_A3, B_FREE = B_A3 + 8, B_D3 = B_FREE + 4, B_D1, B_D2, B_C1 = B_D2 + 4, B_A2, B_DEP, B_PUB, N_BAR };
+enum { B_W1 = 0, B_W2, B_W3, B_A3, B_FREE = B_A3 + 8, B_D3 = B_FREE + 4, B_D1, B_D2, B_C1 = B_D2 + 4, B_A2, B_DEP, B_PUB,
+       // fused first / output layer (FUSED): stem weight chunk landed (even / odd chunk), stem A chunk ready, stem chunk consumed, stem done,
+       // stem aux landed, output-layer weights landed (K chunks 0-1 / 2-3), its aux landed, its A chunk ready (x8), its N half done
+       B_SW, B_SA = B_SW + 2, B_SD, B_SDONE = B_SD + 2, B_SX, B_HW, B_HX = B_HW + 2, B_HA, B_HD = B_HA + 8, N_BAR = B_HD + 2 };
 constexpr int SM_MISC = SM_BAR + N_BAR * 8;                // tmem slot, item[2]
 constexpr int SMEM_BYTES = SM_MISC + 16;
 static_assert(SMEM_BYTES <= 232448, "shared memory map exceeds the 227 KB a CTA can have");
 constexpr int AUX_FLOATS = AUXA_FLOATS + 256, AUX_B3 = AUXA_FLOATS;      // global aux record per block: b1 | colsum(W1) | b2 | scales | B3cum
 // TMEM column map
 constexpr uint32_t COL_H = 0, COL_D13 = 256, COL_A2_HI = 320, COL_A2_LO = 352, COL_A3 = 384;
+// fused first layer: |X| as fp16 hi | lo (K = 256: 128 + 128 columns) in the columns the blocks use later; fused output layer: the
+// residual row becomes its own A operand IN PLACE (32 fp32 columns -> 16 hi + 16 lo) and the 256 output columns land in [256, 512)
+constexpr uint32_t COL_SA_HI = 256, COL_SA_LO = 384, COL_XD = 256;
+constexpr int STAGE_LD = TILE + 1;                         // transposing stage of the first layer: [64 bins][129] floats in the c1 region
+constexpr int SM_XAUX = SM_C1 + 33280;                     // above both stages: first-layer aux (b0 | W0[256,:] | gamma | 1/s0), later the output layer's (bo | Wo[:,256])
+constexpr int STEM_AUX_FLOATS = 772, HEAD_AUX_FLOATS = 516;
+constexpr int SM_OSTAGE = SM_W3, OSTAGE_LD = TILE + 1;      // output staging [128 rows][129] floats: the W3 region and the first 512 B of the c1 region
+static_assert(SM_XAUX + STEM_AUX_FLOATS * 4 <= SM_C1 + 2 * C1_PLANE && 64 * STAGE_LD * 4 <= 33280, "first-layer stage / aux overlap");
+static_assert(SM_OSTAGE + TILE * OSTAGE_LD * 4 <= SM_XAUX, "output stage overlaps the output layer's aux");
 }  // namespace chain
 
 struct ChainArgs {
@@ -80,6 +92,12 @@ struct ChainArgs {
   int* counter;                // work-item counter (zeroed by the host with the flags)
   int T, tiles_per_utt, B, n_items, n_blocks, nd;
   int zero;                    // always 0 (keeps the MMA warp's descriptors out of its loop invariants, see tcn_umma.cu)
+  // fused first / output layer (tcn_chain_kernel<.., true>): |X| in, x_bar out, h / stem_stats unused
+  const float* mag;            // [B, T, n_feat]
+  float* xbar;                 // [B, T, n_outp]
+  const float* stem_aux;       // b0[256] | W0[256, :] (the 257th input row, fp32) | gamma[256] | 1/s0, pad
+  const float* head_aux;       // bo[257] | 1/s_o | pad (260) | Wo[:, 256] (the 257th output column, fp32)
+  int n_feat, n_outp;
   float sc0;                   // operand scale of the first block: power of two next to 1 / rms(gamma) (the first layer's output is LN * gamma)
 };
 
@@ -124,10 +142,196 @@ __device__ __forceinline__ void ln_merge(float2* red, int row, int qd, float n, 
   inv = rsqrtf(m2 / (n * NSPLIT) + eps);
 }
 
-template <bool SPLIT>
+// ---- fused first / output layer, epilogue side.  Out of line on purpose: inlined, their register pressure leaks into the allocation of
+// the block loop (local-memory loads appear inside it: +7 % per block); called once per tile by all 512 epilogue threads, convergently.
+static __device__ __noinline__ uint32_t fused_first_layer(unsigned char* smem, const float* mb, int T, int n_feat, int t0, uint32_t pn, uint32_t mrg) {
+  using namespace chain;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+  float2* red = reinterpret_cast<float2*>(smem + SM_RED);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qd = warp >> 2, row = (warp & 3) * 32 + lane;
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+  const int t = t0 + row;
+  const bool valid = t < T;
+  auto warp_arrive = [&](uint64_t* bar) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar); };
+  auto epi_barrier = [&]() { asm volatile("bar.sync 1, 512;" ::: "memory"); };
+  // ---- tile prologue, fused first layer (tcn.py:166-180).  (1) |X|[128 frames, bins 0..255] -> fp16 hi | lo A operand in tensor
+  // memory, 64 bins per round through a transposing stage in the (still unused) c1 region: coalesced row loads, the next round's
+  // loads in flight while this one is split; (2) the MMA warp accumulates H = |X| W0 as the rounds arrive; (3) z = H / s0 + b0 +
+  // |X|[256] W0[256, :], LayerNorm(gamma) + ReLU over the 256 channels, written back to H in place.
+  float* stage = reinterpret_cast<float*>(smem + SM_C1);
+  float x[16], xn[16];
+  const int r0 = tid >> 6;      // this thread loads rows r0 + 8 q, bin 64 kq + (tid & 63): a warp reads 128 contiguous bytes of one row
+  const float* src = mb + (size_t)(t0 + r0) * n_feat + (tid & 63);
+  const int row_step = 8 * n_feat;
+  auto load_round = [&](int kq, float (&d)[16]) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) d[q] = (t0 + r0 + 8 * q < T) ? __ldcs(src + q * row_step + 64 * kq) : 0.0f;
+  };
+  load_round(0, x);
+#pragma unroll 1      // cold code (once per tile): kept compact, it runs at instruction-fetch speed
+  for (int kq = 0; kq < 4; ++kq) {
+    if (kq < 3) load_round(kq + 1, xn);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int i = tid + q * 512, r = i >> 6, c = i & 63;
+      stage[c * STAGE_LD + r] = x[q];
+    }
+    epi_barrier();
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      split_h2(stage[(16 * qd + 2 * k) * STAGE_LD + row], stage[(16 * qd + 2 * k + 1) * STAGE_LD + row], hi[k], lo[k]);
+    tmem_st8(lane_addr + COL_SA_HI + 32 * kq + 8 * qd, hi);
+    tmem_st8(lane_addr + COL_SA_LO + 32 * kq + 8 * qd, lo);
+    tmem_wait_st(); warp_arrive(&bars[B_SA]);
+    epi_barrier();      // every thread has read the stage: the next round may overwrite it
+#pragma unroll
+    for (int q = 0; q < 16; ++q) x[q] = xn[q];
+  }
+  const float x256 = valid ? __ldg(mb + (size_t)t * n_feat + 256) : 0.0f;
+  mbar_wait_bounded(&bars[B_SX], pn);
+  mbar_wait_bounded(&bars[B_SDONE], pn); tc_fence_after();
+  const float* xa = reinterpret_cast<const float*>(smem + SM_XAUX);      // b0 | W0[256, :] | gamma | 1/s0
+  const float is0 = xa[768];
+  float cm[2], cq[2];      // pass 1: (mean, sum of squared deviations) of z over each of this thread's two 32-channel chunks
+#pragma unroll 1
+  for (int i = 0; i < 2; ++i) {
+    const int cc = qd + 4 * i;
+    float v[32];
+    tmem_ld32(lane_addr + COL_H + 32 * cc, v); tmem_wait_ld();
+    float sm_ = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      v[k] = valid ? fmaf(v[k], is0, fmaf(x256, xa[256 + 32 * cc + k], xa[32 * cc + k])) : 0.0f;
+      sm_ += v[k];
+    }
+    const float cmi = sm_ * (1.0f / 32.0f);
+    float q2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { const float dd = v[k] - cmi; q2 = fmaf(dd, dd, q2); }
+    if (i == 0) { cm[0] = cmi; cq[0] = q2; } else { cm[1] = cmi; cq[1] = q2; }
+  }
+  float mean0, inv0;
+  {
+    const float m1 = 0.5f * (cm[0] + cm[1]), dm = cm[0] - m1;      // Chan: two chunks of 32 -> this thread's 64 channels
+    ln_merge(red + (mrg & 1) * (NSPLIT * TILE), row, qd, 64.0f, m1, cq[0] + cq[1] + 64.0f * dm * dm, 1e-6f, mean0, inv0);
+    ++mrg;
+  }
+#pragma unroll 1
+  for (int i = 0; i < 2; ++i) {      // pass 2: h0 = ReLU(LayerNorm(z) * gamma) back into H
+    const int cc = qd + 4 * i;
+    float v[32];
+    tmem_ld32(lane_addr + COL_H + 32 * cc, v); tmem_wait_ld();
+    uint32_t o[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float zz = fmaf(v[k], is0, fmaf(x256, xa[256 + 32 * cc + k], xa[32 * cc + k]));
+      const float g = inv0 * xa[512 + 32 * cc + k];
+      o[k] = __float_as_uint(valid ? relu(fmaf(zz, g, -mean0 * g)) : 0.0f);
+    }
+    tmem_st32(lane_addr + COL_H + 32 * cc, o);
+  }
+  tmem_wait_st();
+  return mrg;
+}
+
+static __device__ __noinline__ uint32_t fused_output_layer(unsigned char* smem, float* xb, int T, int n_outp, int t0, uint32_t pn, uint32_t pd2,
+                                                           uint32_t mrg) {
+  using namespace chain;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+  float2* red = reinterpret_cast<float2*>(smem + SM_RED);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qd = warp >> 2, row = (warp & 3) * 32 + lane;
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+  const int t = t0 + row;
+  const bool valid = t < T;
+  auto warp_arrive = [&](uint64_t* bar) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar); };
+  auto epi_barrier = [&]() { asm volatile("bar.sync 1, 512;" ::: "memory"); };
+  const float* sB3 = reinterpret_cast<const float*>(smem + SM_B3);
+  // ---- fused output layer (tcn.py:158-161): x_bar = sigmoid(h Wo + bo), h = H + B3cum_nb.  Pass 1: the row maximum of |h| (fp16
+  // range guard: the row is scaled by the power of two that brings it into [1, 2) and the accumulator is scaled back); pass 2: h
+  // becomes its own A operand in place (fp16 hi | lo over its 32 fp32 columns), chunk by chunk, and the 257th output column is
+  // accumulated as an fp32 dot product; then sigmoid and coalesced row stores through a staging buffer in the W3 region.
+  float mx = 0.0f;
+#pragma unroll 1
+  for (int i = 0; i < 2; ++i) {
+    const int cc = qd + 4 * i;
+    mbar_wait_bounded(&bars[B_D2 + (cc >> 1)], pd2); tc_fence_after();
+    float v[32];
+    tmem_ld32(lane_addr + COL_H + 32 * cc, v); tmem_wait_ld();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) mx = fmaxf(mx, fabsf(v[k] + sB3[32 * cc + k]));
+  }
+  {
+    float2* rb = red + (mrg & 1) * (NSPLIT * TILE);
+    ++mrg;
+    rb[qd * TILE + row] = make_float2(mx, 0.0f);
+    quarter_barrier(row >> 5);
+    mx = fmaxf(fmaxf(rb[row].x, rb[TILE + row].x), fmaxf(rb[2 * TILE + row].x, rb[3 * TILE + row].x));
+  }
+  const uint32_t ex = min(max((__float_as_uint(mx) >> 23) & 0xFFu, 1u), 253u);      // biased exponent of the row maximum
+  const float hsc = __uint_as_float((254u - ex) << 23);
+  mbar_wait_bounded(&bars[B_HX], pn);      // bo | 1/s_o | Wo[:, 256]
+  const float* ha = reinterpret_cast<const float*>(smem + SM_XAUX);
+  const float isc = __uint_as_float(ex << 23) * ha[257];
+  float d256 = 0.0f;
+#pragma unroll 1
+  for (int i = 0; i < 2; ++i) {
+    const int cc = qd + 4 * i;
+    float v[32];
+    tmem_ld32(lane_addr + COL_H + 32 * cc, v); tmem_wait_ld();
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float h0 = v[2 * k] + sB3[32 * cc + 2 * k], h1 = v[2 * k + 1] + sB3[32 * cc + 2 * k + 1];
+      d256 = fmaf(h0, ha[260 + 32 * cc + 2 * k], d256);
+      d256 = fmaf(h1, ha[260 + 32 * cc + 2 * k + 1], d256);
+      split_h2(h0 * hsc, h1 * hsc, hi[k], lo[k]);
+    }
+    tmem_st16(lane_addr + COL_H + 32 * cc, hi);
+    tmem_st16(lane_addr + COL_H + 32 * cc + 16, lo);
+    tmem_wait_st(); warp_arrive(&bars[B_HA + cc]);
+  }
+  {
+    float2* rb = red + (mrg & 1) * (NSPLIT * TILE);
+    ++mrg;
+    rb[qd * TILE + row] = make_float2(d256, 0.0f);
+    quarter_barrier(row >> 5);
+    if (qd == 0 && valid) {
+      const float z = (rb[row].x + rb[TILE + row].x) + (rb[2 * TILE + row].x + rb[3 * TILE + row].x) + ha[256];
+      xb[(size_t)t * n_outp + 256] = 1.0f / (1.0f + expf(-z));
+    }
+  }
+  mbar_wait_bounded(&bars[B_HD], pn);
+  mbar_wait_bounded(&bars[B_HD + 1], pn); tc_fence_after();      // every MMA of the tile is done: the W3 region is the output stage
+  float* ost = reinterpret_cast<float*>(smem + SM_OSTAGE);
+#pragma unroll 1
+  for (int nh = 0; nh < 2; ++nh) {
+#pragma unroll 1
+    for (int c8 = 0; c8 < 4; ++c8) {      // 8 columns at a time: a compact loop body
+      float v[8];
+      tmem_ld8(lane_addr + COL_XD + 128 * nh + 32 * qd + 8 * c8, v); tmem_wait_ld();
+      float* st = ost + row * OSTAGE_LD + 32 * qd + 8 * c8;
+      const float* bb = ha + 128 * nh + 32 * qd + 8 * c8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) st[k] = __fdividef(1.0f, 1.0f + __expf(-fmaf(v[k], isc, bb[k])));
+    }
+    epi_barrier();
+    for (int i = tid; i < TILE * 128; i += 512) {
+      const int r = i >> 7, c = i & 127;
+      if (t0 + r < T) __stcs(xb + (size_t)(t0 + r) * n_outp + 128 * nh + c, ost[r * OSTAGE_LD + c]);
+    }
+    epi_barrier();
+  }
+  return mrg;
+}
+
+template <bool SPLIT, bool FUSED>
 __global__ void __launch_bounds__(chain::THREADS, 1)
 tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
-                 const __grid_constant__ CUtensorMap tm_w3, const ChainArgs p) {
+                 const __grid_constant__ CUtensorMap tm_w3, const __grid_constant__ CUtensorMap tm_stem,
+                 const __grid_constant__ CUtensorMap tm_head, const ChainArgs p) {
   using namespace chain;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
@@ -148,6 +352,11 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
     for (int i = 0; i < 4; ++i) mbar_init(&bars[B_D2 + i], 1);
     mbar_init(&bars[B_C1], EPI_WARPS); mbar_init(&bars[B_A2], EPI_WARPS);
     mbar_init(&bars[B_DEP], 1); mbar_init(&bars[B_PUB], EPI_WARPS);
+    mbar_init(&bars[B_SW], 1); mbar_init(&bars[B_SW + 1], 1); mbar_init(&bars[B_SA], EPI_WARPS);
+    mbar_init(&bars[B_SD], 1); mbar_init(&bars[B_SD + 1], 1); mbar_init(&bars[B_SDONE], 1); mbar_init(&bars[B_SX], 1);
+    mbar_init(&bars[B_HW], 1); mbar_init(&bars[B_HW + 1], 1); mbar_init(&bars[B_HX], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&bars[B_HA + i], 4);
+    mbar_init(&bars[B_HD], 1); mbar_init(&bars[B_HD + 1], 1);
     fence_mbar_init();
   }
   tc_fence_before();
@@ -183,6 +392,28 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
       tma_load_2d(smem + SM_W3 + part * W3_PART, &tm_w3, 0, (b * 2 + part) * 256, &bars[B_W3]);
   };
 
+  // ---- fused first / output layer: weight chunks travel through the W1 / W3 regions before block 0 and after the last block
+  auto issue_stem = [&](int kc) {      // K chunk kc of W0 (hi + lo, [256 x 128 B] each) -> W1 region (kc even) / W3 region (kc odd)
+    mbar_arrive_expect_tx(&bars[B_SW + (kc & 1)], 65536u);
+    unsigned char* dst = smem + ((kc & 1) ? SM_W3 : SM_W1);
+    tma_load_2d(dst, &tm_stem, kc * 64, 0, &bars[B_SW + (kc & 1)]);
+    tma_load_2d(dst + 32768, &tm_stem, kc * 64, 256, &bars[B_SW + (kc & 1)]);
+  };
+  auto issue_stem_aux = [&]() {
+    mbar_arrive_expect_tx(&bars[B_SX], (uint32_t)(STEM_AUX_FLOATS * 4));
+    bulk_g2s(smem + SM_XAUX, p.stem_aux, STEM_AUX_FLOATS * 4, &bars[B_SX]);
+  };
+  auto issue_head = [&](int half) {      // K chunks 2 half, 2 half + 1 of Wo (hi only, [256 x 128 B] each) -> W1 region (half 0) / W3 region (half 1)
+    mbar_arrive_expect_tx(&bars[B_HW + half], 65536u);
+    unsigned char* dst = smem + (half ? SM_W3 : SM_W1);
+    tma_load_2d(dst, &tm_head, (2 * half) * 64, 0, &bars[B_HW + half]);
+    tma_load_2d(dst + 32768, &tm_head, (2 * half + 1) * 64, 0, &bars[B_HW + half]);
+  };
+  auto issue_head_aux = [&]() {
+    mbar_arrive_expect_tx(&bars[B_HX], (uint32_t)(HEAD_AUX_FLOATS * 4));
+    bulk_g2s(smem + SM_XAUX, p.head_aux, HEAD_AUX_FLOATS * 4, &bars[B_HX]);
+  };
+
   // No setmaxnreg here (tcn_umma.cu moves registers from the MMA warpgroup to the epilogue): with it ptxas keeps the MMA warp's
   // descriptor arithmetic in vector registers (13 instructions per UTCHMMA, R2UR + VOTEU for every operand) instead of the
   // uniform datapath (3-4), and this kernel is bound by that warp's issue rate; the epilogue fits the 96 registers of a 640-thread CTA.
@@ -191,7 +422,12 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
   if (warp == 17) {
     if (elect_one()) {
       tma_prefetch_desc(&tm_w1); tma_prefetch_desc(&tm_w2); tma_prefetch_desc(&tm_w3);
-      issue_w1(0); issue_w2(0); issue_w3(0);
+      if (FUSED) {      // the first layer's first two weight chunks take the W1 / W3 regions; block 0's matrices follow them
+        tma_prefetch_desc(&tm_stem); tma_prefetch_desc(&tm_head);
+        issue_stem(0); issue_stem(1); issue_w2(0);
+      } else {
+        issue_w1(0); issue_w2(0); issue_w3(0);
+      }
     }
     __syncwarp();
   }
@@ -218,6 +454,26 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
       constexpr uint32_t A_HI = desc_hi_noswz(128);
       const uint32_t e = elect_leader();
       uint32_t pw1 = (uint32_t)(n * (nb + 1)) & 1u;
+      if (FUSED) {
+        // ---- first layer (tcn.py:166-180): H = |X|[:, 0:256] W0[0:256, :], K = 256 in four chunks, fp16 hi / lo split operands on
+        // both sides (3 products: the layer the 0.1 dB budget is most sensitive to); the 257th bin is added by the epilogue in fp32
+        constexpr uint32_t id256 = make_idesc_f16(TILE, 256);
+        const uint32_t z = (uint32_t)(p.zero * n), sbase = smem_u32(smem) + z;
+#pragma unroll 1
+        for (int kc = 0; kc < 4; ++kc) {
+          mbar_wait_bounded(&bars[B_SW + (kc & 1)], (uint32_t)(kc >> 1));
+          mbar_wait_bounded(&bars[B_SA], (uint32_t)(kc & 1)); tc_fence_after();
+          const uint32_t w = desc_lo_sw128(sbase + ((kc & 1) ? SM_W3 : SM_W1));
+#pragma unroll
+          for (int part = 0; part < 3; ++part)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              mma_ts_lo<DESC_HI_SW128>(z + COL_H, z + (part == 1 ? COL_SA_LO : COL_SA_HI) + 32 * kc + 8 * ks,
+                                       w + (((part == 2 ? 32768 : 0) + ks * 32) >> 4), id256, (kc | part | ks) != 0, e);
+          mma_commit_lo(&bars[B_SD + (kc & 1)], e);      // the chunk's weight region may be re-filled
+        }
+        mma_commit_lo(&bars[B_SDONE], e);
+      }
       for (int b = 0; b < nb; ++b, ++it) {
         const uint32_t ph = it & 1u;
         // p.zero (= 0, but only the host knows) makes every operand base depend on the iteration, so that the ~130 descriptors of
@@ -289,23 +545,70 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
         CH_STAMP(22);
       }
       mbar_wait_bounded(&bars[B_W1], pw1);      // the end-of-tile aux record: keeps this warp's view of the barrier in step
+      if (FUSED) {
+        // ---- output layer (tcn.py:158-161): x_bar[:, 0:256] pre-activation = h Wo[:, 0:256]; h as fp16 hi + lo (in place over H),
+        // Wo as fp16 (2 products); two halves of 128 columns into [256, 512); the 257th column is an fp32 dot product in the epilogue
+        constexpr uint32_t id128 = make_idesc_f16(TILE, 128);
+        const uint32_t z = (uint32_t)(p.zero * n), sbase = smem_u32(smem) + z, pn = (uint32_t)n & 1u;
+        const uint32_t wa = desc_lo_sw128(sbase + SM_W1), wb = desc_lo_sw128(sbase + SM_W3);
+#pragma unroll 1
+        for (int nh = 0; nh < 2; ++nh) {
+#pragma unroll 1
+          for (int cc = 0; cc < 8; ++cc) {
+            if (nh == 0) {
+              if (cc == 0) mbar_wait_bounded(&bars[B_HW], pn);
+              if (cc == 4) mbar_wait_bounded(&bars[B_HW + 1], pn);
+              mbar_wait_bounded(&bars[B_HA + cc], pn); tc_fence_after();
+            }
+            const uint32_t w = (cc < 4 ? wa : wb) + ((((cc >> 1) & 1) * 32768 + nh * 16384 + (cc & 1) * 64) >> 4);
+#pragma unroll
+            for (int part = 0; part < 2; ++part)
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)
+                mma_ts_lo<DESC_HI_SW128>(z + COL_XD + 128 * nh, z + COL_H + 32 * cc + (part ? 16 : 0) + 8 * ks, w + ((ks * 32) >> 4), id128,
+                                         (cc | part | ks) != 0, e);
+          }
+          mma_commit_lo(&bars[B_HD + nh], e);
+        }
+      }
     } else if (warp == 17) {
       // ================= weight loader: re-fill a matrix as soon as the GEMM that reads it has committed =================
       int next = 0;
       if (lane == 0) { next = atomicAdd(p.counter, 1); s_item[(n + 1) & 1] = next; }
       next = __shfl_sync(0xffffffffu, next, 0);
       const bool more = next < p.n_items;
+      if (FUSED) {      // first layer: chunks 0, 1 are in flight (kernel prologue / end of the previous tile); the aux record, then 2, 3, then block 0
+        if (elect_one()) issue_stem_aux();
+        __syncwarp();
+        mbar_wait_bounded(&bars[B_SD], 0u);
+        if (elect_one()) issue_stem(2);
+        __syncwarp();
+        mbar_wait_bounded(&bars[B_SD + 1], 0u);
+        if (elect_one()) issue_stem(3);
+        __syncwarp();
+        mbar_wait_bounded(&bars[B_SD], 1u);
+        if (elect_one()) issue_w1(0);
+        __syncwarp();
+        mbar_wait_bounded(&bars[B_SD + 1], 1u);
+        if (elect_one()) issue_w3(0);
+        __syncwarp();
+      }
       for (int b = 0; b < nb; ++b, ++it) {
         const uint32_t ph = it & 1u;
         const bool last = b + 1 == nb;
         mbar_wait_bounded(&bars[B_D3], ph);
-        if (elect_one()) { if (!last) issue_w1(b + 1); else issue_aux_final(); }
+        if (elect_one()) { if (!last) issue_w1(b + 1); else { issue_aux_final(); if (FUSED) issue_head(0); } }
         __syncwarp();
         mbar_wait_bounded(&bars[B_D1], ph);
-        if (elect_one()) { if (!last) issue_w2(b + 1); else if (more) issue_w2(0); }
+        if (elect_one()) { if (!last) issue_w2(b + 1); else { if (more) issue_w2(0); if (FUSED) issue_head_aux(); } }
         __syncwarp();
         mbar_wait_bounded(&bars[B_D2 + 3], ph);
-        if (elect_one()) { if (!last) issue_w3(b + 1); else if (more) issue_w3(0); }
+        if (elect_one()) { if (!last) issue_w3(b + 1); else if (FUSED) issue_head(1); else if (more) issue_w3(0); }
+        __syncwarp();
+      }
+      if (FUSED) {      // the output layer has read the W1 region: the next tile's first chunk may travel (the W3 region holds the output stage)
+        mbar_wait_bounded(&bars[B_HD + 1], (uint32_t)n & 1u);
+        if (more && elect_one()) issue_stem(0);
         __syncwarp();
       }
     } else if (warp == 18) {
@@ -337,7 +640,7 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
       float2* red = reinterpret_cast<float2*>(smem + SM_RED);
       const float* sB3 = reinterpret_cast<const float*>(smem + SM_B3);
       auto warp_arrive = [&](uint64_t* bar) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bar); };
-      uint32_t pw1 = (uint32_t)(n * (nb + 1)) & 1u, pd2 = (uint32_t)(n * nb) & 1u, mrg = 0;
+      uint32_t pw1 = (uint32_t)(n * (nb + 1)) & 1u, pd2 = (uint32_t)(n * nb) & 1u, mrg = 0;      // mrg: LayerNorm merges done (alternates the two scratch buffers)
       // this thread's piece of a halo record (8 KB = 512 x 16 B): plane = tid >> 8, unit = (tid >> 5) & 7, row = tid & 31
       unsigned char* halo_dst = smem + SM_C1 + (tid >> 8) * C1_PLANE + ((tid >> 5) & 7) * C1_UNIT + (tid & 31) * 16;
       const bool halo_mine = SPLIT || tid < 256;
@@ -345,6 +648,12 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
       __half* halo_out = p.halo + ((size_t)(u * 2 + (j & 1)) * nb) * 4096;
 
       CH_TILE_STAMP(24);
+      auto epi_barrier = [&]() { asm volatile("bar.sync 1, 512;" ::: "memory"); };
+      if (FUSED) {
+        mrg = fused_first_layer(smem, p.mag + (size_t)u * p.T * p.n_feat, p.T, p.n_feat, j * TILE, (uint32_t)n & 1u, mrg);
+        epi_barrier();      // every thread is done with the aux record: the halo rows (inside it) may be zeroed, P3 may write the c1 tile
+        if (!has_prev && halo_mine) *reinterpret_cast<uint4*>(halo_dst) = make_uint4(0, 0, 0, 0);      // causal zero padding
+      } else {
       // ---- tile prologue: H <- ReLU(LayerNorm(z) * gamma) of the stem pre-activation z (tcn.py:176-179); rows beyond T are zero
       {
         const float2* sp = p.stem_stats + ((size_t)tile * TILE + row) * 8;
@@ -380,6 +689,7 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
         }
         tmem_wait_st();
         if (!has_prev && halo_mine) *reinterpret_cast<uint4*>(halo_dst) = make_uint4(0, 0, 0, 0);      // causal zero padding
+      }
       }
       CH_TILE_STAMP(25);
       float sc = p.sc0;      // power-of-two operand scale of the row (see the header)
@@ -521,6 +831,9 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
       CH_TILE_STAMP(26);
       mbar_wait_bounded(&bars[B_W1], pw1);
       CH_TILE_STAMP(27);
+      if (FUSED) {
+        mrg = fused_output_layer(smem, p.xbar + (size_t)u * p.T * p.n_outp, p.T, p.n_outp, j * TILE, (uint32_t)n & 1u, pd2, mrg);
+      } else {
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const int cc = qd + 4 * i;
@@ -535,6 +848,7 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
               valid ? make_float4(v[4 * q] + bq.x, v[4 * q + 1] + bq.y, v[4 * q + 2] + bq.z, v[4 * q + 3] + bq.w) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
+      }
       CH_TILE_STAMP(28);
       tc_fence_before();
     }
@@ -544,7 +858,7 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
 #endif
     if (warp == 17) {
       const int next = s_item[(n + 1) & 1];
-      if (next < p.n_items && elect_one()) issue_w1(0);
+      if (next < p.n_items && elect_one()) { if (FUSED) issue_stem(1); else issue_w1(0); }
       __syncwarp();
     }
   }
@@ -639,7 +953,10 @@ int resnet_chain_prepare(dxi_net& net, cudaStream_t st) {
   // global images: W1 [nb][2][64][256], W2 [nb][2][64][192], W3 [nb][2][256][64] fp16; aux [nb + 1][448] fp32
   const size_t n1 = (size_t)nb * 2 * 64 * 256, n2 = (size_t)nb * 2 * 64 * 192, n3 = (size_t)nb * 2 * 256 * 64;
   const size_t off2 = align_up(n1 * 2, 1024), off3 = off2 + align_up(n2 * 2, 1024), offa = off3 + align_up(n3 * 2, 1024);
-  const size_t total = offa + (size_t)(nb + 1) * AUX_FLOATS * 4;
+  // fused first / output layer: W0[0:256, :] as [2][256][256] fp16 (hi, lo), Wo[:, 0:256] as [256][256] fp16, and their aux records
+  const size_t offs = align_up(offa + (size_t)(nb + 1) * AUX_FLOATS * 4, 1024), offh = offs + (size_t)2 * 256 * 256 * 2;
+  const size_t offsa = offh + (size_t)256 * 256 * 2, offha = offsa + align_up(STEM_AUX_FLOATS * 4, 256);
+  const size_t total = offha + align_up(HEAD_AUX_FLOATS * 4, 256);
   std::vector<unsigned char> img(total, 0);
   __half* w1 = reinterpret_cast<__half*>(img.data());
   __half* w2 = reinterpret_cast<__half*>(img.data() + off2);
@@ -664,6 +981,32 @@ int resnet_chain_prepare(dxi_net& net, cudaStream_t st) {
     const float* b3 = net.host_tensor(li + 2, "bias")->data();
     for (int k = 0; k < 256; ++k) b3cum[k] += (double)b3[k];
   }
+  {
+    const float* W0 = net.host_tensor(0, "kernel")->data();      // [1][257][256]
+    const float* b0 = net.host_tensor(0, "bias")->data();
+    const float* gm = net.host_tensor(1, "gamma")->data();
+    __half* ws = reinterpret_cast<__half*>(img.data() + offs);
+    const float s0 = weight_pow2_scale(W0, (size_t)256 * 256, false);
+    pack_nk(ws, ws + (size_t)256 * 256, 256, 256, W0, true, nullptr, s0);
+    float* sa = reinterpret_cast<float*>(img.data() + offsa);
+    for (int k = 0; k < 256; ++k) { sa[k] = b0[k]; sa[256 + k] = W0[(size_t)256 * 256 + k]; sa[512 + k] = gm[k]; }
+    sa[768] = 1.0f / s0;
+    const int lo_ = 2 + 3 * nb;
+    const float* Wo = net.host_tensor(lo_, "kernel")->data();    // [1][256][257]
+    const float* bo = net.host_tensor(lo_, "bias")->data();
+    std::vector<float> sq((size_t)256 * 256);
+    for (int k = 0; k < 256; ++k)
+      for (int n = 0; n < 256; ++n) sq[(size_t)k * 256 + n] = Wo[(size_t)k * 257 + n];
+    const float so = weight_pow2_scale(sq.data(), sq.size(), false);
+    std::vector<__half> scratch((size_t)256 * 256);
+    pack_nk(reinterpret_cast<__half*>(img.data() + offh), scratch.data(), 256, 256, sq.data(), false, nullptr, so);
+    float* ha = reinterpret_cast<float*>(img.data() + offha);
+    for (int n = 0; n < 257; ++n) ha[n] = bo[n];
+    ha[257] = 1.0f / so;
+    for (int k = 0; k < 256; ++k) ha[260 + k] = Wo[(size_t)k * 257 + 256];
+  }
+  net.chain_stem_aux_offset = offsa;
+  net.chain_head_aux_offset = offha;
   if (net.d_chain) { cudaFree(net.d_chain); net.d_chain = nullptr; }
   DXI_CUDA(cudaMalloc(&net.d_chain, total));
   DXI_CUDA(cudaMemcpyAsync(net.d_chain, img.data(), total, cudaMemcpyHostToDevice, st));
@@ -673,6 +1016,8 @@ int resnet_chain_prepare(dxi_net& net, cudaStream_t st) {
   if (int rc = make_weight_map(net.chain_tm[0], d, 256, (size_t)nb * 2 * 64, 64)) return rc;
   if (int rc = make_weight_map(net.chain_tm[1], d + off2, 192, (size_t)nb * 2 * 64, 64)) return rc;
   if (int rc = make_weight_map(net.chain_tm[2], d + off3, 64, (size_t)nb * 2 * 256, 256)) return rc;
+  if (int rc = make_weight_map(net.chain_tm[3], d + offs, 256, (size_t)2 * 256, 256)) return rc;
+  if (int rc = make_weight_map(net.chain_tm[4], d + offh, 256, (size_t)256, 256)) return rc;
   return DXI_OK;
 }
 
@@ -680,10 +1025,14 @@ size_t resnet_chain_extra_workspace(const dxi_net& net, int B, int tiles) {
   return align_up((size_t)B * tiles * sizeof(int) + 64, 256) + (size_t)B * 2 * net.cfg.n_blocks * 8192;
 }
 
-// The residual blocks of one batch: h (tiled, stem pre-activation + stem_stats in, residual sum out).  `extra` is
-// resnet_chain_extra_workspace() bytes, 256-byte aligned; its first align_up(B * tiles * 4 + 64, 256) bytes (tile flags + work
-// counter) must have been zeroed earlier in the stream (before the stem launches, so that the launch chain stays kernel -> kernel).
-int resnet_chain_blocks(const dxi_net& net, float* h, const float2* stem_stats, int B, int T, void* extra, int n_sm, cudaStream_t st) {
+// DXI_TCN_UNFUSED=1 (A/B switch): the first and the output layer run as their own kernels (tcn_umma.cu) around the depth-first blocks.
+bool resnet_chain_fused(const dxi_net& net) {
+  static const bool off = [] { const char* v = getenv("DXI_TCN_UNFUSED"); return v && *v && *v != '0'; }();
+  return !off && resnet_chain_supported(net) && net.cfg.n_feat == 257 && net.cfg.n_outp == 257;
+}
+
+static int chain_launch(const dxi_net& net, bool fused, const float* mag, float* xbar, float* h, const float2* stem_stats, int B, int T,
+                        void* extra, int n_sm, cudaStream_t st) {
   using namespace chain;
   const dxi_net_cfg& c = net.cfg;
   const int tiles = (T + TILE - 1) / TILE;
@@ -691,8 +1040,9 @@ int resnet_chain_blocks(const dxi_net& net, float* h, const float2* stem_stats, 
   int* flags = reinterpret_cast<int*>(extra);
   int* counter = flags + (size_t)B * tiles;
   __half* halo = reinterpret_cast<__half*>(reinterpret_cast<unsigned char*>(extra) + flag_bytes);      // the caller has zeroed [extra, extra + flag_bytes)
+  const unsigned char* d = reinterpret_cast<const unsigned char*>(net.d_chain);
   ChainArgs a{};
-  a.aux = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(net.d_chain) + net.chain_aux_offset);
+  a.aux = reinterpret_cast<const float*>(d + net.chain_aux_offset);
   a.gamma = net.dev_tensor(1, "gamma");
   a.h = h; a.stem_stats = stem_stats; a.halo = halo; a.flags = flags; a.counter = counter;
   a.T = T; a.tiles_per_utt = tiles; a.B = B; a.n_items = B * tiles; a.n_blocks = c.n_blocks;
@@ -700,16 +1050,33 @@ int resnet_chain_blocks(const dxi_net& net, float* h, const float2* stem_stats, 
   for (int m = c.max_d_rate; m > 0; m >>= 1) ++a.nd;
   a.zero = 0;
   a.sc0 = resnet_first_operand_scale(net);
+  a.mag = mag; a.xbar = xbar;
+  a.stem_aux = reinterpret_cast<const float*>(d + net.chain_stem_aux_offset);
+  a.head_aux = reinterpret_cast<const float*>(d + net.chain_head_aux_offset);
+  a.n_feat = c.n_feat; a.n_outp = c.n_outp;
   const int grid = a.n_items < n_sm ? a.n_items : n_sm;
-  CUtensorMap tm[3];
+  CUtensorMap tm[5];
   memcpy(tm, net.chain_tm, sizeof(tm));
   const bool split = c.precision == DXI_PREC_F16X3;
-  auto kern = split ? tcn_chain_kernel<true> : tcn_chain_kernel<false>;
+  auto kern = fused ? (split ? tcn_chain_kernel<true, true> : tcn_chain_kernel<false, true>)
+                    : (split ? tcn_chain_kernel<true, false> : tcn_chain_kernel<false, false>);
   DXI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   ProfScope prof("tcn_chain", st, 1);
-  DXI_CUDA(launch_pdl(kern, grid, THREADS, (size_t)SMEM_BYTES, st, tm[0], tm[1], tm[2], a));
+  DXI_CUDA(launch_pdl(kern, grid, THREADS, (size_t)SMEM_BYTES, st, tm[0], tm[1], tm[2], tm[3], tm[4], a));
   DXI_LAUNCHED("tcn_chain_kernel");
   return DXI_OK;
+}
+
+// The residual blocks of one batch: h (tiled, stem pre-activation + stem_stats in, residual sum out).  `extra` is
+// resnet_chain_extra_workspace() bytes, 256-byte aligned; its first align_up(B * tiles * 4 + 64, 256) bytes (tile flags + work
+// counter) must have been zeroed earlier in the stream (before the stem launches, so that the launch chain stays kernel -> kernel).
+int resnet_chain_blocks(const dxi_net& net, float* h, const float2* stem_stats, int B, int T, void* extra, int n_sm, cudaStream_t st) {
+  return chain_launch(net, false, nullptr, nullptr, h, stem_stats, B, T, extra, n_sm, st);
+}
+
+// The whole network in one launch: |X| [B, T, 257] -> x_bar [B, T, 257] (first layer, 40 blocks, output layer; causal padding).
+int resnet_chain_network(const dxi_net& net, const float* mag, float* xbar, int B, int T, void* extra, int n_sm, cudaStream_t st) {
+  return chain_launch(net, true, mag, xbar, nullptr, nullptr, B, T, extra, n_sm, st);
 }
 
 }  // namespace dxi

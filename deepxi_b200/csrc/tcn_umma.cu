@@ -997,6 +997,8 @@ static int resnet_umma_group(const dxi_net& net, const float* mag, int B, int T,
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
   const unsigned char* images = reinterpret_cast<const unsigned char*>(net.d_umma);
+  if (chain && resnet_chain_fused(net))      // first layer, blocks and output layer in ONE launch (tcn_chain.cu)
+    return resnet_chain_network(net, mag, xbar, B, T, chain_ws, n_sm, st);
   // ---- stem (tcgen05, two 128-column halves) -> pre-activation z in the tiled buffer + partial row statistics
   {
     const size_t smem_stem = STEM_IMG_BYTES + 64 * STEM_STAGE_LD * sizeof(float) + 1024;

@@ -47,13 +47,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Same, but a wait that lasts longer than ~2 s of SM clocks is a protocol error (a missed arrival, a producer that never
 // ran): trap, so that the launch fails with an error instead of hanging the GPU.
 constexpr long long SPIN_LIMIT_CYCLES = 4000000000ll;
-__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// The retry loop is out of line: a kernel with ~25 waits per iteration would otherwise carry ~300 instructions of it in its hot loop,
+// and these kernels are sensitive to the instruction-cache footprint of that loop.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) {
   const long long t0 = clock64();
   uint32_t n = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (ok) return;
     if ((++n & 1023u) == 0 && clock64() - t0 > SPIN_LIMIT_CYCLES) __trap();
   }
+}
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(smem_u32(bar), parity);
 }
 
 // ---- bulk async copy global -> shared (TMA engine, no tensor map); bytes % 16 == 0 ---------------
@@ -132,6 +145,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// Whole-warp load of 8 consecutive fp32 columns of this thread's lane.
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
                : "memory");
 }
 // Whole-warp load of 16 consecutive fp32 columns of this thread's lane.
