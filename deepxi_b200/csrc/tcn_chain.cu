@@ -107,9 +107,15 @@ __device__ long long* g_chain_dbg = nullptr;
 __device__ int g_chain_dbg_item = -1;
 #define CH_STAMP(k) do { if (dbgp) dbgp[b * 32 + (k)] = clock64(); } while (0)
 #define CH_TILE_STAMP(k) do { if (dbgp) dbgp[(k)] = clock64(); } while (0)      // tile-level stamps live in block 0's unused slots 24..31
+#define CH_FUSED_STAMP(blk, k) do { if (dbgp) dbgp[(blk) * 32 + 24 + (k)] = clock64(); } while (0)      // ... and in blocks 1 (first layer), 2 (output layer)
+#define DXI_DBG_PARAM , long long* dbgp
+#define DXI_DBG_ARG , dbgp
 #else
 #define CH_STAMP(k) do { } while (0)
 #define CH_TILE_STAMP(k) do { } while (0)
+#define CH_FUSED_STAMP(blk, k) do { } while (0)
+#define DXI_DBG_PARAM
+#define DXI_DBG_ARG
 #endif
 
 __device__ __forceinline__ float relu(float x) { return fmaxf(x, 0.0f); }
@@ -144,7 +150,7 @@ __device__ __forceinline__ void ln_merge(float2* red, int row, int qd, float n, 
 
 // ---- fused first / output layer, epilogue side.  Out of line on purpose: inlined, their register pressure leaks into the allocation of
 // the block loop (local-memory loads appear inside it: +7 % per block); called once per tile by all 512 epilogue threads, convergently.
-static __device__ __noinline__ uint32_t fused_first_layer(unsigned char* smem, const float* mb, int T, int n_feat, int t0, uint32_t pn, uint32_t mrg) {
+static __device__ __noinline__ uint32_t fused_first_layer(unsigned char* smem, const float* mb, int T, int n_feat, int t0, uint32_t pn, uint32_t mrg DXI_DBG_PARAM) {
   using namespace chain;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
   float2* red = reinterpret_cast<float2*>(smem + SM_RED);
@@ -168,6 +174,7 @@ static __device__ __noinline__ uint32_t fused_first_layer(unsigned char* smem, c
 #pragma unroll
     for (int q = 0; q < 16; ++q) d[q] = (t0 + r0 + 8 * q < T) ? __ldcs(src + q * row_step + 64 * kq) : 0.0f;
   };
+  CH_FUSED_STAMP(1, 0);
   load_round(0, x);
 #pragma unroll 1      // cold code (once per tile): kept compact, it runs at instruction-fetch speed
   for (int kq = 0; kq < 4; ++kq) {
@@ -188,10 +195,13 @@ static __device__ __noinline__ uint32_t fused_first_layer(unsigned char* smem, c
     epi_barrier();      // every thread has read the stage: the next round may overwrite it
 #pragma unroll
     for (int q = 0; q < 16; ++q) x[q] = xn[q];
+    if (kq == 0) CH_FUSED_STAMP(1, 1);
   }
+  CH_FUSED_STAMP(1, 2);
   const float x256 = valid ? __ldg(mb + (size_t)t * n_feat + 256) : 0.0f;
   mbar_wait_bounded(&bars[B_SX], pn);
   mbar_wait_bounded(&bars[B_SDONE], pn); tc_fence_after();
+  CH_FUSED_STAMP(1, 3);
   const float* xa = reinterpret_cast<const float*>(smem + SM_XAUX);      // b0 | W0[256, :] | gamma | 1/s0
   const float is0 = xa[768];
   float cm[2], cq[2];      // pass 1: (mean, sum of squared deviations) of z over each of this thread's two 32-channel chunks
@@ -212,6 +222,7 @@ static __device__ __noinline__ uint32_t fused_first_layer(unsigned char* smem, c
     for (int k = 0; k < 32; ++k) { const float dd = v[k] - cmi; q2 = fmaf(dd, dd, q2); }
     if (i == 0) { cm[0] = cmi; cq[0] = q2; } else { cm[1] = cmi; cq[1] = q2; }
   }
+  CH_FUSED_STAMP(1, 4);
   float mean0, inv0;
   {
     const float m1 = 0.5f * (cm[0] + cm[1]), dm = cm[0] - m1;      // Chan: two chunks of 32 -> this thread's 64 channels
@@ -233,11 +244,12 @@ static __device__ __noinline__ uint32_t fused_first_layer(unsigned char* smem, c
     tmem_st32(lane_addr + COL_H + 32 * cc, o);
   }
   tmem_wait_st();
+  CH_FUSED_STAMP(1, 5);
   return mrg;
 }
 
 static __device__ __noinline__ uint32_t fused_output_layer(unsigned char* smem, float* xb, int T, int n_outp, int t0, uint32_t pn, uint32_t pd2,
-                                                           uint32_t mrg) {
+                                                           uint32_t mrg DXI_DBG_PARAM) {
   using namespace chain;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
   float2* red = reinterpret_cast<float2*>(smem + SM_RED);
@@ -270,6 +282,7 @@ static __device__ __noinline__ uint32_t fused_output_layer(unsigned char* smem, 
     quarter_barrier(row >> 5);
     mx = fmaxf(fmaxf(rb[row].x, rb[TILE + row].x), fmaxf(rb[2 * TILE + row].x, rb[3 * TILE + row].x));
   }
+  CH_FUSED_STAMP(2, 0);
   const uint32_t ex = min(max((__float_as_uint(mx) >> 23) & 0xFFu, 1u), 253u);      // biased exponent of the row maximum
   const float hsc = __uint_as_float((254u - ex) << 23);
   mbar_wait_bounded(&bars[B_HX], pn);      // bo | 1/s_o | Wo[:, 256]
@@ -303,8 +316,10 @@ static __device__ __noinline__ uint32_t fused_output_layer(unsigned char* smem, 
       xb[(size_t)t * n_outp + 256] = 1.0f / (1.0f + expf(-z));
     }
   }
+  CH_FUSED_STAMP(2, 1);
   mbar_wait_bounded(&bars[B_HD], pn);
-  mbar_wait_bounded(&bars[B_HD + 1], pn); tc_fence_after();      // every MMA of the tile is done: the W3 region is the output stage
+  mbar_wait_bounded(&bars[B_HD + 1], pn); tc_fence_after();
+  CH_FUSED_STAMP(2, 2);      // every MMA of the tile is done: the W3 region is the output stage
   float* ost = reinterpret_cast<float*>(smem + SM_OSTAGE);
 #pragma unroll 1
   for (int nh = 0; nh < 2; ++nh) {
@@ -318,9 +333,20 @@ static __device__ __noinline__ uint32_t fused_output_layer(unsigned char* smem, 
       for (int k = 0; k < 8; ++k) st[k] = __fdividef(1.0f, 1.0f + __expf(-fmaf(v[k], isc, bb[k])));
     }
     epi_barrier();
-    for (int i = tid; i < TILE * 128; i += 512) {
-      const int r = i >> 7, c = i & 127;
-      if (t0 + r < T) __stcs(xb + (size_t)(t0 + r) * n_outp + 128 * nh + c, ost[r * OSTAGE_LD + c]);
+    if (nh == 0) CH_FUSED_STAMP(2, 3);
+    {      // 128 rows x 128 columns: a warp writes 128 contiguous bytes of one row; four rows per iteration in flight
+      const int c = tid & 127, r0 = tid >> 7;
+      float* dst = xb + (size_t)(t0 + r0) * n_outp + 128 * nh + c;
+      const float* srcp = ost + r0 * OSTAGE_LD + c;
+#pragma unroll 1
+      for (int rr = 0; rr < TILE; rr += 16) {
+        float y[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) y[q] = srcp[(rr + 4 * q) * OSTAGE_LD];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (t0 + r0 + rr + 4 * q < T) __stcs(dst + (size_t)(rr + 4 * q) * n_outp, y[q]);
+      }
     }
     epi_barrier();
   }
@@ -577,6 +603,19 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
       if (lane == 0) { next = atomicAdd(p.counter, 1); s_item[(n + 1) & 1] = next; }
       next = __shfl_sync(0xffffffffu, next, 0);
       const bool more = next < p.n_items;
+      if (FUSED && more) {
+        // the next tile's 128 rows of |X| are one contiguous run (131 KB): pull them into L2 now, so that its first-layer rounds
+        // load at L2 latency instead of HBM latency (32 lanes x 4 KB, 16-byte aligned pieces)
+        const int jn = next / p.B, un = next - jn * p.B;
+        const int rows = min(TILE, p.T - jn * TILE);
+        const uintptr_t lo_a = reinterpret_cast<uintptr_t>(p.mag + ((size_t)un * p.T + (size_t)jn * TILE) * p.n_feat) & ~(uintptr_t)15;
+        const uintptr_t hi_a = (reinterpret_cast<uintptr_t>(p.mag + ((size_t)un * p.T + (size_t)jn * TILE + rows) * p.n_feat) + 15) & ~(uintptr_t)15;
+        for (uintptr_t a = lo_a + (uintptr_t)lane * 4096; a < hi_a; a += 32 * 4096) {
+          const uint32_t nbytes = (uint32_t)(hi_a - a < 4096 ? hi_a - a : 4096);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(nbytes) : "memory");
+        }
+        __syncwarp();
+      }
       if (FUSED) {      // first layer: chunks 0, 1 are in flight (kernel prologue / end of the previous tile); the aux record, then 2, 3, then block 0
         if (elect_one()) issue_stem_aux();
         __syncwarp();
@@ -650,7 +689,7 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
       CH_TILE_STAMP(24);
       auto epi_barrier = [&]() { asm volatile("bar.sync 1, 512;" ::: "memory"); };
       if (FUSED) {
-        mrg = fused_first_layer(smem, p.mag + (size_t)u * p.T * p.n_feat, p.T, p.n_feat, j * TILE, (uint32_t)n & 1u, mrg);
+        mrg = fused_first_layer(smem, p.mag + (size_t)u * p.T * p.n_feat, p.T, p.n_feat, j * TILE, (uint32_t)n & 1u, mrg DXI_DBG_ARG);
         epi_barrier();      // every thread is done with the aux record: the halo rows (inside it) may be zeroed, P3 may write the c1 tile
         if (!has_prev && halo_mine) *reinterpret_cast<uint4*>(halo_dst) = make_uint4(0, 0, 0, 0);      // causal zero padding
       } else {
@@ -832,7 +871,7 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
       mbar_wait_bounded(&bars[B_W1], pw1);
       CH_TILE_STAMP(27);
       if (FUSED) {
-        mrg = fused_output_layer(smem, p.xbar + (size_t)u * p.T * p.n_outp, p.T, p.n_outp, j * TILE, (uint32_t)n & 1u, pd2, mrg);
+        mrg = fused_output_layer(smem, p.xbar + (size_t)u * p.T * p.n_outp, p.T, p.n_outp, j * TILE, (uint32_t)n & 1u, pd2, mrg DXI_DBG_ARG);
       } else {
 #pragma unroll
       for (int i = 0; i < 2; ++i) {

@@ -56,3 +56,9 @@ t = s[0]
 print('  tile: prologue (stats + z load + LN + TMEM store) %d, blocks %d, wait final aux %d, read-out + store %d, tile-end barrier %d  => tile %d cycles'
       % (t[25] - t[24], t[26] - t[25], t[27] - t[26], t[28] - t[27], t[29] - t[28], t[29] - t[24]))
 print('  first block of the tile: start -> aux landed %d (W1 of block 0 is re-loaded after the tile-end barrier)' % (s[0][1] - s[0][0]))
+f1, f2 = s[1][24:32], s[2][24:32]
+if f1[0]:
+    print('  first layer: round 0 %d, rounds 1-3 %d, wait aux + MMA done %d, statistics pass %d, merge + write-back pass %d'
+          % (f1[1] - f1[0], f1[2] - f1[1], f1[3] - f1[2], f1[4] - f1[3], f1[5] - f1[4]))
+    print('  output layer: max pass + merge %d (from tile-end stamp), convert pass + 257th column %d, wait MMAs %d, sigmoid half 0 %d, stores + half 1 %d'
+          % (f2[0] - s[0][27], f2[1] - f2[0], f2[2] - f2[1], f2[3] - f2[2], s[0][28] - f2[3]))
