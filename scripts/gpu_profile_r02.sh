@@ -1,17 +1,16 @@
 #!/bin/bash
-# Round-2 ncu evidence for profiles/: (1) launch list with per-launch device time of one bench step, (2) --set full captures of the
-# depth-first TCN kernel and of the signal / stem / output-layer kernels.  Plain run first (same command line), as the recipe asks.
+# Round-2 ncu evidence for profiles/: (1) launch list with per-launch device time of one bench step (3 launches: stft, the network,
+# map + gain + istft), (2) --set full captures of the network kernel and of the two signal kernels.  Plain run first, as the recipe asks.
 set -u
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
 CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-sustained --no-extra-configs"
 $CMD > gpurun_out/prof_plain.json 2> gpurun_out/prof_plain.err || { echo "plain run failed"; tail -20 gpurun_out/prof_plain.err; exit 1; }
 echo "plain ok"
-# 6 launches per step (stft, 2 stem, chain, head, enhance): skip the 3 warm-up steps, list the timed step
-ncu --metrics gpu__time_duration.sum --clock-control none -s 18 -c 6 --csv --log-file gpurun_out/r02_launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 9 -c 3 --csv --log-file gpurun_out/r02_launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:tcn_chain -s 3 -c 1 -o gpurun_out/r02_prof_tcn_chain -f $CMD > gpurun_out/ncu_tcn.log 2>&1
 echo "tcn full rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:"stft_kernel|istft_kernel|stem_umma|head_umma" -s 12 -c 5 -o gpurun_out/r02_prof_signal -f $CMD > gpurun_out/ncu_signal.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"stft_kernel|istft_kernel" -s 6 -c 2 -o gpurun_out/r02_prof_signal -f $CMD > gpurun_out/ncu_signal.log 2>&1
 echo "signal full rc=$?"
-ls -la gpurun_out | head -40
+ls -la gpurun_out | head -30
