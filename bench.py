@@ -46,7 +46,7 @@ STFT_BYTES_PER_FRAME = 512 + 2 * 257 * 4                                 # int16
 TCN_CHAIN_BYTES_PER_FRAME = 1028 + 1028 + 40 * 128
 # dram__bytes_read.sum + dram__bytes_write.sum of the one tcn_chain_kernel<true> launch of this workload, from the committed
 # ncu --set full capture (profiles/r02_prof_tcn_chain.csv); a citation, NOT measured in the run
-NCU_TCN_CHAIN_TRAFFIC = None
+NCU_TCN_CHAIN_TRAFFIC = 1235.4e6      # 732.3 MB read + 503.1 MB written
 MHA_KW = dict(d_model=256, n_blocks=5, n_heads=8, warmup_steps=40000, max_len=2048, causal=1, outp_act='Sigmoid')
 RES_KW = dict(d_model=256, n_blocks=40, d_f=64, k=3, max_d_rate=16, unit_type='ReLU->LN->W+b', outp_act='Sigmoid')
 

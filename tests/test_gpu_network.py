@@ -67,6 +67,8 @@ def test_resnetv2_forward_vs_oracle(xi_stats, padding, precision, tol_db):
         assert np.median(err) < 0.1
     else:
         assert err.max() < 0.1
+    if precision == 'f16x3':      # measured on B200: median 0.0016, p99 0.0065, max 0.012 dB; the distribution is asserted at 3x
+        assert np.median(err) < 5e-3 and np.percentile(err, 99) < 2e-2, (np.median(err), np.percentile(err, 99))
 
 
 @pytest.mark.parametrize('kind', ['ResNet', 'ResNetV3'])
@@ -422,3 +424,30 @@ def test_deepmmse_and_maggain_through_deepxi(xi_stats, tmp_path):
         dg.infer_batch(x, lens, 'xi_hat')
     dg.infer(x, lens, ['a', 'b'], test_epoch=7, out_path=str(tmp_path), out_type='y', gain='srwf')
     assert (tmp_path / 'maggain' / 'e7' / 'y' / 'a.wav').exists()
+
+
+def test_two_forwards_on_two_streams_do_not_interfere(xi_stats):
+    """The depth-first kernel's CTAs wait for each other (a tile needs its predecessor's halo rows); work items are claimed from an
+    atomic counter so that an item only ever waits for one a RUNNING CTA holds.  Two forward passes enqueued on two streams therefore
+    may share the SMs in any proportion without deadlock (every wait is bounded: a violation would trap), and each must give the bits
+    of its own sequential run (separate workspaces per stream)."""
+    w = weights.synthetic_resnetv2(0)
+    net = network_selector('ResNetV2', None, 257, padding='causal', precision='f16x3', **RES_KW).load_weights(w)
+    from deepxi_b200.inp_tgt import inp_tgt_selector
+    it = inp_tgt_selector('MagXi', 512, 256, 512, 16000, map_type='DBNormalCDF', map_params=None)
+    xa = np.tile(synth.noisy_speech(4, 160000, seed=91), (25, 1))      # 100 utterances x 5 tiles: 3.4 rounds of work items
+    xb = np.tile(synth.noisy_speech(3, 70000, seed=92), (11, 1))       # 33 utterances x 3 tiles: fewer items than SMs
+    inp_a, _, _ = it.observation_batch(torch.from_numpy(xa).cuda(), [160000] * 100)
+    inp_b, _, _ = it.observation_batch(torch.from_numpy(xb).cuda(), [70000 - 999 * (i % 4) for i in range(33)])
+    ref_a, ref_b = net(inp_a).clone(), net(inp_b).clone()
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            ya = net(inp_a)
+        with torch.cuda.stream(s2):
+            yb = net(inp_b)
+        with torch.cuda.stream(s1):
+            ya2 = net(inp_a)
+        torch.cuda.synchronize()
+        assert torch.equal(ya, ref_a) and torch.equal(yb, ref_b) and torch.equal(ya2, ref_a)
