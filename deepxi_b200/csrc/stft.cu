@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(256, ISTFT_CTAS_PER_SM) istft_kernel(const flo
         };
         const int k = tid;
         if (MODE != 0) { mu_k = __ldg(mu + k); sg_k = __ldg(sigma + k); s2_k = __fmul_rn(sg_k, 1.41421354f); }
-        constexpr int NU = 4;      // frames per iteration: 3 NU loads in flight per thread
+        constexpr int NU = 4;      // frames per iteration: 3 NU loads in flight per thread (NU = 2 has no spills at 64 registers but is 8 % slower)
         for (int fi = 0; fi < nf; fi += NU) {
           float mv[NU], pv[NU], gv[NU];
           bool ok[NU];

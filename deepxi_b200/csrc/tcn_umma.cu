@@ -957,6 +957,8 @@ constexpr int g_dbg_stop_after = -1;
 
 int64_t resnet_umma_workspace_bytes(const dxi_net& net, int B, int T) {
   const int tiles = (T + TILE - 1) / TILE;
+  if (resnet_chain_fused(net))      // one launch, residual tile in tensor memory: only the tile flags, the work counter and the halo records
+    return (int64_t)(512 + resnet_chain_extra_workspace(net, B, tiles));
   const size_t Ts = (size_t)tiles * TILE + 2 * C1_PAD;
   const size_t h_bytes = (size_t)B * tiles * TILE * 256 * 4;
   const size_t c1_bytes = align_up((size_t)B * 2 * 8 * Ts * 16, 256);
@@ -980,6 +982,12 @@ static int resnet_umma_group(const dxi_net& net, const float* mag, int B, int T,
   const size_t flag_bytes = align_up((size_t)B * tiles * sizeof(int), 256);
   int* flags = reinterpret_cast<int*>(base + h_bytes + 2 * c1_bytes);
   float2* stem_stats = reinterpret_cast<float2*>(base + h_bytes + 2 * c1_bytes + flag_bytes);
+  if (resnet_chain_fused(net)) {      // first layer, blocks and output layer in ONE launch (tcn_chain.cu)
+    int n_sm_ = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm_, cudaDevAttrMultiProcessorCount, dev); }
+    DXI_CUDA(cudaMemsetAsync(base, 0, align_up((size_t)B * tiles * sizeof(int) + 64, 256), st));      // tile flags + work counter
+    return resnet_chain_network(net, mag, xbar, B, T, base, n_sm_, st);
+  }
   const bool chain = resnet_chain_supported(net);      // causal padding: depth-first residual blocks (tcn_chain.cu)
   const size_t stats_bytes = (size_t)B * tiles * TILE * 8 * sizeof(float2);
   unsigned char* chain_ws = reinterpret_cast<unsigned char*>(align_up(reinterpret_cast<uintptr_t>(base + h_bytes + 2 * c1_bytes + flag_bytes + stats_bytes), 256));
@@ -997,8 +1005,6 @@ static int resnet_umma_group(const dxi_net& net, const float* mag, int B, int T,
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
   const unsigned char* images = reinterpret_cast<const unsigned char*>(net.d_umma);
-  if (chain && resnet_chain_fused(net))      // first layer, blocks and output layer in ONE launch (tcn_chain.cu)
-    return resnet_chain_network(net, mag, xbar, B, T, chain_ws, n_sm, st);
   // ---- stem (tcgen05, two 128-column halves) -> pre-activation z in the tiled buffer + partial row statistics
   {
     const size_t smem_stem = STEM_IMG_BYTES + 64 * STEM_STAGE_LD * sizeof(float) + 1024;
