@@ -125,6 +125,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
   } else if (warp == L_PROD_WARPS + 4) {
     // ================= MMA issue =================
     constexpr uint32_t idesc = make_idesc_f16(LM, LNT);
+    const uint32_t e = elect_leader();      // issue path as in tcn_chain.cu: one election, 32-bit descriptor words in uniform registers
+    const uint32_t ring_a = smem_u32(ring);
     int gch = 0, lt = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
       const int buf = lt & 1, u = lt >> 1;
@@ -135,18 +137,17 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
         mbar_wait(&full_a[slot], use & 1);
         mbar_wait(&full_w[slot], use & 1);
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(ring + slot * L_SLOT), a_lo = a_hi + LA_PART, w_hi = a_hi + 2 * LA_PART, w_lo = w_hi + LW_PART;
+        const uint32_t a32 = desc_lo_sw128(ring_a + slot * L_SLOT), w32 = desc_lo_sw128(ring_a + slot * L_SLOT + 2 * LA_PART);
 #pragma unroll
-        for (int part = 0; part < 3; ++part) {
-          const uint32_t a0 = part == 1 ? a_lo : a_hi, w0 = part == 2 ? w_lo : w_hi;
+        for (int part = 0; part < 3; ++part)
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks)
-            mma_ss_elect(d_col, make_smem_desc_sw128(a0 + ks * 32), make_smem_desc_sw128(w0 + ks * 32), idesc,
-                         (kc > 0 || part > 0 || ks > 0) ? 1u : 0u);
-        }
-        mma_commit_elect(&empty[slot]);
+            mma_ss_lo<DESC_HI_SW128, DESC_HI_SW128>(d_col, a32 + (((part == 1 ? LA_PART : 0) + ks * 32) >> 4),
+                                                     w32 + (((part == 2 ? LW_PART : 0) + ks * 32) >> 4), idesc,
+                                                     (kc > 0 || part > 0 || ks > 0) ? 1u : 0u, e);
+        mma_commit_lo(&empty[slot], e);
       }
-      mma_commit_elect(&acc_full[buf]);
+      mma_commit_lo(&acc_full[buf], e);
     }
   } else {
     // ================= epilogue (warps 8-11: TMEM lane quarter = warp & 3) =================
