@@ -313,7 +313,8 @@ def run_ours(args, rank, world, local_rank):
     # HostPipeline chains H2D -> kernels -> D2H of every step over three streams so that the PCIe copies of one step overlap the
     # kernels of its neighbours; every step still copies its whole input in and its whole result out.
     from deepxi_b200.model import HostPipeline
-    pipe = HostPipeline(dx, n_streams=3)
+    n_sub, n_cs = int(os.environ.get('DXI_E2E_SUB', '2')), int(os.environ.get('DXI_E2E_CS', '2'))
+    pipe = HostPipeline(dx, n_streams=3, n_sub=n_sub, n_compute=n_cs)
     y_hosts = [torch.empty((B, (T + 1) * 256), dtype=torch.int16).pin_memory() for _ in range(3)]
     for i in range(max(6, args.warmup)):          # two rounds per stream: the allocator pools of all streams settle
         pipe.submit(x_host, lens, y_hosts[i % 3])
@@ -413,7 +414,8 @@ def run_ours(args, rank, world, local_rank):
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': 'audio-s/s',
                 'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
-                'api': 'HostPipeline(DeepXi).submit(pinned int16 in, lens, pinned int16 out): H2D, DeepXi.infer_batch and D2H on three event-chained streams, 3 batches in flight',
+                'api': 'HostPipeline(DeepXi).submit(pinned int16 in, lens, pinned int16 out): H2D, DeepXi.infer_batch and D2H on event-chained streams, 3 batches in flight, '
+                       'each batch as %d sub-batches alternating over %d compute streams' % (n_sub, n_cs),
                 'host_binding': numa,
                 'pcie_ceiling_gbs': {'h2d_per_gpu_min': h2d_min, 'd2h_per_gpu_min': d2h_min, 'h2d_all_gpus': float(tsum[0]), 'd2h_all_gpus': float(tsum[1]),
                                      'with_write_combined_input': {'h2d_per_gpu_min': h2d_wc_min, 'd2h_per_gpu_min': d2h_wc_min},
