@@ -1,5 +1,6 @@
-// ResNetV2 (causal) residual blocks, DEPTH FIRST: one CTA takes a tile of 128 frames through all n_blocks blocks while the
-// tile's fp32 residual stream never leaves the SM.  Restates deepxi/network/tcn.py:182-223 (block / unit), :156-157 (dilation cycle).
+// ResNetV2 (causal), DEPTH FIRST: one CTA takes a tile of 128 frames through the first layer, all n_blocks residual blocks and the
+// output layer while the tile's fp32 residual stream never leaves the SM -- the whole network is ONE launch.  Restates
+// deepxi/network/tcn.py:166-180 (first layer), :182-223 (block / unit), :156-157 (dilation cycle), :158-161 (output layer).
 //
 // Why.  The stage-per-launch formulation (tcn_umma.cu: tcn_stage_kernel, kept for padding='same') moves the fp32 residual
 // stream through HBM once per block: 2560 B per frame and block, 15.8 GB per forward of 256 x 10 s against 0.33 GB of
@@ -33,9 +34,17 @@
 // loads them.  An item only ever waits for an item that was claimed earlier by a CTA that is already running, so the scheme
 // cannot deadlock whatever the residency of the grid.
 //
-// Warps 0-15 epilogue (thread = (row, column quarter), as in tcn_umma.cu), 16 MMA issue, 17 weight loader (TMA) + work claims,
-// 18 flag agent, 19 idle (completes the warpgroup setmaxnreg takes registers from).  Every wait is bounded: a protocol error
-// traps instead of hanging the GPU.
+// First and output layer (template flag FUSED; without it the kernel runs the blocks only, between the stem / output-layer kernels
+// of tcn_umma.cu).  Per tile |X| becomes the first layer's fp16 hi | lo A operand in TMEM [256,512) through a transposing stage in
+// the still unused c1 region, W0 streams in four 64 KB chunks through the W1 / W3 regions ahead of block 0, LayerNorm(gamma) +
+// ReLU are applied to the accumulator in place.  After the last block the residual row becomes the output layer's A operand in
+// place (32 fp32 columns -> 16 hi + 16 lo), Wo streams into the W1 / W3 regions as they become free, the accumulator goes to
+// [256,512), and sigmoid rows leave through a staging buffer in the W3 region as coalesced stores.  The 257th input bin and the
+// 257th output column stay fp32 (rank-1 term / dot product in the epilogue).
+//
+// Warps 0-15 epilogue (thread = (row, column quarter), as in tcn_umma.cu), 16 MMA issue, 17 weight loader (TMA) + work claims +
+// L2 prefetch of the next tile's |X| rows, 18 flag agent, 19 idle.  No setmaxnreg (see the kernel).  Every wait is bounded: a
+// protocol error traps instead of hanging the GPU.
 #include <cuda.h>
 #include <cstdlib>
 #include <cmath>
