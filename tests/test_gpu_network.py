@@ -451,3 +451,12 @@ def test_two_forwards_on_two_streams_do_not_interfere(xi_stats):
             ya2 = net(inp_a)
         torch.cuda.synchronize()
         assert torch.equal(ya, ref_a) and torch.equal(yb, ref_b) and torch.equal(ya2, ref_a)
+
+
+def test_one_launch_network_over_random_shapes():
+    """scripts/chain_stress.py on 16 random batch shapes (1 .. 7 tiles per utterance, ragged lengths, fewer / more work items than
+    SMs): bit-repeatable, independent of the batch composition, within 0.05 dB of the exact fp32 CUDA-core path, no trap."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'scripts', 'chain_stress.py'), '16', '7'], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and 'chain_stress: 16 shapes ok' in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
