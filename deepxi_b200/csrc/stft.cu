@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(256, 4) stft_kernel(const void* __restrict__ w
 // ----------------------------------------------------------------------------------------------
 // Synthesis
 // ----------------------------------------------------------------------------------------------
-constexpr int HOPS_PER_STRIP = 64;   // a strip recomputes one leading frame: 1/64 redundant work
+constexpr int HOPS_PER_STRIP_MAX = 256;   // a strip of h hops recomputes one leading frame (1/h redundant work); h is chosen per launch, see istft_launch
 constexpr int ISTFT_CTAS_PER_SM = 4;  // 47 KB of shared memory and 64 registers per thread: the kernel is issue / latency bound, not HBM bound
 
 struct IstftSmem {
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(256, ISTFT_CTAS_PER_SM) istft_kernel(const flo
                                                     const float* __restrict__ phase, const float* __restrict__ mu,
                                                     const float* __restrict__ sigma, int gtype,
                                                     const int32_t* __restrict__ n_frames, int B, int Tmax,
-                                                    int strips_per_utt, float* __restrict__ wav_f32,
+                                                    int strips_per_utt, int hops_per_strip, float* __restrict__ wav_f32,
                                                     int16_t* __restrict__ wav_i16, int64_t out_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   IstftSmem& sm = *reinterpret_cast<IstftSmem*>(smem_raw);
@@ -230,8 +230,8 @@ __global__ void __launch_bounds__(256, ISTFT_CTAS_PER_SM) istft_kernel(const flo
   auto frame_of = [&](int fi) { return reinterpret_cast<float*>(sm.buf + fi * FFT_FRAME_SLOTS); };      // windowed frame fi (512 floats)
   for (int s = blockIdx.x; s < total; s += gridDim.x) {
     const int b = s / strips_per_utt;
-    const int hs = (s - b * strips_per_utt) * HOPS_PER_STRIP;      // first hop of the strip
-    const int he = min(hs + HOPS_PER_STRIP, Tmax + 1);              // hops hs..he-1; hop h = tail(h-1) + head(h)
+    const int hs = (s - b * strips_per_utt) * hops_per_strip;      // first hop of the strip
+    const int he = min(hs + hops_per_strip, Tmax + 1);              // hops hs..he-1; hop h = tail(h-1) + head(h)
     int T = n_frames ? min(n_frames[b], Tmax) : Tmax;
     const int64_t in0 = (int64_t)b * Tmax * NBINS;
     float* of = wav_f32 ? wav_f32 + (int64_t)b * out_stride : nullptr;
@@ -348,22 +348,38 @@ static int istft_launch(int mode, const float* mag, const float* g_or_xbar, cons
                         const float* sigma, int gtype, const int32_t* n_frames, int B, int Tmax, float* wav_f32,
                         int16_t* wav_i16, int64_t out_stride, cudaStream_t st) {
   if (int rc = ensure_tables(st)) return rc;
-  const int strips = (Tmax + 1 + HOPS_PER_STRIP - 1) / HOPS_PER_STRIP;
+  // Strip length: the persistent CTAs walk B * ceil((Tmax + 1) / h) strips of h hops (+ one recomputed leading frame each) in rounds;
+  // h minimises rounds x (cost of a strip), i.e. the ragged last round is kept full (C2: 592 CTAs, h = 64 gave 5 rounds of which the
+  // last was a third full; h = 70 gives 4 full ones).  A strip costs its frames in the per-bin spectrum phase (57 % of the kernel) and
+  // whole passes of FR frames in the FFT / overlap-add phases.
+  int n_sm = 148;
+  { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+  const int64_t cap = (int64_t)n_sm * ISTFT_CTAS_PER_SM;
+  int hops = 64;
+  {
+    int64_t best = -1;
+    for (int h = 16; h <= HOPS_PER_STRIP_MAX; ++h) {
+      const int64_t tot = (int64_t)B * ((Tmax + 1 + h - 1) / h), g = tot < cap ? tot : cap;
+      const int64_t cost = ((tot + g - 1) / g) * (57 * (h + 1) + 43 * FR * ((h + 1 + FR - 1) / FR));
+      if (best < 0 || cost < best) { best = cost; hops = h; }
+    }
+  }
+  const int strips = (Tmax + 1 + hops - 1) / hops;
   const int64_t total = (int64_t)B * strips;
-  const int grid = (int)(total < 148 * ISTFT_CTAS_PER_SM ? total : 148 * ISTFT_CTAS_PER_SM);
+  const int grid = (int)(total < cap ? total : cap);
   const size_t smem = sizeof(IstftSmem);
   ProfScope prof(mode == 0 ? "istft" : "enhance", st, 1);
   if (mode == 0) {
     DXI_CUDA(cudaFuncSetAttribute(istft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    istft_kernel<0><<<grid, 256, smem, st>>>(mag, g_or_xbar, phase, mu, sigma, gtype, n_frames, B, Tmax, strips,
+    istft_kernel<0><<<grid, 256, smem, st>>>(mag, g_or_xbar, phase, mu, sigma, gtype, n_frames, B, Tmax, strips, hops,
                                              wav_f32, wav_i16, out_stride);
   } else if (gtype == DXI_G_MMSE_LSA && !exact_enhance()) {
     DXI_CUDA(cudaFuncSetAttribute(istft_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    istft_kernel<2><<<grid, 256, smem, st>>>(mag, g_or_xbar, phase, mu, sigma, gtype, n_frames, B, Tmax, strips,
+    istft_kernel<2><<<grid, 256, smem, st>>>(mag, g_or_xbar, phase, mu, sigma, gtype, n_frames, B, Tmax, strips, hops,
                                              wav_f32, wav_i16, out_stride);
   } else {
     DXI_CUDA(cudaFuncSetAttribute(istft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    istft_kernel<1><<<grid, 256, smem, st>>>(mag, g_or_xbar, phase, mu, sigma, gtype, n_frames, B, Tmax, strips,
+    istft_kernel<1><<<grid, 256, smem, st>>>(mag, g_or_xbar, phase, mu, sigma, gtype, n_frames, B, Tmax, strips, hops,
                                              wav_f32, wav_i16, out_stride);
   }
   DXI_LAUNCHED("istft_kernel");
