@@ -60,6 +60,7 @@ using namespace umma;
 namespace chain {
 constexpr int TILE = 128, HALO = 32, C1_ROWS = HALO + TILE;
 constexpr int NSPLIT = 4, EPI_WARPS = 16, THREADS = 640;
+
 // shared memory map (bytes from the 1024-aligned base)
 constexpr int SM_W1 = 0, W1_PART = 32768;                  // [part][4 K-chunks][64 rows x 128 B]
 constexpr int SM_W2 = 65536, W2_PART = 24576;              // [part][3 taps][64 rows x 128 B]
@@ -799,21 +800,27 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
           float a[16];
           tmem_ld16(lane_addr + COL_D13 + 16 * qd, a); tmem_wait_ld();
           const float inv3w = inv3 * auxa[192], nim3 = -inv3w * mu3;      // auxa[192] = 1 / s1: W1 is stored as W1 * s1
-          float s = 0.0f;
+          const float2 iw2 = make_float2(inv3w, inv3w), nm2 = make_float2(nim3, nim3);
+          const float2* b1p = reinterpret_cast<const float2*>(auxa + 16 * qd);
+          const float2* csp = reinterpret_cast<const float2*>(auxa + 64 + 16 * qd);
+          float2 x[8], sv = make_float2(0.0f, 0.0f);
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            a[k] = relu(fmaf(inv3w, a[k], fmaf(nim3, auxa[64 + 16 * qd + k], auxa[16 * qd + k])));
-            s += a[k];
+          for (int k = 0; k < 8; ++k) {      // packed fp32x2 arithmetic: the phase is bound by instruction issue
+            const float2 t = __ffma2_rn(iw2, make_float2(a[2 * k], a[2 * k + 1]), __ffma2_rn(nm2, csp[k], b1p[k]));
+            x[k] = make_float2(relu(t.x), relu(t.y));
+            sv = __fadd2_rn(sv, x[k]);
           }
-          const float mean_i = s * (1.0f / 16.0f);
-          float q2 = 0.0f;
+          const float mean_i = (sv.x + sv.y) * (1.0f / 16.0f);
+          const float2 nmean = make_float2(-mean_i, -mean_i);
+          float2 qv = make_float2(0.0f, 0.0f);
 #pragma unroll
-          for (int k = 0; k < 16; ++k) { const float dd = a[k] - mean_i; q2 = fmaf(dd, dd, q2); }
+          for (int k = 0; k < 8; ++k) { const float2 dd = __fadd2_rn(x[k], nmean); qv = __ffma2_rn(dd, dd, qv); }
           float mean, inv;
-          ln_merge(red + (mrg & 1) * (NSPLIT * TILE), row, qd, 16.0f, mean_i, q2, 1e-6f, mean, inv);
+          ln_merge(red + (mrg & 1) * (NSPLIT * TILE), row, qd, 16.0f, mean_i, qv.x + qv.y, 1e-6f, mean, inv);
           ++mrg;
           CH_STAMP(14);
-          const float off = -mean * inv;
+          if (!valid) { inv = 0.0f; mean = 0.0f; }      // frames beyond the utterance enter the convolution as zeros
+          const float2 inv2 = make_float2(inv, inv), off2 = make_float2(-mean * inv, -mean * inv);
           unsigned char* c1w = smem + SM_C1 + (2 * qd) * C1_UNIT + (HALO + row) * 16;
           uint4 vh[2], vl[2];
 #pragma unroll
@@ -821,8 +828,8 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float x0 = valid ? fmaf(a[8 * e + 2 * k], inv, off) : 0.0f, x1 = valid ? fmaf(a[8 * e + 2 * k + 1], inv, off) : 0.0f;
-              to_h2<SPLIT>(x0, x1, hi[k], lo[k]);
+              const float2 y = __ffma2_rn(x[4 * e + k], inv2, off2);
+              to_h2<SPLIT>(y.x, y.y, hi[k], lo[k]);
             }
             vh[e] = make_uint4(hi[0], hi[1], hi[2], hi[3]); vl[e] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             *reinterpret_cast<uint4*>(c1w + e * C1_UNIT) = vh[e];
@@ -851,25 +858,37 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
         {
           float a[16];
           tmem_ld16(lane_addr + COL_D13 + 16 * qd, a); tmem_wait_ld();
-          float s = 0.0f;
-          const float is2 = auxa[193];      // W2 is stored as W2 * s2
+          if (b >= 3) CH_STAMP(24);
+          const float2 is2 = make_float2(auxa[193], auxa[193]);      // W2 is stored as W2 * s2
+          const float2* b2p = reinterpret_cast<const float2*>(auxa + 128 + 16 * qd);
+          float2 x[8], sv = make_float2(0.0f, 0.0f);
 #pragma unroll
-          for (int k = 0; k < 16; ++k) { a[k] = relu(fmaf(a[k], is2, auxa[128 + 16 * qd + k])); s += a[k]; }
-          const float mean_i = s * (1.0f / 16.0f);
-          float q2 = 0.0f;
+          for (int k = 0; k < 8; ++k) {
+            const float2 t = __ffma2_rn(make_float2(a[2 * k], a[2 * k + 1]), is2, b2p[k]);
+            x[k] = make_float2(relu(t.x), relu(t.y));
+            sv = __fadd2_rn(sv, x[k]);
+          }
+          const float mean_i = (sv.x + sv.y) * (1.0f / 16.0f);
+          const float2 nmean = make_float2(-mean_i, -mean_i);
+          float2 qv = make_float2(0.0f, 0.0f);
 #pragma unroll
-          for (int k = 0; k < 16; ++k) { const float dd = a[k] - mean_i; q2 = fmaf(dd, dd, q2); }
+          for (int k = 0; k < 8; ++k) { const float2 dd = __fadd2_rn(x[k], nmean); qv = __ffma2_rn(dd, dd, qv); }
+          if (b >= 3) CH_STAMP(25);
           float mean, inv;
-          ln_merge(red + (mrg & 1) * (NSPLIT * TILE), row, qd, 16.0f, mean_i, q2, 1e-6f, mean, inv);
+          ln_merge(red + (mrg & 1) * (NSPLIT * TILE), row, qd, 16.0f, mean_i, qv.x + qv.y, 1e-6f, mean, inv);
           ++mrg;
+          if (b >= 3) CH_STAMP(26);
           inv *= auxa[194];      // W3 is stored as W3 * s3 and GEMM2 lands in H: the operand carries 1 / s3 (s3 takes half of W3's exponent)
-          const float off = -mean * inv;
+          const float2 inv2 = make_float2(inv, inv), off2 = make_float2(-mean * inv, -mean * inv);
           uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) to_h2<SPLIT>(fmaf(a[2 * k], inv, off), fmaf(a[2 * k + 1], inv, off), hi[k], lo[k]);
+          for (int k = 0; k < 8; ++k) { const float2 y = __ffma2_rn(x[k], inv2, off2); to_h2<SPLIT>(y.x, y.y, hi[k], lo[k]); }
+          if (b >= 3) CH_STAMP(27);
           tmem_st8(lane_addr + COL_A2_HI + 8 * qd, hi);
           if (SPLIT) tmem_st8(lane_addr + COL_A2_LO + 8 * qd, lo);
-          tmem_wait_st(); warp_arrive(&bars[B_A2]);
+          tmem_wait_st();
+          if (b >= 3) CH_STAMP(28);
+          warp_arrive(&bars[B_A2]);
         }
         CH_STAMP(13);
         // operand scale of the next block: the exponent of this block's 1 / std (true scale = inv3 * sc)

@@ -171,6 +171,85 @@ namespace dxi { int make_weight_map(void* out, const void* dev, int K, size_t ro
 static int selftest_weight_map(CUtensorMap* tm, const void* b, int K, int N) { return dxi::make_weight_map(tm, b, K, (size_t)N, N); }
 
 #ifdef DXI_ENABLE_DEBUG
+// Layout discovery for the 16-lane TMEM access shapes (tuning build).  Phase 1: TMEM[lane][col] = lane * 256 + col for 64 columns is
+// written with the 32x32b shape (thread = lane); every warp then reads its two 16-lane halves with 16x256b.x8 and dumps its 32 + 32
+// registers: out[tid][0..63].  Phase 2: every thread writes (tid << 8 | register index) with 16x128b.x8 (16 registers per half) into
+// columns 64..95; the 32x32b read-back of those columns is dumped to out[128 * 64 + lane * 32 + col].
+namespace dxi {
+__global__ void __launch_bounds__(128) tmem_layout_kernel(uint32_t* out) {
+  __shared__ uint32_t slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc(&slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t base = slot + ((uint32_t)(warp * 32) << 16);
+  {
+    uint32_t v[32];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) v[c] = (uint32_t)tid * 256u + 32 * h + c;
+      tmem_st32(base + 32 * h, v);
+    }
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(base + ((uint32_t)(16 * half) << 16))
+        : "memory");
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) out[(size_t)tid * 64 + 32 * half + i] = r[i];
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t r[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = ((uint32_t)tid << 8) | (uint32_t)(16 * half + i);
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x128b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+            base + ((uint32_t)(16 * half) << 16) + 64),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+  }
+  tmem_wait_st();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  {
+    float v[32];
+    tmem_ld32(base + 64, v); tmem_wait_ld();
+#pragma unroll
+    for (int c = 0; c < 32; ++c) out[(size_t)128 * 64 + (size_t)tid * 32 + c] = __float_as_uint(v[c]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(slot, 512);
+}
+}  // namespace dxi
+
+extern "C" DXI_API int dxi_debug_tmem_layout(uint32_t* dev_out, void* stream) {
+  if (int rc = check_device()) return rc;
+  dxi::tmem_layout_kernel<<<1, 128, 0, as_stream(stream)>>>(dev_out);
+  DXI_LAUNCHED("tmem_layout_kernel");
+  return DXI_OK;
+}
+
 extern "C" DXI_API int dxi_debug_tmem_bw(int mode, int warps, int rounds, long long* dev_out, void* stream) {
   if (int rc = check_device()) return rc;
   DXI_REQUIRE(warps >= 4 && warps <= 32 && warps % 4 == 0 && rounds > 0 && dev_out, "dxi_debug_tmem_bw: bad argument");

@@ -15,7 +15,7 @@ ITEM = int(sys.argv[3]) if len(sys.argv) > 3 else 300
 kw = dict(d_model=256, n_blocks=40, d_f=64, k=3, max_d_rate=16, unit_type='ReLU->LN->W+b', outp_act='Sigmoid')
 lib = _lib.load()
 lib.dxi_debug_chain_clocks.argtypes = [ctypes.c_void_p, ctypes.c_int]
-net = network_selector('ResNetV2', None, 257, padding='causal', precision='f16x3', **kw).load_weights(weights.synthetic_resnetv2(0))
+net = network_selector('ResNetV2', None, 257, padding='causal', precision=os.environ.get('DXI_CLK_PREC', 'f16x3'), **kw).load_weights(weights.synthetic_resnetv2(0))
 it = inp_tgt_selector('MagXi', 512, 256, 512, 16000, map_type='DBNormalCDF', map_params=None)
 L = int(SEC * 16000)
 x = np.tile(synth.noisy_speech(min(B, 16), L, seed=5), (-(-B // min(B, 16)), 1))[:B]
@@ -37,6 +37,11 @@ prev = 0
 for k in [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 14, 15, 11, 12, 13]:
     print('  epi  %-26s +%6.0f' % (names[k], (blk[:, k] - blk[:, prev]).mean()))
     prev = k
+if os.environ.get('DXI_CLK_P1'):
+    b3 = s[3:39]
+    pv = 12
+    for k, nm in ((24, 'P1 ld done'), (25, 'P1 math 1'), (26, 'P1 merged'), (27, 'P1 converted'), (28, 'P1 tmem st done'), (13, 'P1 arrive')):
+        print('       %-26s +%6.0f' % (nm, (b3[:, k] - b3[:, pv]).mean())); pv = k
 print('  epi  %-26s +%6.0f' % ('-> next block start', (s[2:40, 0] - s[1:39, 13]).mean()))
 mn = {16: 'W1 landed', 17: 'A3 chunk 0 ready', 23: 'A3 chunk 3 ready', 18: 'A3 chunk 7 ready', 19: 'c1 + W2 ready', 20: 'GEMM1 issued', 21: 'A2 + W3 ready', 22: 'GEMM2 issued'}
 order = [16, 17, 23, 18, 19, 20, 21, 22]
