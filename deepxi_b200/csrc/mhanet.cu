@@ -14,6 +14,7 @@
 // This is the correctness-first path of round 1; the GEMMs move to tcgen05 next.
 #include <math.h>
 #include <stdlib.h>
+#include <algorithm>
 #include "net.cuh"
 
 namespace dxi {
@@ -244,7 +245,9 @@ __global__ void __launch_bounds__(256) attn_f32_kernel(const float* __restrict__
 
 int64_t mhanet_workspace_bytes(const dxi_net& net, int B, int T) {
   const int64_t rows = (int64_t)B * T, d = net.cfg.d_model;
-  return 512 + sizeof(float) * rows * (d /*x*/ + 3 * d /*qkv*/ + d /*att*/ + d /*a*/ + 4 * d /*ffn*/) + rows /*valid*/;
+  // the feed-forward activations and the packed K / V tiles of the tensor-core attention are never live together: one region
+  const int64_t f_bytes = std::max<int64_t>(sizeof(float) * rows * 4 * d, (int64_t)mhanet_umma_attention_workspace(net, B, T));
+  return 512 + sizeof(float) * rows * (d /*x*/ + 3 * d /*qkv*/ + d /*att*/ + d /*a*/) + f_bytes + rows /*valid*/;
 }
 
 int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xbar, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -260,7 +263,8 @@ int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xb
   float* att = qkv + (size_t)rows * 3 * d;
   float* a = att + (size_t)rows * d;
   float* f = a + (size_t)rows * d;
-  uint8_t* valid = reinterpret_cast<uint8_t*>(f + (size_t)rows * 4 * d);
+  const size_t f_bytes = std::max<size_t>(sizeof(float) * (size_t)rows * 4 * d, mhanet_umma_attention_workspace(net, B, T));
+  uint8_t* valid = reinterpret_cast<uint8_t*>(f) + f_bytes;
   if (c.mask_mode == DXI_MASK_CAUSAL_PAD) {
     valid_mask_kernel<<<(rows + 7) / 8, 256, 0, st>>>(mag, rows, c.n_feat, valid);
     DXI_LAUNCHED("valid_mask_kernel");
@@ -288,7 +292,7 @@ int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xb
       if (int rc = launch_gemm(g, st, "mha_gemm")) return rc;
     }
     if (tc && !(getenv("DXI_MHA_ATTN_F32") && atoi(getenv("DXI_MHA_ATTN_F32")))) {
-      if (int rc = mhanet_umma_attention(net, qkv, valid, B, T, att, st)) return rc;
+      if (int rc = mhanet_umma_attention(net, qkv, valid, B, T, att, f, st)) return rc;
     } else {
       dim3 grid((T + AQ - 1) / AQ, c.n_heads, B);
       ProfScope prof("mha_attn", st, 1);

@@ -59,7 +59,8 @@ int64_t mhanet_workspace_bytes(const dxi_net& net, int B, int T);
 int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xbar, void* ws, size_t ws_bytes,
                    cudaStream_t st);
 int mhanet_umma_prepare(dxi_net& net, cudaStream_t st);
-int mhanet_umma_attention(const dxi_net& net, const float* qkv, const uint8_t* valid, int B, int T, float* att, cudaStream_t st);
+size_t mhanet_umma_attention_workspace(const dxi_net& net, int B, int T);
+int mhanet_umma_attention(const dxi_net& net, const float* qkv, const uint8_t* valid, int B, int T, float* att, void* kv, cudaStream_t st);
 int mhanet_umma_linear(const dxi_net& net, int image, int epi, const float* A, int lda, const float* bias, const float* res,
                        const float* gamma, const float* beta, const float* pos, int T, float* out, int ldo, int M, int Nr, int Kr,
                        cudaStream_t st);
