@@ -17,6 +17,10 @@
 //              residual + LayerNorm (row statistics by Chan's merge over the 8 chunks, normalised in a second pass
 //              over the tile kept in TMEM); two accumulator buffers, so the epilogue of a tile overlaps the next tile's MMAs.
 // Shared memory: 2 ring slots x (A hi|lo 32 KB + W hi|lo 64 KB) = 192 KB + bias / gamma / beta of the column tile.
+// The kernel is bound by L2 -> SM bytes (96 KB per 1536 tensor cycles and SM, two thirds of it the weight chunk every row tile re-reads),
+// so CS CTAs form a thread-block cluster that walks CS row tiles of the SAME column tile in lock step: each CTA fetches 1 / CS of the
+// weight chunk and multicasts it to all of them (a ring slot is re-filled when the MMAs of ALL CS CTAs on it have committed: the commit
+// arrives on every CTA's barrier).
 #include <vector>
 #include "net.cuh"
 #include "umma.cuh"
@@ -31,7 +35,7 @@ constexpr int L_SLOT = 2 * LA_PART + 2 * LW_PART;     // 96 KB
 constexpr int L_WCHUNK = 2 * LW_PART;                 // packed weight chunk in global memory: hi | lo
 constexpr int L_PROD_WARPS = 8;                       // two groups of 4: group p fills ring slot p (chunks of parity p)
 constexpr int L_THREADS = (L_PROD_WARPS + 5) * 32;    // + 4 epilogue warps + 1 MMA warp
-constexpr int L_STAGE_LD = 33;
+constexpr int L_STAGE_LD = 36;                        // per-warp [32 rows][32 + 4] fp32 transposition stage: float4 accesses by row and by column group are conflict free
 constexpr int L_SMEM = 1024 + 2 * L_SLOT + 3 * LNT * 4 + LM * L_STAGE_LD * 4;
 enum { LEPI_PLAIN = 0, LEPI_BIAS_RELU = 1, LEPI_RES_LN = 2, LEPI_SIGMOID = 3 };
 
@@ -47,18 +51,19 @@ struct LinArgs {
   int Nr, Kr;                  // real sizes (Kr = 257 for the input layer, Nr = 257 for the output layer)
 };
 
+template <int CS>
 __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_a[2], full_w[2], empty[2], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
   unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* sVec = reinterpret_cast<float*>(ring + 2 * L_SLOT);      // bias[256], gamma[256], beta[256] of the column tile
-  float* sStage = sVec + 3 * LNT;                                 // [128][33]: row-major re-ordering of a 32-column chunk (unaligned outputs)
+  float* sStage = sVec + 3 * LNT;                                 // [4 warps][32][36]: thread-owns-row <-> warp-writes-row re-ordering of a 32-column chunk
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == L_PROD_WARPS + 4) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&full_a[i], 4); mbar_init(&full_w[i], 1); mbar_init(&empty[i], 1);
+      mbar_init(&full_a[i], 4); mbar_init(&full_w[i], 1); mbar_init(&empty[i], CS);
       mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4);
     }
     fence_mbar_init();
@@ -67,60 +72,78 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
   __syncthreads();
   tc_fence_after();
   if (tmem_slot != 0) __trap();
+  if (CS > 1) cluster_sync_all();      // every CTA's barriers exist before a peer's copy or commit can reach them
 
+  // The cluster walks (group of CS row tiles) x (column tile), n fastest; CTA `rank` takes row tile CS * group + rank (beyond the
+  // matrix: a tile of zeros that only keeps the multicast protocol in step).
   const int n_nt = g.N / LNT, n_mt = (g.M + LM - 1) / LM, n_kc = g.K / LK;
-  const int n_tiles = n_mt * n_nt;
+  const int rank = blockIdx.x % CS, cid = blockIdx.x / CS, n_cl = gridDim.x / CS;
+  const int n_tiles = (n_mt + CS - 1) / CS * n_nt;      // per cluster: "tile" t = (row group t / n_nt, column tile t % n_nt)
+  constexpr uint16_t cl_mask = (uint16_t)((1u << CS) - 1);
 
   if (warp < L_PROD_WARPS) {
     // ================= producers =================
-    int gch = 0;                                                  // chunk counter of this CTA: ring slot = gch & 1
+    // Group grp owns ring slot grp and the chunks of parity grp in this CTA's chunk sequence.  The fp32 rows of a group's NEXT chunk are
+    // loaded into registers as soon as the current one has been stored: those loads need no ring slot, so their latency (the
+    // kernel's bound before) runs under the MMAs of the current chunk and the other group's work.
     const int grp = warp >> 2, ptid = tid & 127;                  // producer group = the ring slot it owns
     const int c4 = ptid & 15, r0 = ptid >> 4;                     // float4 column, first row; rows r0 + 8 j
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int mt = t / n_nt, nt = t - mt * n_nt, m0 = mt * LM;
-      for (int kc = 0; kc < n_kc; ++kc, ++gch) {
-        const int slot = gch & 1, use = gch >> 1;
-        if (slot != grp) continue;                                // the other group's chunk
-        if (use >= 1) mbar_wait(&empty[slot], (use - 1) & 1);     // the MMAs that read this slot have completed
-        unsigned char* sA = ring + slot * L_SLOT;
-        if (ptid == 0) {
-          mbar_arrive_expect_tx(&full_w[slot], L_WCHUNK);
-          const unsigned char* src = g.W + ((size_t)nt * n_kc + kc) * L_WCHUNK;
-          for (int off = 0; off < L_WCHUNK; off += 16384) bulk_g2s(sA + 2 * LA_PART + off, src + off, 16384, &full_w[slot]);
+    int t = cid, kc = 0, gch = 0;                                 // this group's current chunk: (tile, K chunk), position in the CTA's sequence
+    auto advance = [&]() { if (++kc == n_kc) { kc = 0; t += n_cl; } ++gch; };
+    auto seek = [&]() { while (t < n_tiles && (gch & 1) != grp) advance(); };
+    float4 v[16];
+    auto load = [&]() {
+      if (t >= n_tiles) return;
+      const int mt = (t / n_nt) * CS + rank, m0 = mt * LM;
+      const float* ap = g.A + (size_t)m0 * g.lda + kc * LK + 4 * c4;
+      const bool vec = (g.lda & 3) == 0 && (kc + 1) * LK <= g.Kr;      // else: rows not 16-byte aligned / ragged K (input layer)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int r = r0 + 8 * j;
+        if (vec) {
+          v[j] = (m0 + r < g.M) ? __ldg(reinterpret_cast<const float4*>(ap + (size_t)r * g.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+          const float* q = ap + (size_t)r * g.lda;
+          const int k = kc * LK + 4 * c4;
+          const bool in = m0 + r < g.M;
+          v[j].x = (in && k < g.Kr) ? __ldg(q) : 0.f;         v[j].y = (in && k + 1 < g.Kr) ? __ldg(q + 1) : 0.f;
+          v[j].z = (in && k + 2 < g.Kr) ? __ldg(q + 2) : 0.f; v[j].w = (in && k + 3 < g.Kr) ? __ldg(q + 3) : 0.f;
         }
-        const float* ap = g.A + (size_t)m0 * g.lda + kc * LK + 4 * c4;
-        const bool vec = (g.lda & 3) == 0 && (kc + 1) * LK <= g.Kr;      // else: rows not 16-byte aligned / ragged K (input layer)
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float4 v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int r = r0 + 8 * (8 * half + j);
-            if (vec) {
-              v[j] = (m0 + r < g.M) ? __ldg(reinterpret_cast<const float4*>(ap + (size_t)r * g.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-              const float* q = ap + (size_t)r * g.lda;
-              const int k = kc * LK + 4 * c4;
-              const bool in = m0 + r < g.M;
-              v[j].x = (in && k < g.Kr) ? __ldg(q) : 0.f;         v[j].y = (in && k + 1 < g.Kr) ? __ldg(q + 1) : 0.f;
-              v[j].z = (in && k + 2 < g.Kr) ? __ldg(q + 2) : 0.f; v[j].w = (in && k + 3 < g.Kr) ? __ldg(q + 3) : 0.f;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int r = r0 + 8 * (8 * half + j);
-            uint32_t h0, l0, h1, l1;
-            split_h2(v[j].x, v[j].y, h0, l0);
-            split_h2(v[j].z, v[j].w, h1, l1);
-            const uint32_t off = (uint32_t)(r >> 3) * 1024 + (r & 7) * 128 + ((((uint32_t)c4 >> 1) ^ (r & 7)) << 4) + (c4 & 1) * 8;
-            *reinterpret_cast<uint2*>(sA + off) = make_uint2(h0, h1);
-            *reinterpret_cast<uint2*>(sA + LA_PART + off) = make_uint2(l0, l1);
-          }
-        }
-        fence_proxy_async();                                       // generic-proxy stores -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_a[slot]);
       }
+    };
+    seek();
+    load();
+    while (t < n_tiles) {
+      const int slot = grp, use = gch >> 1;
+      const int nt = t % n_nt;
+      if (use >= 1) mbar_wait_bounded(&empty[slot], (use - 1) & 1);       // the MMAs of every CTA of the cluster that read this slot have completed
+      unsigned char* sA = ring + slot * L_SLOT;
+      if (ptid == 0) {
+        mbar_arrive_expect_tx(&full_w[slot], L_WCHUNK);
+        const unsigned char* src = g.W + ((size_t)nt * n_kc + kc) * L_WCHUNK;
+        if (CS == 1) {
+          for (int off = 0; off < L_WCHUNK; off += 16384) bulk_g2s(sA + 2 * LA_PART + off, src + off, 16384, &full_w[slot]);
+        } else {      // this CTA's share of the chunk, to every CTA of the cluster
+          constexpr int share = L_WCHUNK / CS;
+          for (int off = rank * share; off < (rank + 1) * share; off += 16384)
+            bulk_g2s_multicast(sA + 2 * LA_PART + off, src + off, 16384, &full_w[slot], cl_mask);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int r = r0 + 8 * j;
+        uint32_t h0, l0, h1, l1;
+        split_h2(v[j].x, v[j].y, h0, l0);
+        split_h2(v[j].z, v[j].w, h1, l1);
+        const uint32_t off = (uint32_t)(r >> 3) * 1024 + (r & 7) * 128 + ((((uint32_t)c4 >> 1) ^ (r & 7)) << 4) + (c4 & 1) * 8;
+        *reinterpret_cast<uint2*>(sA + off) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(sA + LA_PART + off) = make_uint2(l0, l1);
+      }
+      fence_proxy_async();                                       // generic-proxy stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_a[slot]);
+      advance(); seek();
+      load();
     }
   } else if (warp == L_PROD_WARPS + 4) {
     // ================= MMA issue =================
@@ -128,14 +151,14 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
     const uint32_t e = elect_leader();      // issue path as in tcn_chain.cu: one election, 32-bit descriptor words in uniform registers
     const uint32_t ring_a = smem_u32(ring);
     int gch = 0, lt = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
+    for (int t = cid; t < n_tiles; t += n_cl, ++lt) {
       const int buf = lt & 1, u = lt >> 1;
-      if (u >= 1) { mbar_wait(&acc_empty[buf], (u - 1) & 1); tc_fence_after(); }      // the epilogue has drained this accumulator
+      if (u >= 1) { mbar_wait_bounded(&acc_empty[buf], (u - 1) & 1); tc_fence_after(); }      // the epilogue has drained this accumulator
       const uint32_t d_col = 256u * buf;
       for (int kc = 0; kc < n_kc; ++kc, ++gch) {
         const int slot = gch & 1, use = gch >> 1;
-        mbar_wait(&full_a[slot], use & 1);
-        mbar_wait(&full_w[slot], use & 1);
+        mbar_wait_bounded(&full_a[slot], use & 1);
+        mbar_wait_bounded(&full_w[slot], use & 1);
         tc_fence_after();
         const uint32_t a32 = desc_lo_sw128(ring_a + slot * L_SLOT), w32 = desc_lo_sw128(ring_a + slot * L_SLOT + 2 * LA_PART);
 #pragma unroll
@@ -145,78 +168,103 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
             mma_ss_lo<DESC_HI_SW128, DESC_HI_SW128>(d_col, a32 + (((part == 1 ? LA_PART : 0) + ks * 32) >> 4),
                                                      w32 + (((part == 2 ? LW_PART : 0) + ks * 32) >> 4), idesc,
                                                      (kc > 0 || part > 0 || ks > 0) ? 1u : 0u, e);
-        mma_commit_lo(&empty[slot], e);
+        if (CS == 1) mma_commit_lo(&empty[slot], e); else mma_commit_multicast_lo(&empty[slot], cl_mask, e);
       }
       mma_commit_lo(&acc_full[buf], e);
     }
   } else {
     // ================= epilogue (warps 8-11: TMEM lane quarter = warp & 3) =================
+    // A thread owns one output row in TMEM, but a warp must touch global memory one row SEGMENT at a time (the first version stored
+    // 16 bytes per thread into 32 different rows per instruction: 32 line requests and half-written sectors, and that - not the MMAs -
+    // set the pace of the K = 256 layers).  Every 32-column chunk therefore passes through a per-warp stage: rows in, 4 rows x 128
+    // bytes out per instruction (and the reverse for the residual rows).
     const int ew = warp & 3, row = ew * 32 + lane, et = tid - L_PROD_WARPS * 32;      // et: 0..127
     const uint32_t lane_addr = (uint32_t)(ew * 32) << 16;
+    float* wst = sStage + ew * (32 * L_STAGE_LD);
+    const int sub_r = lane >> 3, sub_c = 4 * (lane & 7);      // coalesced side: 4 rows per instruction, 8 lanes x float4 per row
     auto epi_sync = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
     int lt = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++lt) {
-      const int mt = t / n_nt, nt = t - mt * n_nt, m = mt * LM + row, n0 = nt * LNT;
+    for (int t = cid; t < n_tiles; t += n_cl, ++lt) {
+      const int mt = (t / n_nt) * CS + rank, nt = t % n_nt, m = mt * LM + row, n0 = nt * LNT;
+      const int mw = mt * LM + ew * 32;      // first row of this warp
       const int buf = lt & 1, u = lt >> 1;
-      const bool valid = m < g.M;
+      // registers (thread = row) -> global rows of the warp, columns n0 + c0 .. + 31
+      auto store_rows = [&](const float (&v)[32], int c0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(wst + lane * L_STAGE_LD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = 4 * j + sub_r;
+          if (mw + r < g.M)
+            *reinterpret_cast<float4*>(g.out + (size_t)(mw + r) * g.ldo + n0 + c0 + sub_c) = *reinterpret_cast<const float4*>(wst + r * L_STAGE_LD + sub_c);
+        }
+        __syncwarp();
+      };
+      // global rows (row r of the warp at rowptr(r), 32 floats from column c0) -> registers (thread = row); rows beyond M: zeros
+      auto load_rows = [&](auto rowptr, int c0, float (&v)[32]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = 4 * j + sub_r;
+          const float4 x = (mw + r < g.M) ? __ldg(reinterpret_cast<const float4*>(rowptr(mw + r) + c0 + sub_c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(wst + r * L_STAGE_LD + sub_c) = x;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 x = *reinterpret_cast<const float4*>(wst + lane * L_STAGE_LD + 4 * q);
+          v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+        }
+        __syncwarp();
+      };
       epi_sync();                                                  // previous tile's readers of sVec are done
       for (int i = et; i < LNT; i += 128) {
         sVec[i] = (g.bias && n0 + i < g.Nr) ? __ldg(g.bias + n0 + i) : 0.0f;
         if (g.epi == LEPI_RES_LN) { sVec[LNT + i] = __ldg(g.gamma + i); sVec[2 * LNT + i] = __ldg(g.beta + i); }
       }
       epi_sync();
-      mbar_wait(&acc_full[buf], u & 1); tc_fence_after();
+      mbar_wait_bounded(&acc_full[buf], u & 1); tc_fence_after();
       const uint32_t d_addr = lane_addr + 256u * buf;
-      float* orow = g.out + (size_t)m * g.ldo + n0;
       if (g.epi == LEPI_SIGMOID) {
-        // sigmoid(acc + bias) -> [M][Nr] with an unaligned row pitch: every 32-column chunk is re-ordered through shared memory
-        // so that a warp writes 32 consecutive floats of one row
+        // sigmoid(acc + bias) -> [M][Nr] with an unaligned row pitch: a warp writes 32 consecutive floats of one row per instruction
 #pragma unroll 1
         for (int c8 = 0; c8 < 8 && n0 + 32 * c8 < g.Nr; ++c8) {
           float v[32];
           tmem_ld32(d_addr + 32 * c8, v); tmem_wait_ld();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) sStage[row * L_STAGE_LD + e] = 1.0f / (1.0f + __expf(-(v[e] + sVec[32 * c8 + e])));
-          epi_sync();
-          for (int i = et; i < LM * 32; i += 128) {
-            const int r = i >> 5, c = i & 31, mm = mt * LM + r, col = n0 + 32 * c8 + c;
-            if (mm < g.M && col < g.Nr) g.out[(size_t)mm * g.ldo + col] = sStage[r * L_STAGE_LD + c];
-          }
-          epi_sync();
+          for (int e = 0; e < 32; ++e) wst[lane * L_STAGE_LD + e] = 1.0f / (1.0f + __expf(-(v[e] + sVec[32 * c8 + e])));
+          __syncwarp();
+          const int col = n0 + 32 * c8 + lane;
+          for (int r = 0; r < 32; ++r)
+            if (mw + r < g.M && col < g.Nr) g.out[(size_t)(mw + r) * g.ldo + col] = wst[r * L_STAGE_LD + lane];
+          __syncwarp();
         }
       } else if (g.epi != LEPI_RES_LN) {
 #pragma unroll 1
         for (int c8 = 0; c8 < 8; ++c8) {
           float v[32];
           tmem_ld32(d_addr + 32 * c8, v); tmem_wait_ld();
-          if (valid) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float4 o;
-              o.x = v[4 * q] + sVec[32 * c8 + 4 * q];         o.y = v[4 * q + 1] + sVec[32 * c8 + 4 * q + 1];
-              o.z = v[4 * q + 2] + sVec[32 * c8 + 4 * q + 2]; o.w = v[4 * q + 3] + sVec[32 * c8 + 4 * q + 3];
-              if (g.epi == LEPI_BIAS_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-              *reinterpret_cast<float4*>(orow + 32 * c8 + 4 * q) = o;
-            }
+          for (int e = 0; e < 32; ++e) {
+            v[e] += sVec[32 * c8 + e];
+            if (g.epi == LEPI_BIAS_RELU) v[e] = fmaxf(v[e], 0.f);
           }
+          store_rows(v, 32 * c8);
         }
       } else {
         // y = acc + bias + residual, kept in TMEM; LayerNorm(y) * gamma + beta (Keras non-fused order, eps 1e-6)
-        const float* rrow = g.res ? g.res + (size_t)m * g.N : nullptr;
-        const float* prow = g.pos ? g.pos + (size_t)(m % g.T) * LNT : nullptr;
         float mean = 0.0f, m2 = 0.0f;
 #pragma unroll 1
         for (int c8 = 0; c8 < 8; ++c8) {
-          float v[32];
-          tmem_ld32(d_addr + 32 * c8, v); tmem_wait_ld();
+          float v[32], rs[32];
+          tmem_ld32(d_addr + 32 * c8, v);
+          if (g.res) load_rows([&](int mm) { return g.res + (size_t)mm * g.N; }, 32 * c8, rs);
+          tmem_wait_ld();
           float s = 0.0f;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 r4 = (valid && rrow) ? __ldg(reinterpret_cast<const float4*>(rrow + 32 * c8 + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[4 * q] += sVec[32 * c8 + 4 * q] + r4.x;         v[4 * q + 1] += sVec[32 * c8 + 4 * q + 1] + r4.y;
-            v[4 * q + 2] += sVec[32 * c8 + 4 * q + 2] + r4.z; v[4 * q + 3] += sVec[32 * c8 + 4 * q + 3] + r4.w;
-            s += (v[4 * q] + v[4 * q + 1]) + (v[4 * q + 2] + v[4 * q + 3]);
-          }
+          for (int e = 0; e < 32; ++e) { v[e] += sVec[32 * c8 + e] + (g.res ? rs[e] : 0.0f); }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) s += (v[4 * q] + v[4 * q + 1]) + (v[4 * q + 2] + v[4 * q + 3]);
           const float mc = s * (1.0f / 32.0f);
           float qc = 0.0f;
 #pragma unroll
@@ -231,22 +279,18 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
         const float rstd = rsqrtf(m2 * (1.0f / LNT) + 1e-6f);
 #pragma unroll 1
         for (int c8 = 0; c8 < 8; ++c8) {
-          float v[32];
-          tmem_ld32(d_addr + 32 * c8, v); tmem_wait_ld();
-          if (valid) {
+          float v[32], pe[32];
+          tmem_ld32(d_addr + 32 * c8, v);
+          if (g.pos) load_rows([&](int mm) { return g.pos + (size_t)(mm % g.T) * LNT; }, 32 * c8, pe);
+          tmem_wait_ld();
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float o[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int c = 32 * c8 + 4 * q + e;
-                const float inv = rstd * sVec[LNT + c];
-                o[e] = fmaf(v[4 * q + e], inv, sVec[2 * LNT + c] - mean * inv);
-                if (prow) o[e] = fmaxf(o[e], 0.0f) + __ldg(prow + c);
-              }
-              *reinterpret_cast<float4*>(orow + 32 * c8 + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
-            }
+          for (int e = 0; e < 32; ++e) {
+            const int c = 32 * c8 + e;
+            const float inv = rstd * sVec[LNT + c];
+            v[e] = fmaf(v[e], inv, sVec[2 * LNT + c] - mean * inv);
+            if (g.pos) v[e] = fmaxf(v[e], 0.0f) + pe[e];
           }
+          store_rows(v, 32 * c8);
         }
       }
       tc_fence_before();
@@ -256,6 +300,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
   }
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();      // no CTA leaves while a peer's commit may still arrive on its barriers
   if (warp == L_PROD_WARPS + 4) tmem_dealloc(0, 512);
 }
 
@@ -328,12 +373,31 @@ int mhanet_umma_linear(const dxi_net& net, int image, int epi, const float* A, i
             out, ldo, M, N, K, epi, Nr, Kr};
   if (epi == LEPI_RES_LN && Nr != LNT) { set_error("lin_umma: LayerNorm epilogue needs N = 256"); return DXI_E_INVALID; }
   if (epi != LEPI_SIGMOID && ((ldo & 3) || Nr != N)) { set_error("lin_umma: unaligned outputs only through the sigmoid epilogue"); return DXI_E_INVALID; }
-  DXI_CUDA(cudaFuncSetAttribute(lin_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM));      // per device, so per call
   int n_sm = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
-  const int tiles = ((M + LM - 1) / LM) * (N / LNT);
+  const int n_mt = (M + LM - 1) / LM, n_nt = N / LNT;
+  // clusters of 4 row tiles share every weight chunk (2 when the matrix has few row tiles; DXI_LIN_CLUSTER overrides for A/B runs)
+  int cs = n_mt >= 4 * n_sm / 4 ? 4 : (n_mt >= 2 ? 2 : 1);
+  if (const char* e = getenv("DXI_LIN_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) cs = v; }
+  auto kern = cs == 4 ? lin_umma_kernel<4> : cs == 2 ? lin_umma_kernel<2> : lin_umma_kernel<1>;
+  DXI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM));      // per device, so per call
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(L_THREADS); cfg.dynamicSmemBytes = L_SMEM; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = 1;
+  int n_cl = n_sm / cs;
+  if (cs > 1) {
+    cfg.gridDim = dim3(n_sm / cs * cs);
+    int max_cl = 0;
+    DXI_CUDA(cudaOccupancyMaxActiveClusters(&max_cl, kern, &cfg));      // GPCs whose SM count is not a multiple of cs hold fewer clusters
+    if (max_cl < 1) { set_error("lin_umma: no cluster of %d CTAs fits the device", cs); return DXI_E_STATE; }
+    n_cl = max_cl < n_cl ? max_cl : n_cl;
+  }
+  const int tiles = (n_mt + cs - 1) / cs * n_nt;
+  cfg.gridDim = dim3((tiles < n_cl ? tiles : n_cl) * cs);
   ProfScope prof("mha_gemm", st, 1);
-  lin_umma_kernel<<<tiles < n_sm ? tiles : n_sm, L_THREADS, L_SMEM, st>>>(g);
+  DXI_CUDA(cudaLaunchKernelEx(&cfg, kern, g));
   DXI_LAUNCHED("lin_umma_kernel");
   return DXI_OK;
 }

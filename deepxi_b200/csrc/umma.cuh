@@ -76,6 +76,17 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// The same copy delivered to the same shared-memory offset of every CTA of the cluster named in cta_mask; each destination CTA's
+// mbarrier (same offset) receives the byte count.
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- tensor-map TMA (cp.async.bulk.tensor): a 2-D box of a global tensor -> shared memory, swizzled by the engine as the
@@ -342,6 +353,14 @@ __device__ __forceinline__ void mma_commit_lo(uint64_t* bar, uint32_t e) {
   asm volatile(
       "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
       "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)), "r"(e)
+      : "memory");
+}
+// ... and arrives on the mbarrier at the same offset in every CTA of cta_mask (operands delivered by multicast are released cluster-wide)
+__device__ __forceinline__ void mma_commit_multicast_lo(uint64_t* bar, uint16_t cta_mask, uint32_t e) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "h"(cta_mask), "r"(e)
       : "memory");
 }
 __device__ __forceinline__ void mma_ss_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {

@@ -248,6 +248,24 @@ def test_mhanetv3_tensor_core_path_tile_edges(xi_stats, T):
         assert _db_err(xbar[i], ref[i], mu, sg).max() < 5e-3, (T, i)
 
 
+@pytest.mark.parametrize('lens', [[150000, 90000, 33333], [300], [66000] * 5])
+def test_mhanetv3_linear_layers_cluster_sizes_agree(lens, monkeypatch):
+    """The linear layers share every weight chunk across a thread-block cluster of 1, 2 or 4 row tiles (multicast bulk copies,
+    mha_umma.cu).  The arithmetic of a row tile does not depend on its cluster, so the three must agree bit for bit - including
+    shapes where the last cluster holds row tiles beyond the matrix (586 + 352 + 131 frames -> 14 row tiles; 2 frames -> 1 tile;
+    5 x 258 frames -> 11 tiles)."""
+    w = weights.synthetic_mhanetv3(4)
+    x = synth.noisy_speech(len(lens), max(lens), seed=64)
+    inp, _, _ = osig.observation_batch(x, lens)
+    net = network_selector('MHANetV3', None, 257, mask_mode='none', precision='f16x3', **MHA_KW).load_weights(w)
+    out = {}
+    for cs in ('1', '2', '4'):
+        monkeypatch.setenv('DXI_LIN_CLUSTER', cs)
+        out[cs] = np.asarray(net(inp))
+        assert np.isfinite(out[cs]).all()
+    assert np.array_equal(out['1'], out['2']) and np.array_equal(out['1'], out['4'])
+
+
 def test_mhanetv3_infer_and_limits(xi_stats):
     w = weights.synthetic_mhanetv3(1)
     dx = DeepXi(512, 256, 512, 16000, 'MagXi', 'MHANetV3', ver='mhanet-1.1c', map_type='DBNormalCDF', map_params=None,
