@@ -177,16 +177,22 @@ __global__ void __launch_bounds__((4 * NH + 2) * 32, 2) attn_umma_kernel(const A
         // interior tiles of the unmasked mode need no per-element tests (every key exists, nothing is masked)
         const bool plain = !MASK && k0 + KH <= g.T;
         float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < KH / 16; ++c) {
-          float s[16];
-          tmem_ld16(s_addr + 16 * c, s); tmem_wait_ld();
-          if (plain) {
+        {   // the chunk loads are issued one ahead of their use: their latency is what this pass costs
+          float sa[16], sb[16];
+          tmem_ld16(s_addr, sa);
 #pragma unroll
-            for (int e = 0; e < 16; e += 2) mx = fmaxf(mx, fmaxf(s[e], s[e + 1]));
-          } else {
+          for (int c = 0; c < KH / 16; ++c) {
+            float (&cur)[16] = (c & 1) ? sb : sa;
+            float (&nxt)[16] = (c & 1) ? sa : sb;
+            tmem_wait_ld(); tmem_ld_fence16(cur);
+            if (c + 1 < KH / 16) tmem_ld16(s_addr + 16 * (c + 1), nxt);
+            if (plain) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) mx = fmaxf(mx, logit(s[e], 16 * c + e));
+              for (int e = 0; e < 16; e += 2) mx = fmaxf(mx, fmaxf(cur[e], cur[e + 1]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) mx = fmaxf(mx, logit(cur[e], 16 * c + e));
+            }
           }
         }
         const float m_new = fmaxf(m_run, mx);
@@ -194,30 +200,36 @@ __global__ void __launch_bounds__((4 * NH + 2) * 32, 2) attn_umma_kernel(const A
         if (kt > 0) { mbar_wait(&pv_done[half], (kt - 1) & 1); tc_fence_after(); }      // P and O of this half are free again
         float2 psum = make_float2(0.0f, 0.0f);
         const float2 nm = make_float2(-m_new, -m_new);
-#pragma unroll 1
-        for (int c = 0; c < KH / 16; ++c) {
-          float s[16];
-          tmem_ld16(s_addr + 16 * c, s); tmem_wait_ld();
-          uint32_t hi[8], lo[8];
-          if (plain) {
+        {
+          float sa[16], sb[16];
+          tmem_ld16(s_addr, sa);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float2 d = __fadd2_rn(make_float2(s[2 * e], s[2 * e + 1]), nm);
-              const float2 pp = make_float2(fast_ex2(d.x), fast_ex2(d.y));
-              psum = __fadd2_rn(psum, pp);
-              split_h2x(pp, hi[e], lo[e]);
-            }
-          } else {
+          for (int c = 0; c < KH / 16; ++c) {
+            float (&s)[16] = (c & 1) ? sb : sa;
+            float (&nxt)[16] = (c & 1) ? sa : sb;
+            tmem_wait_ld(); tmem_ld_fence16(s);
+            if (c + 1 < KH / 16) tmem_ld16(s_addr + 16 * (c + 1), nxt);      // lands while this chunk is exponentiated
+            uint32_t hi[8], lo[8];
+            if (plain) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float l0 = logit(s[2 * e], 16 * c + 2 * e), l1 = logit(s[2 * e + 1], 16 * c + 2 * e + 1);
-              const float2 pp = make_float2((l0 == -INFINITY) ? 0.0f : fast_ex2(l0 - m_new), (l1 == -INFINITY) ? 0.0f : fast_ex2(l1 - m_new));
-              psum = __fadd2_rn(psum, pp);
-              split_h2x(pp, hi[e], lo[e]);
+              for (int e = 0; e < 8; ++e) {
+                const float2 d = __fadd2_rn(make_float2(s[2 * e], s[2 * e + 1]), nm);
+                const float2 pp = make_float2(fast_ex2(d.x), fast_ex2(d.y));
+                psum = __fadd2_rn(psum, pp);
+                split_h2x(pp, hi[e], lo[e]);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float l0 = logit(s[2 * e], 16 * c + 2 * e), l1 = logit(s[2 * e + 1], 16 * c + 2 * e + 1);
+                const float2 pp = make_float2((l0 == -INFINITY) ? 0.0f : fast_ex2(l0 - m_new), (l1 == -INFINITY) ? 0.0f : fast_ex2(l1 - m_new));
+                psum = __fadd2_rn(psum, pp);
+                split_h2x(pp, hi[e], lo[e]);
+              }
             }
+            tmem_st8(s_addr + 16 * c, hi);               // in place: these 16 logits are in registers
+            tmem_st8(s_addr + 16 * c + 8, lo);
           }
-          tmem_st8(s_addr + 16 * c, hi);               // in place: these 16 logits are in registers
-          tmem_st8(s_addr + 16 * c + 8, lo);
         }
         l_run = fmaf(l_run, alpha, psum.x + psum.y);
         m_run = m_new;
@@ -278,7 +290,7 @@ __global__ void __launch_bounds__((4 * NH + 2) * 32, 2) attn_umma_kernel(const A
       const unsigned char* src = g.kv + (size_t)bh * n_kt * A_SLOT;
       const int nk = n_ktiles(qt);
       for (int j = 0; j < nk; ++j) {
-        if (use >= 1) mbar_wait(&kv_empty[slot], (use - 1) & 1);
+        if (use >= 1) while (!mbar_try_wait(&kv_empty[slot], (use - 1) & 1)) __nanosleep(200);      // not on the critical path: leave the issue slots to the softmax warps
         if (MASK) {
           const int k0 = j * AT + 4 * lane;
 #pragma unroll
@@ -298,6 +310,7 @@ __global__ void __launch_bounds__((4 * NH + 2) * 32, 2) attn_umma_kernel(const A
     // The key halves are independent streams (own S columns, own O, own barriers): per tile and half, P V of the tile is followed at
     // once by Q K^T of the NEXT tile for the same half, so that while the softmax warps of one half work, the tensor pipe serves the other.
     constexpr uint32_t id_s = make_idesc_f16(AT, KH), id_o = make_idesc_f16(AT, AHD);
+    const uint32_t e = elect_leader();      // one election; descriptors as 32-bit words (the issue path of tcn_chain.cu)
     int slot = 0, use = 0;
     auto issue_s = [&](int hf, int sl) {      // S_hf = Q K_hf^T of the tile in ring slot sl (the caller has awaited kv_full)
       const uint32_t k_hi = smem_u32(ring + sl * A_SLOT) + hf * (KH / 8) * 512, k_lo = k_hi + AK_PART;
@@ -306,9 +319,9 @@ __global__ void __launch_bounds__((4 * NH + 2) * 32, 2) attn_umma_kernel(const A
         const uint32_t a0 = part == 1 ? AC_QLO : AC_QHI, b0 = part == 2 ? k_lo : k_hi;
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
-          mma_ts_elect(tbase + AC_S + KH * hf, tbase + a0 + 8 * ks, make_smem_desc_noswz(b0 + ks * 256, 128, 512), id_s, (part > 0 || ks > 0) ? 1u : 0u);
+          mma_ts_lo<desc_hi_noswz(512)>(tbase + AC_S + KH * hf, tbase + a0 + 8 * ks, desc_lo_noswz(b0 + ks * 256, 128), id_s, (part > 0 || ks > 0) ? 1u : 0u, e);
       }
-      mma_commit_elect(&s_full[hf]);
+      mma_commit_lo(&s_full[hf], e);
     };
     int kt = 0, it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -331,12 +344,12 @@ __global__ void __launch_bounds__((4 * NH + 2) * 32, 2) attn_umma_kernel(const A
 #pragma unroll
             for (int k2 = 0; k2 < 8 / NH; ++k2) {      // keys 16 ks ..: hi pairs of P at column 16 ks, lo pairs 8 columns further
               const int ks = hf * (8 / NH) + k2;
-              mma_ts_elect(tbase + AC_O + 32 * hf, tbase + AC_S + 16 * ks + (part == 1 ? 8 : 0),
-                           make_smem_desc_noswz(b0 + ks * 256, 128, 2048), id_o, (j > 0 || part > 0 || k2 > 0) ? 1u : 0u);
+              mma_ts_lo<desc_hi_noswz(2048)>(tbase + AC_O + 32 * hf, tbase + AC_S + 16 * ks + (part == 1 ? 8 : 0),
+                                             desc_lo_noswz(b0 + ks * 256, 128), id_o, (j > 0 || part > 0 || k2 > 0) ? 1u : 0u, e);
             }
           }
-          mma_commit_elect(&pv_done[hf]);
-          if (hf == NH - 1) mma_commit_elect(&kv_empty[slot]);      // every product that reads the slot has been issued
+          mma_commit_lo(&pv_done[hf], e);
+          if (hf == NH - 1) mma_commit_lo(&kv_empty[slot], e);      // every product that reads the slot has been issued
           if (j + 1 < nk) {
             if (hf == 0) { mbar_wait(&kv_full[nslot], nuse & 1); tc_fence_after(); }
             issue_s(hf, nslot);

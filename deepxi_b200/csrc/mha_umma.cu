@@ -376,9 +376,9 @@ int mhanet_umma_linear(const dxi_net& net, int image, int epi, const float* A, i
   int n_sm = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
   const int n_mt = (M + LM - 1) / LM, n_nt = N / LNT;
-  // clusters of 4 row tiles share every weight chunk (2 when the matrix has few row tiles; DXI_LIN_CLUSTER overrides for A/B runs)
-  int cs = n_mt >= 4 * n_sm / 4 ? 4 : (n_mt >= 2 ? 2 : 1);
-  if (const char* e = getenv("DXI_LIN_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) cs = v; }
+  // DXI_LIN_CLUSTER = 2 / 4: clusters of that many row tiles share every weight chunk by multicast.  Measured on B200 at 64 x 1875 frames:
+  // 4.85 ms (1), 4.92 ms (2), slower at 4 (fewer SMs fit whole clusters) - the L2 already merges the concurrent reads of a chunk.
+  int cs = 1;
   auto kern = cs == 4 ? lin_umma_kernel<4> : cs == 2 ? lin_umma_kernel<2> : lin_umma_kernel<1>;
   DXI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM));      // per device, so per call
   cudaLaunchConfig_t cfg{};

@@ -203,6 +203,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
       : "memory");
 }
 
+// After a tcgen05.wait::ld that completes a load issued EARLIER than the statement before it (software-pipelined loads): ties the
+// destination registers to this point of the program, so that the compiler cannot move their uses above the wait.
+__device__ __forceinline__ void tmem_ld_fence16(float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+               "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])::"memory");
+}
+
 // ---- descriptors ------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major, SWIZZLE_128B, 8-row atoms 1024 bytes apart.
 __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
