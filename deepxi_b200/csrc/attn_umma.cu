@@ -368,8 +368,9 @@ size_t mhanet_umma_attention_workspace(const dxi_net& net, int B, int T) {
   return (size_t)B * net.cfg.n_heads * ((T + AT - 1) / AT) * A_SLOT;
 }
 
-// kv: mhanet_umma_attention_workspace(net, B, T) bytes of scratch (16-byte aligned)
-int mhanet_umma_attention(const dxi_net& net, const float* qkv, const uint8_t* valid, int B, int T, float* att, void* kv, cudaStream_t st) {
+// kv: mhanet_umma_attention_workspace(net, B, T) bytes (16-byte aligned): the packed key tiles, already written by the fused QKV
+// projection (kv_packed, mha_umma.cu) or packed here from the K / V columns of qkv
+int mhanet_umma_attention(const dxi_net& net, const float* qkv, const uint8_t* valid, int B, int T, float* att, void* kv, bool kv_packed, cudaStream_t st) {
   const dxi_net_cfg& c = net.cfg;
   if (c.d_model / c.n_heads != AHD || (c.d_model & 3)) { set_error("tcgen05 attention is built for head size 32"); return DXI_E_INVALID; }
   AttnArgs a{qkv, reinterpret_cast<const unsigned char*>(kv), valid, att, B, T, c.d_model, c.n_heads};
@@ -382,9 +383,11 @@ int mhanet_umma_attention(const dxi_net& net, const float* qkv, const uint8_t* v
   const int n_kt = (T + AT - 1) / AT;
   const int items = B * c.n_heads * n_kt;
   const int grid = items < 2 * n_sm ? items : 2 * n_sm;      // two CTAs per SM
-  ProfScope prof("mha_attn", st, 2);
-  attn_pack_kv_kernel<<<items, 128, 0, st>>>(qkv, reinterpret_cast<unsigned char*>(kv), T, c.d_model, c.n_heads);
-  DXI_LAUNCHED("attn_pack_kv_kernel");
+  ProfScope prof("mha_attn", st, kv_packed ? 1 : 2);
+  if (!kv_packed) {
+    attn_pack_kv_kernel<<<items, 128, 0, st>>>(qkv, reinterpret_cast<unsigned char*>(kv), T, c.d_model, c.n_heads);
+    DXI_LAUNCHED("attn_pack_kv_kernel");
+  }
   if (c.mask_mode == DXI_MASK_CAUSAL_PAD) attn_umma_kernel<1, A_NH><<<grid, threads, A_SMEM, st>>>(a);
   else attn_umma_kernel<0, A_NH><<<grid, threads, A_SMEM, st>>>(a);
   DXI_LAUNCHED("attn_umma_kernel");

@@ -37,7 +37,8 @@ constexpr int L_PROD_WARPS = 8;                       // two groups of 4: group 
 constexpr int L_THREADS = (L_PROD_WARPS + 5) * 32;    // + 4 epilogue warps + 1 MMA warp
 constexpr int L_STAGE_LD = 36;                        // per-warp [32 rows][32 + 4] fp32 transposition stage: float4 accesses by row and by column group are conflict free
 constexpr int L_SMEM = 1024 + 2 * L_SLOT + 3 * LNT * 4 + LM * L_STAGE_LD * 4;
-enum { LEPI_PLAIN = 0, LEPI_BIAS_RELU = 1, LEPI_RES_LN = 2, LEPI_SIGMOID = 3 };
+enum { LEPI_PLAIN = 0, LEPI_BIAS_RELU = 1, LEPI_RES_LN = 2, LEPI_SIGMOID = 3, LEPI_QKV = 4 };
+constexpr int L_KV_PART = 128 * 32 * 2, L_KV_TILE = 4 * L_KV_PART;      // the attention kernel's key-tile image (attn_umma.cu): K hi | K lo | V^T hi | V^T lo
 
 struct LinArgs {
   const float* A; int lda;
@@ -49,6 +50,11 @@ struct LinArgs {
   float* out; int ldo;
   int M, N, K, epi;            // N, K: padded to multiples of 256 / 64 (the packed weights carry the zeros)
   int Nr, Kr;                  // real sizes (Kr = 257 for the input layer, Nr = 257 for the output layer)
+  // LEPI_QKV (fused QKV projection, N = 768 = Q | K | V): the row space is padded per utterance to whole 128-row tiles, row tile mt =
+  // (utterance mt / n_kt, key tile mt % n_kt) reads rows b T + 128 j .. of A (rows at or beyond T: zeros).  Column tile 0 (Q) goes to
+  // out as fp32; tiles 1, 2 (K, V) leave as the attention kernel's operand images, one head per 32-column chunk:
+  // kv[((b n_heads + h) n_kt + j)][L_KV_TILE] - fp16 hi | lo, K-major core matrices, V transposed - zero padded for free.
+  unsigned char* kv; int n_kt, n_heads;
 };
 
 template <int CS>
@@ -80,6 +86,17 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
   const int rank = blockIdx.x % CS, cid = blockIdx.x / CS, n_cl = gridDim.x / CS;
   const int n_tiles = (n_mt + CS - 1) / CS * n_nt;      // per cluster: "tile" t = (row group t / n_nt, column tile t % n_nt)
   constexpr uint16_t cl_mask = (uint16_t)((1u << CS) - 1);
+  // first source / destination row of row tile mt and how many of its 128 rows exist
+  auto tile_rows = [&](int mt, int& src0, int& nvalid) {
+    if (g.epi == LEPI_QKV) {
+      const int b = mt / g.n_kt, j = mt - b * g.n_kt;
+      src0 = b * g.T + j * LM;
+      nvalid = mt < n_mt ? min(LM, g.T - j * LM) : 0;
+    } else {
+      src0 = mt * LM;
+      nvalid = min(LM, g.M - mt * LM);
+    }
+  };
 
   if (warp < L_PROD_WARPS) {
     // ================= producers =================
@@ -94,18 +111,20 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
     float4 v[16];
     auto load = [&]() {
       if (t >= n_tiles) return;
-      const int mt = (t / n_nt) * CS + rank, m0 = mt * LM;
+      const int mt = (t / n_nt) * CS + rank;
+      int m0, nvalid;
+      tile_rows(mt, m0, nvalid);
       const float* ap = g.A + (size_t)m0 * g.lda + kc * LK + 4 * c4;
       const bool vec = (g.lda & 3) == 0 && (kc + 1) * LK <= g.Kr;      // else: rows not 16-byte aligned / ragged K (input layer)
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int r = r0 + 8 * j;
         if (vec) {
-          v[j] = (m0 + r < g.M) ? __ldg(reinterpret_cast<const float4*>(ap + (size_t)r * g.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[j] = (r < nvalid) ? __ldg(reinterpret_cast<const float4*>(ap + (size_t)r * g.lda)) : make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
           const float* q = ap + (size_t)r * g.lda;
           const int k = kc * LK + 4 * c4;
-          const bool in = m0 + r < g.M;
+          const bool in = r < nvalid;
           v[j].x = (in && k < g.Kr) ? __ldg(q) : 0.f;         v[j].y = (in && k + 1 < g.Kr) ? __ldg(q + 1) : 0.f;
           v[j].z = (in && k + 2 < g.Kr) ? __ldg(q + 2) : 0.f; v[j].w = (in && k + 3 < g.Kr) ? __ldg(q + 3) : 0.f;
         }
@@ -185,8 +204,10 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
     auto epi_sync = [] { asm volatile("bar.sync 1, 128;" ::: "memory"); };
     int lt = 0;
     for (int t = cid; t < n_tiles; t += n_cl, ++lt) {
-      const int mt = (t / n_nt) * CS + rank, nt = t % n_nt, m = mt * LM + row, n0 = nt * LNT;
-      const int mw = mt * LM + ew * 32;      // first row of this warp
+      const int mt = (t / n_nt) * CS + rank, nt = t % n_nt, n0 = nt * LNT;
+      int src0, nvalid;
+      tile_rows(mt, src0, nvalid);
+      const int mw = src0 + ew * 32, nw = nvalid - ew * 32;      // first row of this warp; rows r < nw of the warp exist
       const int buf = lt & 1, u = lt >> 1;
       // registers (thread = row) -> global rows of the warp, columns n0 + c0 .. + 31
       auto store_rows = [&](const float (&v)[32], int c0) {
@@ -196,7 +217,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int r = 4 * j + sub_r;
-          if (mw + r < g.M)
+          if (r < nw)
             *reinterpret_cast<float4*>(g.out + (size_t)(mw + r) * g.ldo + n0 + c0 + sub_c) = *reinterpret_cast<const float4*>(wst + r * L_STAGE_LD + sub_c);
         }
         __syncwarp();
@@ -206,7 +227,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int r = 4 * j + sub_r;
-          const float4 x = (mw + r < g.M) ? __ldg(reinterpret_cast<const float4*>(rowptr(mw + r) + c0 + sub_c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 x = (r < nw) ? __ldg(reinterpret_cast<const float4*>(rowptr(mw + r) + c0 + sub_c)) : make_float4(0.f, 0.f, 0.f, 0.f);
           *reinterpret_cast<float4*>(wst + r * L_STAGE_LD + sub_c) = x;
         }
         __syncwarp();
@@ -236,8 +257,47 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
           __syncwarp();
           const int col = n0 + 32 * c8 + lane;
           for (int r = 0; r < 32; ++r)
-            if (mw + r < g.M && col < g.Nr) g.out[(size_t)(mw + r) * g.ldo + col] = wst[r * L_STAGE_LD + lane];
+            if (r < nw && col < g.Nr) g.out[(size_t)(mw + r) * g.ldo + col] = wst[r * L_STAGE_LD + lane];
           __syncwarp();
+        }
+      } else if (g.epi == LEPI_QKV && nt > 0) {
+        // K (nt = 1) / V (nt = 2) of key tile (b, j), head c8 -> the operand image; the tile's rows are its keys (rows beyond T: zeros)
+        if (mt < n_mt) {
+          const int b = mt / g.n_kt, j = mt - b * g.n_kt;
+#pragma unroll 1
+          for (int c8 = 0; c8 < 8; ++c8) {
+            float v[32];
+            tmem_ld32(d_addr + 32 * c8, v); tmem_wait_ld();
+            unsigned char* img = g.kv + ((size_t)(b * g.n_heads + c8) * g.n_kt + j) * L_KV_TILE;
+            if (nt == 1) {      // (key, 8 channels) -> one 16-byte row of a core matrix: off = (key >> 3) 512 + u 128 + (key & 7) 16
+              const uint32_t off0 = (uint32_t)(row >> 3) * 512 + (row & 7) * 16;
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                uint4 hi, lo;
+                split_h2(v[8 * u], v[8 * u + 1], hi.x, lo.x); split_h2(v[8 * u + 2], v[8 * u + 3], hi.y, lo.y);
+                split_h2(v[8 * u + 4], v[8 * u + 5], hi.z, lo.z); split_h2(v[8 * u + 6], v[8 * u + 7], hi.w, lo.w);
+                *reinterpret_cast<uint4*>(img + off0 + u * 128) = hi;
+                *reinterpret_cast<uint4*>(img + L_KV_PART + off0 + u * 128) = lo;
+              }
+            } else {            // V^T: (channel, 8 keys) -> one 16-byte row: off = (d >> 3) 2048 + kg 128 + (d & 7) 16; lane = channel
+#pragma unroll
+              for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(wst + lane * L_STAGE_LD + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              __syncwarp();
+              unsigned char* vimg = img + 2 * L_KV_PART + (uint32_t)(lane >> 3) * 2048 + (lane & 7) * 16;
+#pragma unroll
+              for (int kg = 0; kg < 4; ++kg) {
+                float x[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] = wst[(8 * kg + e) * L_STAGE_LD + lane];
+                uint4 hi, lo;
+                split_h2(x[0], x[1], hi.x, lo.x); split_h2(x[2], x[3], hi.y, lo.y);
+                split_h2(x[4], x[5], hi.z, lo.z); split_h2(x[6], x[7], hi.w, lo.w);
+                *reinterpret_cast<uint4*>(vimg + (4 * ew + kg) * 128) = hi;
+                *reinterpret_cast<uint4*>(vimg + L_KV_PART + (4 * ew + kg) * 128) = lo;
+              }
+              __syncwarp();
+            }
+          }
         }
       } else if (g.epi != LEPI_RES_LN) {
 #pragma unroll 1
@@ -363,22 +423,14 @@ int mhanet_umma_prepare(dxi_net& net, cudaStream_t st) {
   return DXI_OK;
 }
 
-// image: index into net.umma_stage_offset (4 blk + {0 qkv, 1 projection, 2 ffn in, 3 ffn out}; 4 n_blocks: input layer, + 1: output)
-int mhanet_umma_linear(const dxi_net& net, int image, int epi, const float* A, int lda, const float* bias, const float* res,
-                       const float* gamma, const float* beta, const float* pos, int T, float* out, int ldo, int M, int Nr, int Kr,
-                       cudaStream_t st) {
-  if (!net.d_umma || (size_t)image >= net.umma_stage_offset.size()) { set_error("tcgen05 weight images missing"); return DXI_E_STATE; }
-  const int N = (Nr + LNT - 1) / LNT * LNT, K = (Kr + LK - 1) / LK * LK;
-  LinArgs g{A, lda, reinterpret_cast<const unsigned char*>(net.d_umma) + net.umma_stage_offset[image], bias, res, gamma, beta, pos, T,
-            out, ldo, M, N, K, epi, Nr, Kr};
-  if (epi == LEPI_RES_LN && Nr != LNT) { set_error("lin_umma: LayerNorm epilogue needs N = 256"); return DXI_E_INVALID; }
-  if (epi != LEPI_SIGMOID && ((ldo & 3) || Nr != N)) { set_error("lin_umma: unaligned outputs only through the sigmoid epilogue"); return DXI_E_INVALID; }
+static int lin_launch(const LinArgs& g, cudaStream_t st) {
   int n_sm = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
-  const int n_mt = (M + LM - 1) / LM, n_nt = N / LNT;
+  const int n_mt = (g.M + LM - 1) / LM, n_nt = g.N / LNT;
   // DXI_LIN_CLUSTER = 2 / 4: clusters of that many row tiles share every weight chunk by multicast.  Measured on B200 at 64 x 1875 frames:
   // 4.85 ms (1), 4.92 ms (2), slower at 4 (fewer SMs fit whole clusters) - the L2 already merges the concurrent reads of a chunk.
   int cs = 1;
+  if (const char* e = getenv("DXI_LIN_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) cs = v; }
   auto kern = cs == 4 ? lin_umma_kernel<4> : cs == 2 ? lin_umma_kernel<2> : lin_umma_kernel<1>;
   DXI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM));      // per device, so per call
   cudaLaunchConfig_t cfg{};
@@ -400,6 +452,34 @@ int mhanet_umma_linear(const dxi_net& net, int image, int epi, const float* A, i
   DXI_CUDA(cudaLaunchKernelEx(&cfg, kern, g));
   DXI_LAUNCHED("lin_umma_kernel");
   return DXI_OK;
+}
+
+// image: index into net.umma_stage_offset (4 blk + {0 qkv, 1 projection, 2 ffn in, 3 ffn out}; 4 n_blocks: input layer, + 1: output)
+int mhanet_umma_linear(const dxi_net& net, int image, int epi, const float* A, int lda, const float* bias, const float* res,
+                       const float* gamma, const float* beta, const float* pos, int T, float* out, int ldo, int M, int Nr, int Kr,
+                       cudaStream_t st) {
+  if (!net.d_umma || (size_t)image >= net.umma_stage_offset.size()) { set_error("tcgen05 weight images missing"); return DXI_E_STATE; }
+  const int N = (Nr + LNT - 1) / LNT * LNT, K = (Kr + LK - 1) / LK * LK;
+  LinArgs g{A, lda, reinterpret_cast<const unsigned char*>(net.d_umma) + net.umma_stage_offset[image], bias, res, gamma, beta, pos, T,
+            out, ldo, M, N, K, epi, Nr, Kr};
+  if (epi == LEPI_QKV) { set_error("lin_umma: the fused QKV epilogue is launched through mhanet_umma_qkv"); return DXI_E_INVALID; }
+  if (epi == LEPI_RES_LN && Nr != LNT) { set_error("lin_umma: LayerNorm epilogue needs N = 256"); return DXI_E_INVALID; }
+  if (epi != LEPI_SIGMOID && ((ldo & 3) || Nr != N)) { set_error("lin_umma: unaligned outputs only through the sigmoid epilogue"); return DXI_E_INVALID; }
+  return lin_launch(g, st);
+}
+
+// Fused QKV projection of block blk: x [B T][d] -> Q (fp32, columns 0 .. d - 1 of qkv [B T][3 d]) and the packed K / V key tiles of the
+// tensor-core attention (kv: mhanet_umma_attention_workspace bytes).  The K / V columns of qkv are NOT written.
+int mhanet_umma_qkv(const dxi_net& net, int blk, const float* x, int B, int T, float* qkv, void* kv, cudaStream_t st) {
+  const dxi_net_cfg& c = net.cfg;
+  const int d = c.d_model, image = 4 * blk;
+  if (!net.d_umma || (size_t)image >= net.umma_stage_offset.size()) { set_error("tcgen05 weight images missing"); return DXI_E_STATE; }
+  if (d != LNT || d / c.n_heads != 32) { set_error("lin_umma: the fused QKV epilogue is built for d_model 256, head size 32"); return DXI_E_INVALID; }
+  const int n_kt = (T + LM - 1) / LM;
+  LinArgs g{x, d, reinterpret_cast<const unsigned char*>(net.d_umma) + net.umma_stage_offset[image], nullptr, nullptr, nullptr, nullptr, nullptr, T,
+            qkv, 3 * d, B * n_kt * LM, 3 * d, d, LEPI_QKV, 3 * d, d};
+  g.kv = reinterpret_cast<unsigned char*>(kv); g.n_kt = n_kt; g.n_heads = c.n_heads;
+  return lin_launch(g, st);
 }
 
 }  // namespace dxi

@@ -285,14 +285,19 @@ int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xb
     snprintf(nm, sizeof(nm), "packed-%d/qkv", li);
     auto it = net.d_offset.find(nm);
     if (it == net.d_offset.end()) { set_error("packed QKV weights missing"); return DXI_E_STATE; }
-    if (tc) {
+    const bool attn_tc = tc && !(getenv("DXI_MHA_ATTN_F32") && atoi(getenv("DXI_MHA_ATTN_F32")));
+    // the QKV projection writes K / V straight into the attention kernel's operand images (DXI_MHA_UNFUSED_PACK=1: fp32 K / V + a packing pass, for A/B)
+    const bool fused_pack = attn_tc && !(getenv("DXI_MHA_UNFUSED_PACK") && atoi(getenv("DXI_MHA_UNFUSED_PACK")));
+    if (fused_pack) {
+      if (int rc = mhanet_umma_qkv(net, blk, x, B, T, qkv, f, st)) return rc;
+    } else if (tc) {
       if (int rc = mhanet_umma_linear(net, 4 * blk + 0, 0 /* plain */, x, d, nullptr, nullptr, nullptr, nullptr, nullptr, T, qkv, 3 * d, rows, 3 * d, d, st)) return rc;
     } else {
       g = GemmArgs{x, d, net.d_arena + it->second, nullptr, nullptr, nullptr, nullptr, nullptr, qkv, 3 * d, rows, 3 * d, d, T, EPI_BIAS};
       if (int rc = launch_gemm(g, st, "mha_gemm")) return rc;
     }
-    if (tc && !(getenv("DXI_MHA_ATTN_F32") && atoi(getenv("DXI_MHA_ATTN_F32")))) {
-      if (int rc = mhanet_umma_attention(net, qkv, valid, B, T, att, f, st)) return rc;
+    if (attn_tc) {
+      if (int rc = mhanet_umma_attention(net, qkv, valid, B, T, att, f, fused_pack, st)) return rc;
     } else {
       dim3 grid((T + AQ - 1) / AQ, c.n_heads, B);
       ProfScope prof("mha_attn", st, 1);

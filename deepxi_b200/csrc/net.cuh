@@ -60,7 +60,8 @@ int mhanet_forward(const dxi_net& net, const float* mag, int B, int T, float* xb
                    cudaStream_t st);
 int mhanet_umma_prepare(dxi_net& net, cudaStream_t st);
 size_t mhanet_umma_attention_workspace(const dxi_net& net, int B, int T);
-int mhanet_umma_attention(const dxi_net& net, const float* qkv, const uint8_t* valid, int B, int T, float* att, void* kv, cudaStream_t st);
+int mhanet_umma_qkv(const dxi_net& net, int blk, const float* x, int B, int T, float* qkv, void* kv, cudaStream_t st);
+int mhanet_umma_attention(const dxi_net& net, const float* qkv, const uint8_t* valid, int B, int T, float* att, void* kv, bool kv_packed, cudaStream_t st);
 int mhanet_umma_linear(const dxi_net& net, int image, int epi, const float* A, int lda, const float* bias, const float* res,
                        const float* gamma, const float* beta, const float* pos, int T, float* out, int ldo, int M, int Nr, int Kr,
                        cudaStream_t st);

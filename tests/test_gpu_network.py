@@ -266,6 +266,25 @@ def test_mhanetv3_linear_layers_cluster_sizes_agree(lens, monkeypatch):
     assert np.array_equal(out['1'], out['2']) and np.array_equal(out['1'], out['4'])
 
 
+@pytest.mark.parametrize('mask_mode', ['none', 'causal+pad'])
+@pytest.mark.parametrize('lens', [[150000, 90000, 33333], [300], [32768, 32767]])
+def test_mhanetv3_fused_kv_pack_agrees_with_packing_pass(lens, mask_mode, monkeypatch):
+    """The QKV projection writes K / V straight into the attention kernel's operand images (row space padded per utterance to whole
+    key tiles, mha_umma.cu LEPI_QKV); DXI_MHA_UNFUSED_PACK=1 writes fp32 K / V and packs them in a separate pass.  Same MMAs, same
+    rounding: bit-identical, for ragged utterances, T = 2 and T exactly one / one short of a tile (128 / 127 frames)."""
+    w = weights.synthetic_mhanetv3(5)
+    x = synth.noisy_speech(len(lens), max(lens), seed=65)
+    inp, _, _ = osig.observation_batch(x, lens)
+    net = network_selector('MHANetV3', None, 257, mask_mode=mask_mode, precision='f16x3', **MHA_KW).load_weights(w)
+    fused = np.asarray(net(inp))
+    monkeypatch.setenv('DXI_MHA_UNFUSED_PACK', '1')
+    unfused = np.asarray(net(inp))
+    assert np.isfinite(fused).all() and np.array_equal(fused, unfused)
+    monkeypatch.delenv('DXI_MHA_UNFUSED_PACK')
+    monkeypatch.setenv('DXI_LIN_CLUSTER', '2')
+    assert np.array_equal(fused, np.asarray(net(inp)))
+
+
 def test_mhanetv3_infer_and_limits(xi_stats):
     w = weights.synthetic_mhanetv3(1)
     dx = DeepXi(512, 256, 512, 16000, 'MagXi', 'MHANetV3', ver='mhanet-1.1c', map_type='DBNormalCDF', map_params=None,
