@@ -58,7 +58,7 @@ struct LinArgs {
 };
 
 template <int CS>
-__global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g) {
+__global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g) {      // 13 warps are allocated as 16: 128 registers is the cap
   extern __shared__ unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_a[2], full_w[2], empty[2], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
@@ -222,22 +222,24 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
         }
         __syncwarp();
       };
-      // global rows (row r of the warp at rowptr(r), 32 floats from column c0) -> registers (thread = row); rows beyond M: zeros
-      auto load_rows = [&](auto rowptr, int c0, float (&v)[32]) {
+      // global rows (row r of the warp at rowptr(r), 32 floats from column c0) -> registers (thread = row); rows beyond M: zeros.
+      // Two halves, so that the loads of the NEXT chunk are in flight while this one is processed (their latency, eight times per
+      // tile, was what the LayerNorm epilogue of the K = 256 projection cost).
+      auto fetch_rows = [&](auto rowptr, int c0, float4 (&x)[8]) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int r = 4 * j + sub_r;
-          const float4 x = (r < nw) ? __ldg(reinterpret_cast<const float4*>(rowptr(mw + r) + c0 + sub_c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(wst + r * L_STAGE_LD + sub_c) = x;
+          x[j] = (r < nw) ? __ldg(reinterpret_cast<const float4*>(rowptr(mw + r) + c0 + sub_c)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        __syncwarp();
+      };
+      // ... stage_rows puts them into the warp's stage; thread = row then reads its 32 values as staged(q), q = 0..7, and the warp
+      // synchronises before the stage is written again
+      auto stage_rows = [&](const float4 (&x)[8]) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 x = *reinterpret_cast<const float4*>(wst + lane * L_STAGE_LD + 4 * q);
-          v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-        }
+        for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(wst + (4 * j + sub_r) * L_STAGE_LD + sub_c) = x[j];
         __syncwarp();
       };
+      auto staged = [&](int q) { return *reinterpret_cast<const float4*>(wst + lane * L_STAGE_LD + 4 * q); };
       epi_sync();                                                  // previous tile's readers of sVec are done
       for (int i = et; i < LNT; i += 128) {
         sVec[i] = (g.bias && n0 + i < g.Nr) ? __ldg(g.bias + n0 + i) : 0.0f;
@@ -314,15 +316,27 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
       } else {
         // y = acc + bias + residual, kept in TMEM; LayerNorm(y) * gamma + beta (Keras non-fused order, eps 1e-6)
         float mean = 0.0f, m2 = 0.0f;
+        auto res_row = [&](int mm) { return g.res + (size_t)mm * g.N; };
+        auto pos_row = [&](int mm) { return g.pos + (size_t)(mm % g.T) * LNT; };
+        float4 nx[8];
+        if (g.res) fetch_rows(res_row, 0, nx);
 #pragma unroll 1
         for (int c8 = 0; c8 < 8; ++c8) {
-          float v[32], rs[32];
+          float v[32];
           tmem_ld32(d_addr + 32 * c8, v);
-          if (g.res) load_rows([&](int mm) { return g.res + (size_t)mm * g.N; }, 32 * c8, rs);
+          if (g.res) {
+            stage_rows(nx);
+            if (c8 + 1 < 8) fetch_rows(res_row, 32 * (c8 + 1), nx);
+          }
           tmem_wait_ld();
           float s = 0.0f;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) { v[e] += sVec[32 * c8 + e] + (g.res ? rs[e] : 0.0f); }
+          for (int q = 0; q < 8; ++q) {
+            const float4 r4 = g.res ? staged(q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * q] += sVec[32 * c8 + 4 * q] + r4.x;         v[4 * q + 1] += sVec[32 * c8 + 4 * q + 1] + r4.y;
+            v[4 * q + 2] += sVec[32 * c8 + 4 * q + 2] + r4.z; v[4 * q + 3] += sVec[32 * c8 + 4 * q + 3] + r4.w;
+          }
+          __syncwarp();      // the stage is free again
 #pragma unroll
           for (int q = 0; q < 8; ++q) s += (v[4 * q] + v[4 * q + 1]) + (v[4 * q + 2] + v[4 * q + 3]);
           const float mc = s * (1.0f / 32.0f);
@@ -337,19 +351,30 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
         }
         tmem_wait_st();
         const float rstd = rsqrtf(m2 * (1.0f / LNT) + 1e-6f);
+        if (g.pos) fetch_rows(pos_row, 0, nx);
 #pragma unroll 1
         for (int c8 = 0; c8 < 8; ++c8) {
-          float v[32], pe[32];
+          float v[32];
           tmem_ld32(d_addr + 32 * c8, v);
-          if (g.pos) load_rows([&](int mm) { return g.pos + (size_t)(mm % g.T) * LNT; }, 32 * c8, pe);
+          if (g.pos) {
+            stage_rows(nx);
+            if (c8 + 1 < 8) fetch_rows(pos_row, 32 * (c8 + 1), nx);
+          }
           tmem_wait_ld();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int c = 32 * c8 + e;
-            const float inv = rstd * sVec[LNT + c];
-            v[e] = fmaf(v[e], inv, sVec[2 * LNT + c] - mean * inv);
-            if (g.pos) v[e] = fmaxf(v[e], 0.0f) + pe[e];
+          for (int q = 0; q < 8; ++q) {
+            const float4 p4 = g.pos ? staged(q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float pe[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = 32 * c8 + 4 * q + e;
+              const float inv = rstd * sVec[LNT + c];
+              float y = fmaf(v[4 * q + e], inv, sVec[2 * LNT + c] - mean * inv);
+              if (g.pos) y = fmaxf(y, 0.0f) + pe[e];
+              v[4 * q + e] = y;
+            }
           }
+          __syncwarp();      // the stage is free again
           store_rows(v, 32 * c8);
         }
       }
