@@ -165,7 +165,7 @@ __global__ void __launch_bounds__((4 * NH + 2) * 32, 2) attn_umma_kernel(const A
       const int nk = n_ktiles(qt);
       for (int j = 0; j < nk; ++j, ++kt) {
         const int k0 = j * AT + KH * half;                     // first key of this thread's half of the tile
-        mbar_wait(&s_full[half], kt & 1); tc_fence_after();
+        mbar_wait_bounded(&s_full[half], kt & 1); tc_fence_after();
         const uint8_t* vk = sValid + slot * AT + KH * half;
         slot = slot + 1 == A_SLOTS ? 0 : slot + 1;
         auto logit = [&](float s, int c) -> float {          // c: key index inside the half tile
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__((4 * NH + 2) * 32, 2) attn_umma_kernel(const A
         }
         const float m_new = fmaxf(m_run, mx);
         const float alpha = (m_run == -INFINITY) ? 0.0f : fast_ex2(m_run - m_new);
-        if (kt > 0) { mbar_wait(&pv_done[half], (kt - 1) & 1); tc_fence_after(); }      // P and O of this half are free again
+        if (kt > 0) { mbar_wait_bounded(&pv_done[half], (kt - 1) & 1); tc_fence_after(); }      // P and O of this half are free again
         float2 psum = make_float2(0.0f, 0.0f);
         const float2 nm = make_float2(-m_new, -m_new);
         {
@@ -259,8 +259,8 @@ __global__ void __launch_bounds__((4 * NH + 2) * 32, 2) attn_umma_kernel(const A
         } else {
           ia = 1.0f / l_run;
         }
-        mbar_wait(&pv_done[0], (kt - 1) & 1);
-        if (NH == 2) mbar_wait(&pv_done[NH - 1], (kt - 1) & 1);
+        mbar_wait_bounded(&pv_done[0], (kt - 1) & 1);
+        if (NH == 2) mbar_wait_bounded(&pv_done[NH - 1], (kt - 1) & 1);
         tc_fence_after();
         float* dst = g.att + ((size_t)b * g.T + qi) * g.d_model + h * AHD;
 #pragma unroll
@@ -327,8 +327,8 @@ __global__ void __launch_bounds__((4 * NH + 2) * 32, 2) attn_umma_kernel(const A
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int qt = item % n_qt;
       const int nk = n_ktiles(qt);
-      mbar_wait(&q_full, it & 1);
-      mbar_wait(&kv_full[slot], use & 1); tc_fence_after();
+      mbar_wait_bounded(&q_full, it & 1);
+      mbar_wait_bounded(&kv_full[slot], use & 1); tc_fence_after();
 #pragma unroll
       for (int hf = 0; hf < NH; ++hf) issue_s(hf, slot);
       for (int j = 0; j < nk; ++j, ++kt) {
@@ -337,7 +337,7 @@ __global__ void __launch_bounds__((4 * NH + 2) * 32, 2) attn_umma_kernel(const A
         const uint32_t v_hi = smem_u32(ring + slot * A_SLOT) + 2 * AK_PART, v_lo = v_hi + AK_PART;
 #pragma unroll
         for (int hf = 0; hf < NH; ++hf) {
-          mbar_wait(&p_ready[hf], kt & 1); tc_fence_after();
+          mbar_wait_bounded(&p_ready[hf], kt & 1); tc_fence_after();
 #pragma unroll
           for (int part = 0; part < 3; ++part) {
             const uint32_t b0 = part == 2 ? v_lo : v_hi;
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__((4 * NH + 2) * 32, 2) attn_umma_kernel(const A
           mma_commit_lo(&pv_done[hf], e);
           if (hf == NH - 1) mma_commit_lo(&kv_empty[slot], e);      // every product that reads the slot has been issued
           if (j + 1 < nk) {
-            if (hf == 0) { mbar_wait(&kv_full[nslot], nuse & 1); tc_fence_after(); }
+            if (hf == 0) { mbar_wait_bounded(&kv_full[nslot], nuse & 1); tc_fence_after(); }
             issue_s(hf, nslot);
           }
         }
