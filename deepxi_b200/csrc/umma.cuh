@@ -12,6 +12,7 @@
 //     tcgen05.st.32x32b (thread i of warp w <-> lane 32*(w&3)+i).
 //   D in tensor memory: element (m, n) at lane m, column n (fp32).
 #pragma once
+#include <cstdio>
 #include "common.cuh"
 
 namespace dxi {
@@ -49,6 +50,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 constexpr long long SPIN_LIMIT_CYCLES = 4000000000ll;
 // The retry loop is out of line: a kernel with ~25 waits per iteration would otherwise carry ~300 instructions of it in its hot loop,
 // and these kernels are sensitive to the instruction-cache footprint of that loop.
+#ifdef DXI_ENABLE_DEBUG
+static __device__ int g_mbar_abort = 0;
+#endif
 static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) {
   const long long t0 = clock64();
   uint32_t n = 0;
@@ -62,7 +66,19 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t p
         : "r"(bar_addr), "r"(parity)
         : "memory");
     if (ok) return;
+#ifdef DXI_ENABLE_DEBUG
+    // tuning build: name the wait that timed out (barrier address inside the CTA's shared window) and give up on it, so that the kernel
+    // ends and the message is printed; the launch's results are then meaningless
+    if ((++n & 1023u) == 0) {
+      if (g_mbar_abort) return;
+      if (clock64() - t0 > 200000000ll) {
+        if ((threadIdx.x & 31) == 0) printf("mbarrier wait timed out: block %d warp %d barrier 0x%x parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), bar_addr, parity);
+        if (clock64() - t0 > 260000000ll) { g_mbar_abort = 1; return; }      // a little later, so that every wait stuck at the same time reports
+      }
+    }
+#else
     if ((++n & 1023u) == 0 && clock64() - t0 > SPIN_LIMIT_CYCLES) __trap();
+#endif
   }
 }
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
