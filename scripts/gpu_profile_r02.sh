@@ -13,4 +13,10 @@ ncu --set full --clock-control none --import-source on -k regex:tcn_chain -s 3 -
 echo "tcn full rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:"stft_kernel|istft_kernel" -s 6 -c 2 -o gpurun_out/r02_prof_signal -f $CMD > gpurun_out/ncu_signal.log 2>&1
 echo "signal full rc=$?"
+# MHANetV3 (C3 shape): one block of the network = QKV projection (with the fused K / V images), attention, projection, feed-forward in / out
+MCMD="python scripts/mhanet_time.py 64 1875 f16x3"
+$MCMD > gpurun_out/mha_plain.log 2>&1 || { echo "mha plain run failed"; tail -20 gpurun_out/mha_plain.log; exit 1; }
+tail -3 gpurun_out/mha_plain.log
+ncu --set full --clock-control none --import-source on -k regex:"lin_umma|attn_umma" -s 28 -c 5 -o gpurun_out/r02_prof_mhanet -f $MCMD > gpurun_out/ncu_mha.log 2>&1
+echo "mha full rc=$?"
 ls -la gpurun_out | head -30
