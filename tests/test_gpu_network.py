@@ -285,6 +285,30 @@ def test_mhanetv3_fused_kv_pack_agrees_with_packing_pass(lens, mask_mode, monkey
     assert np.array_equal(fused, np.asarray(net(inp)))
 
 
+@pytest.mark.parametrize('mask_mode', ['none', 'causal+pad'])
+def test_mhanetv3_more_work_items_than_ctas(xi_stats, mask_mode):
+    """40 utterances x 3 query tiles x 8 heads = 960 attention work items for 296 resident CTAs, 94 x 3 output tiles of the QKV projection
+    for 148: every persistent CTA walks several items, so the operand rings wrap and every barrier passes through both parities many
+    times.  Checked against the exact fp32 CUDA path (precision 'f32'; that path is held to the float64 oracle by the tests above)."""
+    mu, sg = xi_stats['mhanet-1.1c/mu'], xi_stats['mhanet-1.1c/sigma']
+    w = weights.synthetic_mhanetv3(6)
+    rng = np.random.default_rng(66)
+    lens = [int(v) for v in rng.integers(30000, 76800, size=40)]
+    lens[0] = 76800                                                  # T = 300 frames: three tiles, the last with 44 rows
+    x = synth.noisy_speech(40, 76800, seed=67)
+    inp, _, nfr = osig.observation_batch(x, lens)
+    ref = np.asarray(network_selector('MHANetV3', None, 257, mask_mode=mask_mode, precision='f32', **MHA_KW).load_weights(w)(inp))
+    net = network_selector('MHANetV3', None, 257, mask_mode=mask_mode, precision='f16x3', **MHA_KW).load_weights(w)
+    xbar = np.asarray(net(inp))
+    assert np.isfinite(xbar).all()
+    worst = 0.0
+    for i, n in enumerate(nfr):
+        rows = slice(0, n) if mask_mode == 'causal+pad' else slice(0, 300)
+        worst = max(worst, _db_err(xbar[i, rows], ref[i, rows].astype(np.float64), mu, sg).max())
+    assert worst < 5e-3, (mask_mode, worst)
+    assert np.array_equal(xbar, np.asarray(net(inp)))
+
+
 def test_mhanetv3_infer_and_limits(xi_stats):
     w = weights.synthetic_mhanetv3(1)
     dx = DeepXi(512, 256, 512, 16000, 'MagXi', 'MHANetV3', ver='mhanet-1.1c', map_type='DBNormalCDF', map_params=None,
