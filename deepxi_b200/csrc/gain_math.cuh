@@ -209,10 +209,10 @@ __device__ __forceinline__ float lsa_gain_from_xbar_fast(float xbar, float mu, f
 // With gamma_hat = xi_hat + 1 the MMSE-LSA gain is a function of xi_hat alone, smooth and monotone in dB:
 //   g(t) = log2 G,  G = xi / (1 + xi) * exp(E1(xi) / 2),  xi = 10^(t / 10).
 // g is tabulated as piecewise cubics (Hermite data from the analytic derivative, float64 on the host) on [LSA_TAB_LO, LSA_TAB_HI] dB
-// in steps of 0.5 dB: |2^cubic / G - 1| < 1e-7.  Below the table g follows its asymptote t log2(10)/20 - gamma_E / (2 ln 2)
-// (error < 1e-10 at -100 dB); above it G = 1 - O(1e-6).  One LDS.128 + 3 FMA + ex2 replace the E1 branches, two ex2 and an rcp.
-constexpr int LSA_TAB_N = 320;
-constexpr float LSA_TAB_LO = -100.0f, LSA_TAB_HI = 60.0f, LSA_TAB_INV_H = 2.0f;
+// in steps of 0.5 dB: |2^cubic / G - 1| < 1e-7.  The table starts where xi_hat is clamped (1e-12 = -120 dB, gain.py:60), so the clamp is
+// the clamp of the table position; above the table G = 1 - O(1e-6).  One LDS.128 + 3 FMA + ex2 replace the E1 branches, two ex2 and an rcp.
+constexpr int LSA_TAB_N = 360;
+constexpr float LSA_TAB_LO = -120.0f, LSA_TAB_HI = 60.0f, LSA_TAB_INV_H = 2.0f;
 
 // Host: the LSA_TAB_N cubics c0 + c1 f + c2 f^2 + c3 f^3, f in [0, 1) the position inside the interval.
 static inline void lsa_table_build(float4* tab) {
@@ -253,9 +253,7 @@ __device__ __forceinline__ float lsa_gain_from_xbar_tab(float xbar, float mu, fl
   const int i = (int)pos;
   const float f = pos - (float)i;
   const float4 c = tab[i];
-  float g = fmaf(fmaf(fmaf(c.w, f, c.z), f, c.y), f, c.x);
-  if (t < LSA_TAB_LO) g = fmaf(fmaxf(t, -120.0f), 0.16609640f, -0.41636583f);      // xi is clamped at 1e-12 (gain.py:60)
-  return fast_ex2(g);
+  return fast_ex2(fmaf(fmaf(fmaf(c.w, f, c.z), f, c.y), f, c.x));
 }
 
 }  // namespace dxi

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(256, ISTFT_CTAS_PER_SM) istft_kernel(const flo
                                                     const float* __restrict__ sigma, int gtype,
                                                     const int32_t* __restrict__ n_frames, int B, int Tmax,
                                                     int strips_per_utt, int hops_per_strip, float* __restrict__ wav_f32,
-                                                    int16_t* __restrict__ wav_i16, int64_t out_stride) {
+                                                    int16_t* __restrict__ wav_i16, int64_t out_stride, int out_vec) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   IstftSmem& sm = *reinterpret_cast<IstftSmem*>(smem_raw);
   const int tid = threadIdx.x;
@@ -266,6 +266,23 @@ __global__ void __launch_bounds__(256, ISTFT_CTAS_PER_SM) istft_kernel(const flo
         constexpr int NU = 4;      // frames per iteration: 3 NU loads in flight per thread (NU = 2 has no spills at 64 registers but is 8 % slower)
         for (int fi = 0; fi < nf; fi += NU) {
           float mv[NU], pv[NU], gv[NU];
+          const int t0 = f0 + fi;
+          if (fi + NU <= nf && t0 >= 0 && t0 + NU <= T) {
+            // all NU frames exist (every pass but a strip's first and an utterance's last): one base index, constant row offsets, no tests
+            const int64_t g0 = in0 + (int64_t)t0 * NBINS + k;
+            const float* pm = mag + g0;
+            const float* pp = phase + g0;
+            const float* pg = (MODE != 0 || gain_or_xbar) ? gain_or_xbar + g0 : nullptr;
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+              mv[u] = __ldcs(pm + u * NBINS);
+              pv[u] = __ldcs(pp + u * NBINS);
+              gv[u] = pg ? __ldcs(pg + u * NBINS) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < NU; ++u) spectrum(fi + u, k, mv[u], pv[u], gv[u], true, mu_k, sg_k, s2_k);
+            continue;
+          }
           bool ok[NU];
 #pragma unroll
           for (int u = 0; u < NU; ++u) {
@@ -326,6 +343,21 @@ __global__ void __launch_bounds__(256, ISTFT_CTAS_PER_SM) istft_kernel(const flo
       __syncthreads();
       // ---- overlap-add: hop t = head(frame t) + tail(frame t-1); coalesced stores
       const int first = (f0 == hs - 1) ? 1 : 0;
+      if (out_vec) {      // four samples per thread and iteration (rows 16-byte / 8-byte aligned: istft_launch checks)
+        for (int i4 = tid + first * (N_S / 4); i4 < nf * (N_S / 4); i4 += 256) {
+          const int fi = i4 >> 6, n = (i4 & 63) * 4;
+          const float4 a = *reinterpret_cast<const float4*>(frame_of(fi) + n);
+          const float4 c = fi > 0 ? *reinterpret_cast<const float4*>(frame_of(fi - 1) + N_S + n) : *reinterpret_cast<const float4*>(sm.carry + n);
+          const float4 y = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+          const int64_t o = (int64_t)(f0 + fi) * N_S + n;
+          if (of) __stcs(reinterpret_cast<float4*>(of + o), y);
+          if (oi) {      // utils.py:28 truncation
+            const short4 q = make_short4((short)__float2int_rz(y.x * 32768.0f), (short)__float2int_rz(y.y * 32768.0f),
+                                         (short)__float2int_rz(y.z * 32768.0f), (short)__float2int_rz(y.w * 32768.0f));
+            __stcs(reinterpret_cast<short4*>(oi + o), q);
+          }
+        }
+      } else {
       for (int i = tid + first * N_S; i < nf * N_S; i += 256) {
         const int fi = i >> 8, n = i & 255;
         const int t = f0 + fi;
@@ -333,6 +365,7 @@ __global__ void __launch_bounds__(256, ISTFT_CTAS_PER_SM) istft_kernel(const flo
         const int64_t o = (int64_t)t * N_S + n;
         if (of) __stcs(of + o, y);
         if (oi) oi[o] = (int16_t)__float2int_rz(y * 32768.0f);   // utils.py:28 truncation
+      }
       }
       __syncthreads();
       sm.carry[tid] = frame_of(nf - 1)[N_S + tid];
@@ -368,19 +401,21 @@ static int istft_launch(int mode, const float* mag, const float* g_or_xbar, cons
   const int64_t total = (int64_t)B * strips;
   const int grid = (int)(total < cap ? total : cap);
   const size_t smem = sizeof(IstftSmem);
+  // four output samples per store when every row starts 16-byte (f32) / 8-byte (int16) aligned
+  const int out_vec = (out_stride & 3) == 0 && (reinterpret_cast<uintptr_t>(wav_f32) & 15) == 0 && (reinterpret_cast<uintptr_t>(wav_i16) & 7) == 0;
   ProfScope prof(mode == 0 ? "istft" : "enhance", st, 1);
   if (mode == 0) {
     DXI_CUDA(cudaFuncSetAttribute(istft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     istft_kernel<0><<<grid, 256, smem, st>>>(mag, g_or_xbar, phase, mu, sigma, gtype, n_frames, B, Tmax, strips, hops,
-                                             wav_f32, wav_i16, out_stride);
+                                             wav_f32, wav_i16, out_stride, out_vec);
   } else if (gtype == DXI_G_MMSE_LSA && !exact_enhance()) {
     DXI_CUDA(cudaFuncSetAttribute(istft_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     istft_kernel<2><<<grid, 256, smem, st>>>(mag, g_or_xbar, phase, mu, sigma, gtype, n_frames, B, Tmax, strips, hops,
-                                             wav_f32, wav_i16, out_stride);
+                                             wav_f32, wav_i16, out_stride, out_vec);
   } else {
     DXI_CUDA(cudaFuncSetAttribute(istft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     istft_kernel<1><<<grid, 256, smem, st>>>(mag, g_or_xbar, phase, mu, sigma, gtype, n_frames, B, Tmax, strips, hops,
-                                             wav_f32, wav_i16, out_stride);
+                                             wav_f32, wav_i16, out_stride, out_vec);
   }
   DXI_LAUNCHED("istft_kernel");
   return DXI_OK;
