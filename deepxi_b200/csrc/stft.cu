@@ -94,13 +94,22 @@ __global__ void __launch_bounds__(256, 4) stft_kernel(const void* __restrict__ w
 
   const int f = tid >> 4, lane16 = tid & 15;
   const int total = B * groups_per_utt;
+  // g / groups_per_utt without the integer-division sequence (it ran twice per group and thread: 4 % of the kernel's instructions):
+  // the quotient (an utterance index) is far below 2^24, so the float quotient is off by at most one; total < 2^30 (dxi_stft checks)
+  const float inv_gpu = 1.0f / (float)groups_per_utt;
+  auto utt_of = [&](int g) {
+    int b = __float2int_rz((float)g * inv_gpu);
+    if ((b + 1) * groups_per_utt <= g) ++b;
+    if (b * groups_per_utt > g) --b;
+    return b;
+  };
   const elem_t* wav = reinterpret_cast<const elem_t*>(wav_);
   // The (nf + 1) * 256 samples of a group travel HBM -> shared memory as they are (cp.async, 16 bytes per request, zero fill beyond
   // the utterance); the request for the NEXT group is issued as soon as the FFT threads have taken the current samples into
   // registers, so that its latency runs under the split / magnitude / phase phase.  Each sample is read from HBM once.
   auto stage = [&](int g) {
     if (g >= total) return;
-    const int b = g / groups_per_utt, t0 = (g - b * groups_per_utt) * FR;
+    const int b = utt_of(g), t0 = (g - b * groups_per_utt) * FR;
     const int64_t len = min(lens ? (int64_t)lens[b] : stride, stride);
     const int64_t s0 = (int64_t)t0 * N_S;
     if (s0 >= len) return;
@@ -120,7 +129,7 @@ __global__ void __launch_bounds__(256, 4) stft_kernel(const void* __restrict__ w
   stage(blockIdx.x);
   cp_async_commit();
   for (int g = blockIdx.x; g < total; g += gridDim.x) {
-    const int b = g / groups_per_utt, t0 = (g - b * groups_per_utt) * FR;
+    const int b = utt_of(g), t0 = (g - b * groups_per_utt) * FR;
     const int nf = min(FR, Tmax - t0);
     const int64_t len = min(lens ? (int64_t)lens[b] : stride, stride);
     const bool live = (int64_t)t0 * N_S < len;      // else: frames at or beyond ceil(len/256), zeros (model.py:2246-2253 leaves them zero)
@@ -435,7 +444,7 @@ extern "C" DXI_API int dxi_stft(const void* wav, int wav_is_i16, const int32_t* 
   if (int rc = ensure_tables(st)) return rc;
   const int groups = (Tmax + FR - 1) / FR;
   const int64_t total = (int64_t)B * groups;
-  DXI_REQUIRE(total < (1LL << 31), "dxi_stft: batch too large");
+  DXI_REQUIRE(total < (1LL << 30), "dxi_stft: batch too large");
   const int grid = (int)(total < 148 * 4 ? total : 148 * 4);
   const size_t smem = wav_is_i16 ? sizeof(StftSmem<true>) : sizeof(StftSmem<false>);
   const int elem = wav_is_i16 ? 2 : 4;
