@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
     while (t < n_tiles) {
       const int slot = grp, use = gch >> 1;
       const int nt = t % n_nt;
-      if (use >= 1) mbar_wait_bounded(&empty[slot], (use - 1) & 1);       // the MMAs of every CTA of the cluster that read this slot have completed
+      if (use >= 1) mbar_wait_relaxed(&empty[slot], (use - 1) & 1);       // the MMAs of every CTA of the cluster that read this slot have completed
       unsigned char* sA = ring + slot * L_SLOT;
       if (ptid == 0) {
         mbar_arrive_expect_tx(&full_w[slot], L_WCHUNK);
@@ -172,12 +172,12 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
     int gch = 0, lt = 0;
     for (int t = cid; t < n_tiles; t += n_cl, ++lt) {
       const int buf = lt & 1, u = lt >> 1;
-      if (u >= 1) { mbar_wait_bounded(&acc_empty[buf], (u - 1) & 1); tc_fence_after(); }      // the epilogue has drained this accumulator
+      if (u >= 1) { mbar_wait_relaxed(&acc_empty[buf], (u - 1) & 1); tc_fence_after(); }      // the epilogue has drained this accumulator
       const uint32_t d_col = 256u * buf;
       for (int kc = 0; kc < n_kc; ++kc, ++gch) {
         const int slot = gch & 1, use = gch >> 1;
-        mbar_wait_bounded(&full_a[slot], use & 1);
-        mbar_wait_bounded(&full_w[slot], use & 1);
+        mbar_wait_relaxed(&full_a[slot], use & 1);      // the kernel is bound by operand delivery, not by this warp's reaction time:
+        mbar_wait_relaxed(&full_w[slot], use & 1);      // sleeping leaves the issue slots to the producers and the epilogue
         tc_fence_after();
         const uint32_t a32 = desc_lo_sw128(ring_a + slot * L_SLOT), w32 = desc_lo_sw128(ring_a + slot * L_SLOT + 2 * LA_PART);
 #pragma unroll
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
         if (g.epi == LEPI_RES_LN) { sVec[LNT + i] = __ldg(g.gamma + i); sVec[2 * LNT + i] = __ldg(g.beta + i); }
       }
       epi_sync();
-      mbar_wait_bounded(&acc_full[buf], u & 1); tc_fence_after();
+      mbar_wait_relaxed(&acc_full[buf], u & 1); tc_fence_after();
       const uint32_t d_addr = lane_addr + 256u * buf;
       if (g.epi == LEPI_SIGMOID) {
         // sigmoid(acc + bias) -> [M][Nr] with an unaligned row pitch: a warp writes 32 consecutive floats of one row per instruction

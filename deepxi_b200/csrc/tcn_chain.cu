@@ -629,34 +629,34 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
       if (FUSED) {      // first layer: chunks 0, 1 are in flight (kernel prologue / end of the previous tile); the aux record, then 2, 3, then block 0
         if (elect_one()) issue_stem_aux();
         __syncwarp();
-        mbar_wait_bounded(&bars[B_SD], 0u);
+        mbar_wait_relaxed(&bars[B_SD], 0u);
         if (elect_one()) issue_stem(2);
         __syncwarp();
-        mbar_wait_bounded(&bars[B_SD + 1], 0u);
+        mbar_wait_relaxed(&bars[B_SD + 1], 0u);
         if (elect_one()) issue_stem(3);
         __syncwarp();
-        mbar_wait_bounded(&bars[B_SD], 1u);
+        mbar_wait_relaxed(&bars[B_SD], 1u);
         if (elect_one()) issue_w1(0);
         __syncwarp();
-        mbar_wait_bounded(&bars[B_SD + 1], 1u);
+        mbar_wait_relaxed(&bars[B_SD + 1], 1u);
         if (elect_one()) issue_w3(0);
         __syncwarp();
       }
       for (int b = 0; b < nb; ++b, ++it) {
         const uint32_t ph = it & 1u;
         const bool last = b + 1 == nb;
-        mbar_wait_bounded(&bars[B_D3], ph);
+        mbar_wait_relaxed(&bars[B_D3], ph);
         if (elect_one()) { if (!last) issue_w1(b + 1); else { issue_aux_final(); if (FUSED) issue_head(0); } }
         __syncwarp();
-        mbar_wait_bounded(&bars[B_D1], ph);
+        mbar_wait_relaxed(&bars[B_D1], ph);
         if (elect_one()) { if (!last) issue_w2(b + 1); else { if (more) issue_w2(0); if (FUSED) issue_head_aux(); } }
         __syncwarp();
-        mbar_wait_bounded(&bars[B_D2 + 3], ph);
+        mbar_wait_relaxed(&bars[B_D2 + 3], ph);
         if (elect_one()) { if (!last) issue_w3(b + 1); else if (FUSED) issue_head(1); else if (more) issue_w3(0); }
         __syncwarp();
       }
       if (FUSED) {      // the output layer has read the W1 region: the next tile's first chunk may travel (the W3 region holds the output stage)
-        mbar_wait_bounded(&bars[B_HD + 1], (uint32_t)n & 1u);
+        mbar_wait_relaxed(&bars[B_HD + 1], (uint32_t)n & 1u);
         if (more && elect_one()) issue_stem(0);
         __syncwarp();
       }
@@ -675,7 +675,7 @@ tcn_chain_kernel(const __grid_constant__ CUtensorMap tm_w1, const __grid_constan
         __syncwarp();
         if (elect_one()) mbar_arrive(&bars[B_DEP]);
         __syncwarp();
-        mbar_wait_bounded(&bars[B_PUB], it & 1u);      // every epilogue warp has written its c1 rows of block b
+        mbar_wait_relaxed(&bars[B_PUB], it & 1u);      // every epilogue warp has written its c1 rows of block b
         if (has_next && elect_one()) { __threadfence(); red_release_gpu_add(p.flags + tile, 1); }
         __syncwarp();
       }

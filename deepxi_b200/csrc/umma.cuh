@@ -48,41 +48,61 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Same, but a wait that lasts longer than ~2 s of SM clocks is a protocol error (a missed arrival, a producer that never
 // ran): trap, so that the launch fails with an error instead of hanging the GPU.
 constexpr long long SPIN_LIMIT_CYCLES = 4000000000ll;
+constexpr uint32_t MBAR_SUSPEND_NS = 20000u;      // upper bound of one hardware-assisted sleep; the barrier event ends it earlier
 // The retry loop is out of line: a kernel with ~25 waits per iteration would otherwise carry ~300 instructions of it in its hot loop,
 // and these kernels are sensitive to the instruction-cache footprint of that loop.
 #ifdef DXI_ENABLE_DEBUG
 static __device__ int g_mbar_abort = 0;
 #endif
+// SLEEP = false: re-poll at once (a waiter on the critical path: the poll sees the completed phase a few cycles after it happens, but a
+// polling warp takes issue slots - in tcn_chain_kernel 32 % of all executed warp instructions were such polls).
+// SLEEP = true: try_wait WITH a suspend-time hint: ptxas emits TRYWAIT, NANOSLEEP.SYNCS (a sleep that the barrier's phase completion
+// ends) and a re-check, so the waiting warp issues nothing; waking up costs more than a poll (measured: +11 % on the chain kernel when
+// EVERY wait slept), so this is for the warps whose waits are off the critical path (weight loaders, flag agents, operand producers).
+template <bool SLEEP>
 static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) {
   const long long t0 = clock64();
   uint32_t n = 0;
   for (;;) {
     uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar_addr), "r"(parity)
-        : "memory");
+    if (SLEEP) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar_addr), "r"(parity), "r"(MBAR_SUSPEND_NS)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar_addr), "r"(parity)
+          : "memory");
+    }
     if (ok) return;
+    if (!SLEEP && (++n & 1023u) != 0) continue;
 #ifdef DXI_ENABLE_DEBUG
     // tuning build: name the wait that timed out (barrier address inside the CTA's shared window) and give up on it, so that the kernel
     // ends and the message is printed; the launch's results are then meaningless
-    if ((++n & 1023u) == 0) {
-      if (g_mbar_abort) return;
-      if (clock64() - t0 > 200000000ll) {
-        if ((threadIdx.x & 31) == 0) printf("mbarrier wait timed out: block %d warp %d barrier 0x%x parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), bar_addr, parity);
-        if (clock64() - t0 > 260000000ll) { g_mbar_abort = 1; return; }      // a little later, so that every wait stuck at the same time reports
-      }
+    if (g_mbar_abort) return;
+    if (clock64() - t0 > 200000000ll) {
+      if ((threadIdx.x & 31) == 0) printf("mbarrier wait timed out: block %d warp %d barrier 0x%x parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), bar_addr, parity);
+      if (clock64() - t0 > 260000000ll) { g_mbar_abort = 1; return; }      // a little later, so that every wait stuck at the same time reports
     }
 #else
-    if ((++n & 1023u) == 0 && clock64() - t0 > SPIN_LIMIT_CYCLES) __trap();
+    if (clock64() - t0 > SPIN_LIMIT_CYCLES) __trap();
 #endif
   }
 }
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
-  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(smem_u32(bar), parity);
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow<false>(smem_u32(bar), parity);
+}
+// ... for waits off the critical path: the warp sleeps until the barrier's phase completes
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow<true>(smem_u32(bar), parity);
 }
 
 // ---- bulk async copy global -> shared (TMA engine, no tensor map); bytes % 16 == 0 ---------------
