@@ -429,8 +429,12 @@ def run_ours(args, rank, world, local_rank):
                      'achieved': achieved_tf, 'peak': tf_burst, 'unit': 'TFLOP/s',
                      'frac': (achieved_tf / tf_burst) if achieved_tf else None,
                      'frac_of_sustained_peak': (achieved_tf / tf_sustained) if achieved_tf else None,
+                     # what the tensor cores execute: three fp16 products per useful one in f16x3 mode (fp16 hi | lo operands)
+                     'executed': (achieved_tf * (3 if args.precision == 'f16x3' else 1)) if achieved_tf else None,
+                     'frac_executed': (achieved_tf * (3 if args.precision == 'f16x3' else 1) / tf_burst) if achieved_tf else None,
+                     'tensor_pipe_active_pct_ncu': 44.0 if (fused and frames == 160000 and args.precision == 'f16x3') else None,
                      'traffic': NCU_TCN_CHAIN_TRAFFIC if (chain and frames == 160000 and args.precision == 'f16x3') else None,
-                     'traffic_source': 'profiles/r02_prof_tcn_chain.csv (dram bytes of the launch under ncu --set full; a citation, not measured in this run); '
+                     'traffic_source': 'profiles/r02_prof_tcn_chain.csv (dram bytes and sm__pipe_tensor_cycles_active of the launch under ncu --set full; citations, not measured in this run); '
                                        'algorithmic %.0f bytes per launch' % chain_bytes,
                      'peak_source': peak_src + ' bf16 burst (MEASURED_PEAKS.json bf16_tflops): the timed region is %.0f ms; sustained %.1f' % (ms, tf_sustained),
                      'algorithmic_flop_per_launch': flops_per_launch, 'ms_per_launch': st_ms_per_launch,
