@@ -174,6 +174,32 @@ def test_enhanced_speech_fused_vs_oracle(xi_stats, gtype):
         assert di.max() <= 1
 
 
+@pytest.mark.parametrize('int16', [False, True])
+def test_enhance_output_rows_unaligned(xi_stats, int16):
+    """dxi_enhance with an output row pitch that is not a multiple of four samples (and an f32 base 4 bytes off a 16-byte boundary): the
+    kernel then stores one sample at a time instead of four; the samples must be the bits of the aligned call."""
+    mu, sg = xi_stats['resnet-1.1c/mu'], xi_stats['resnet-1.1c/sigma']
+    it = _magxi(xi_stats)
+    lens = [30000, 7777, 256]
+    mag, pha, nfr = it.observation_batch(synth.noisy_speech(3, 30000, seed=81), lens)
+    B, T = mag.shape[0], mag.shape[1]
+    xb = torch.rand((B, T, 257), device='cuda') * 0.98 + 0.01
+    ref = it.enhanced_speech(mag, pha, xb, 'mmse-lsa', n_frames=nfr, int16=int16)
+    n_out = (T + 1) * 256
+    pitch = n_out + 3
+    dt = torch.int16 if int16 else torch.float32
+    buf = torch.zeros(B * pitch + 1, dtype=dt, device='cuda')
+    out = buf[1:]                                   # one element off: 2 / 4 bytes past the allocation's alignment
+    nf = torch.as_tensor(np.asarray(nfr, np.int32)).cuda()
+    mu_d, sg_d = torch.from_numpy(np.asarray(mu, np.float32)).cuda(), torch.from_numpy(np.asarray(sg, np.float32)).cuda()
+    lib = _lib.load()
+    _lib.check(lib.dxi_enhance(_lib.ptr(mag), _lib.ptr(pha), _lib.ptr(xb), _lib.ptr(mu_d), _lib.ptr(sg_d), 0, _lib.ptr(nf, torch.int32), B, T,
+                               None if int16 else out.data_ptr(), out.data_ptr() if int16 else None, pitch, _lib.stream_ptr(mag.device)))
+    torch.cuda.synchronize()
+    got = out[:B * pitch].view(B, pitch)[:, :n_out]
+    assert torch.equal(got, ref)
+
+
 def test_subband_ibm_matches_oracle(xi_stats):
     """xi_hat -> mel-subband a priori SNR -> mask (deepxi/model.py:323-328, sig.py:301-346)."""
     it = inp_tgt_selector('MagXi', 512, 256, 512, 16000, map_type='DBNormalCDF', map_params=None)
