@@ -23,7 +23,7 @@ MASK_MODES = {'none': 0, 'causal+pad': 1}
 SYMBOLS = ['dxi_last_error', 'dxi_host_alloc', 'dxi_host_free', 'dxi_version', 'dxi_device_check', 'dxi_stft', 'dxi_istft', 'dxi_map_gain', 'dxi_gfunc',
            'dxi_cdf_map', 'dxi_deepmmse', 'dxi_enhance', 'dxi_net_create', 'dxi_net_load', 'dxi_net_finalize',
            'dxi_net_workspace_bytes', 'dxi_net_forward', 'dxi_net_destroy', 'dxi_launch_count',
-           'dxi_launch_count_reset', 'dxi_selftest_umma', 'dxi_profile_enable', 'dxi_profile_read',
+           'dxi_launch_count_reset', 'dxi_selftest_umma', 'dxi_selftest_umma_pair', 'dxi_profile_enable', 'dxi_profile_read',
            'dxi_mix_workspace_bytes', 'dxi_mix', 'dxi_xi_map', 'dxi_xi_db_moments', 'dxi_subband_ibm']
 
 
@@ -75,6 +75,7 @@ def load():
     lib.dxi_launch_count.argtypes = []
     lib.dxi_launch_count_reset.restype = None
     lib.dxi_selftest_umma.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    lib.dxi_selftest_umma_pair.argtypes = [vp, vp, i32, vp, vp]
     lib.dxi_profile_enable.argtypes = [i32]
     lib.dxi_profile_enable.restype = None
     lib.dxi_profile_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]

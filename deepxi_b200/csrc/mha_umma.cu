@@ -21,6 +21,10 @@
 // so CS CTAs form a thread-block cluster that walks CS row tiles of the SAME column tile in lock step: each CTA fetches 1 / CS of the
 // weight chunk and multicasts it to all of them (a ring slot is re-filled when the MMAs of ALL CS CTAs on it have committed: the commit
 // arrives on every CTA's barrier).
+// PAIR (CS = 2): the two CTAs run ONE M = 256 product per step (tcgen05.mma.cta_group::2): each converts its own 128 rows of A and fetches
+// only ITS half of the weight chunk (128 of the 256 output columns), the leader CTA issues the MMAs, each keeps its 128 rows of the
+// accumulator.  64 KB instead of 96 KB enter an SM per 1536 tensor cycles - the kernel is bound by exactly that - and the ring holds
+// three slots.  The peer's MMA warp only forwards "my operands of slot s have landed" to the leader's barrier.
 #include <vector>
 #include "net.cuh"
 #include "umma.cuh"
@@ -57,21 +61,23 @@ struct LinArgs {
   unsigned char* kv; int n_kt, n_heads;
 };
 
-template <int CS>
+template <int CS, bool PAIR = false>
 __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g) {      // 13 warps are allocated as 16: 128 registers is the cap
+  static_assert(!PAIR || CS == 2, "a CTA pair is a cluster of two");
+  constexpr int NSLOT = PAIR ? 3 : 2;                              // ring slots
+  constexpr int SLOT = PAIR ? 2 * LA_PART + LW_PART : L_SLOT;      // A hi | A lo | W hi | W lo (PAIR: this CTA's 128 of the 256 weight rows)
+  constexpr int W_LO = PAIR ? LW_PART / 2 : LW_PART;               // bytes from the hi part of the slot's weights to the lo part
   extern __shared__ unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full_a[2], full_w[2], empty[2], acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t full_a[3], full_w[3], empty[3], peer_full[3], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
   unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* sVec = reinterpret_cast<float*>(ring + 2 * L_SLOT);      // bias[256], gamma[256], beta[256] of the column tile
   float* sStage = sVec + 3 * LNT;                                 // [4 warps][32][36]: thread-owns-row <-> warp-writes-row re-ordering of a 32-column chunk
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (warp == L_PROD_WARPS + 4) tmem_alloc(&tmem_slot, 512);
+  if (warp == L_PROD_WARPS + 4) { if (PAIR) tmem_alloc_pair(&tmem_slot, 512); else tmem_alloc(&tmem_slot, 512); }
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&full_a[i], 4); mbar_init(&full_w[i], 1); mbar_init(&empty[i], CS);
-      mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4);
-    }
+    for (int i = 0; i < 3; ++i) { mbar_init(&full_a[i], 4); mbar_init(&full_w[i], 1); mbar_init(&empty[i], PAIR ? 1 : CS); mbar_init(&peer_full[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], PAIR ? 8 : 4); }
     fence_mbar_init();
   }
   tc_fence_before();
@@ -133,14 +139,17 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
     seek();
     load();
     while (t < n_tiles) {
-      const int slot = grp, use = gch >> 1;
+      const int slot = PAIR ? gch % NSLOT : grp, use = PAIR ? gch / NSLOT : gch >> 1;
       const int nt = t % n_nt;
       if (use >= 1) mbar_wait_relaxed(&empty[slot], (use - 1) & 1);       // the MMAs of every CTA of the cluster that read this slot have completed
-      unsigned char* sA = ring + slot * L_SLOT;
+      unsigned char* sA = ring + slot * SLOT;
       if (ptid == 0) {
-        mbar_arrive_expect_tx(&full_w[slot], L_WCHUNK);
+        mbar_arrive_expect_tx(&full_w[slot], PAIR ? LW_PART : L_WCHUNK);
         const unsigned char* src = g.W + ((size_t)nt * n_kc + kc) * L_WCHUNK;
-        if (CS == 1) {
+        if (PAIR) {      // this CTA's 128 of the chunk's 256 weight rows: the second / first half of the hi part and of the lo part
+          bulk_g2s(sA + 2 * LA_PART, src + rank * (LW_PART / 2), LW_PART / 2, &full_w[slot]);
+          bulk_g2s(sA + 2 * LA_PART + LW_PART / 2, src + LW_PART + rank * (LW_PART / 2), LW_PART / 2, &full_w[slot]);
+        } else if (CS == 1) {
           for (int off = 0; off < L_WCHUNK; off += 16384) bulk_g2s(sA + 2 * LA_PART + off, src + off, 16384, &full_w[slot]);
         } else {      // this CTA's share of the chunk, to every CTA of the cluster
           constexpr int share = L_WCHUNK / CS;
@@ -166,30 +175,46 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
     }
   } else if (warp == L_PROD_WARPS + 4) {
     // ================= MMA issue =================
-    constexpr uint32_t idesc = make_idesc_f16(LM, LNT);
+    constexpr uint32_t idesc = make_idesc_f16(PAIR ? 2 * LM : LM, LNT);
     const uint32_t e = elect_leader();      // issue path as in tcn_chain.cu: one election, 32-bit descriptor words in uniform registers
     const uint32_t ring_a = smem_u32(ring);
     int gch = 0, lt = 0;
+    if (PAIR && rank != 0) {
+      // the peer of a CTA pair issues nothing: it tells the leader when its own operands of a slot have landed
+      for (int t = cid; t < n_tiles; t += n_cl)
+        for (int kc = 0; kc < n_kc; ++kc, ++gch) {
+          const int slot = gch % NSLOT, use = gch / NSLOT;
+          mbar_wait_relaxed(&full_a[slot], use & 1);
+          mbar_wait_relaxed(&full_w[slot], use & 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(&peer_full[slot], 0);
+        }
+    } else
     for (int t = cid; t < n_tiles; t += n_cl, ++lt) {
       const int buf = lt & 1, u = lt >> 1;
       if (u >= 1) { mbar_wait_relaxed(&acc_empty[buf], (u - 1) & 1); tc_fence_after(); }      // the epilogue has drained this accumulator
       const uint32_t d_col = 256u * buf;
       for (int kc = 0; kc < n_kc; ++kc, ++gch) {
-        const int slot = gch & 1, use = gch >> 1;
+        const int slot = gch % NSLOT, use = gch / NSLOT;
         mbar_wait_relaxed(&full_a[slot], use & 1);      // the kernel is bound by operand delivery, not by this warp's reaction time:
         mbar_wait_relaxed(&full_w[slot], use & 1);      // sleeping leaves the issue slots to the producers and the epilogue
+        if (PAIR) mbar_wait_relaxed(&peer_full[slot], use & 1);
         tc_fence_after();
-        const uint32_t a32 = desc_lo_sw128(ring_a + slot * L_SLOT), w32 = desc_lo_sw128(ring_a + slot * L_SLOT + 2 * LA_PART);
+        const uint32_t a32 = desc_lo_sw128(ring_a + slot * SLOT), w32 = desc_lo_sw128(ring_a + slot * SLOT + 2 * LA_PART);
 #pragma unroll
         for (int part = 0; part < 3; ++part)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            mma_ss_lo<DESC_HI_SW128, DESC_HI_SW128>(d_col, a32 + (((part == 1 ? LA_PART : 0) + ks * 32) >> 4),
-                                                     w32 + (((part == 2 ? LW_PART : 0) + ks * 32) >> 4), idesc,
-                                                     (kc > 0 || part > 0 || ks > 0) ? 1u : 0u, e);
-        if (CS == 1) mma_commit_lo(&empty[slot], e); else mma_commit_multicast_lo(&empty[slot], cl_mask, e);
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t ad = a32 + (((part == 1 ? LA_PART : 0) + ks * 32) >> 4), wd = w32 + (((part == 2 ? W_LO : 0) + ks * 32) >> 4);
+            const uint32_t acc = (kc > 0 || part > 0 || ks > 0) ? 1u : 0u;
+            if (PAIR) mma_ss_pair_lo<DESC_HI_SW128, DESC_HI_SW128>(d_col, ad, wd, idesc, acc, e);
+            else mma_ss_lo<DESC_HI_SW128, DESC_HI_SW128>(d_col, ad, wd, idesc, acc, e);
+          }
+        if (PAIR) mma_commit_pair_lo(&empty[slot], cl_mask, e);
+        else if (CS == 1) mma_commit_lo(&empty[slot], e);
+        else mma_commit_multicast_lo(&empty[slot], cl_mask, e);
       }
-      mma_commit_lo(&acc_full[buf], e);
+      if (PAIR) mma_commit_pair_lo(&acc_full[buf], cl_mask, e); else mma_commit_lo(&acc_full[buf], e);
     }
   } else {
     // ================= epilogue (warps 8-11: TMEM lane quarter = warp & 3) =================
@@ -380,13 +405,13 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (lane == 0) { if (PAIR && rank != 0) mbar_arrive_remote(&acc_empty[buf], 0); else mbar_arrive(&acc_empty[buf]); }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (CS > 1) cluster_sync_all();      // no CTA leaves while a peer's commit may still arrive on its barriers
-  if (warp == L_PROD_WARPS + 4) tmem_dealloc(0, 512);
+  if (warp == L_PROD_WARPS + 4) { if (PAIR) tmem_dealloc_pair(0, 512); else tmem_dealloc(0, 512); }
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
@@ -456,7 +481,10 @@ static int lin_launch(const LinArgs& g, cudaStream_t st) {
   // 4.85 ms (1), 4.92 ms (2), slower at 4 (fewer SMs fit whole clusters) - the L2 already merges the concurrent reads of a chunk.
   int cs = 1;
   if (const char* e = getenv("DXI_LIN_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) cs = v; }
-  auto kern = cs == 4 ? lin_umma_kernel<4> : cs == 2 ? lin_umma_kernel<2> : lin_umma_kernel<1>;
+  // DXI_LIN_PAIR=1: CTA pairs (tcgen05.mma.cta_group::2, M = 256 per weight fetch)
+  const bool pair = getenv("DXI_LIN_PAIR") && atoi(getenv("DXI_LIN_PAIR")) && n_mt >= 2;
+  if (pair) cs = 2;
+  auto kern = pair ? lin_umma_kernel<2, true> : cs == 4 ? lin_umma_kernel<4> : cs == 2 ? lin_umma_kernel<2> : lin_umma_kernel<1>;
   DXI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L_SMEM));      // per device, so per call
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute at[1];

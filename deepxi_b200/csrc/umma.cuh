@@ -147,6 +147,41 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) 
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// ---- CTA pair (cta_group::2): two CTAs of a cluster on the two SMs of a TPC run ONE MMA of M = 256: each supplies its 128 rows of A and
+// its half of B's N rows from its own shared memory (same offsets in both), the leader CTA issues, each keeps its 128 rows of D.
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier at this offset in every CTA of cta_mask once all MMAs issued so far by this thread have completed
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// arrive on the mbarrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -392,6 +427,23 @@ __device__ __forceinline__ void mma_ss_lo(uint32_t tmem_d, uint32_t a_lo, uint32
   else if (COLL == 2) DXI_MMA_SS_LO(".collector::a::lastuse");
   else DXI_MMA_SS_LO("");
 #undef DXI_MMA_SS_LO
+}
+// The CTA-pair forms of the two above (issued by the leader CTA's elected lane only)
+template <uint32_t A_HI, uint32_t B_HI>
+__device__ __forceinline__ void mma_ss_pair_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate, uint32_t e) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 ad, bd;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "mov.b64 ad, {%1, %6};\n\tmov.b64 bd, {%2, %7};\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], ad, bd, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(e), "n"(A_HI), "n"(B_HI)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_pair_lo(uint64_t* bar, uint16_t cta_mask, uint32_t e) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "h"(cta_mask), "r"(e)
+      : "memory");
 }
 __device__ __forceinline__ void mma_commit_lo(uint64_t* bar, uint32_t e) {
   asm volatile(

@@ -123,6 +123,56 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __grid_constan
 }
 
 
+// CTA-pair self test: D[256, 256] = A[256, K] B[256, K]^T by ONE tcgen05.mma.cta_group::2 sequence.  CTA r of the cluster holds rows
+// 128 r .. of A and rows (n) 128 r .. of B in its own shared memory (128-byte swizzle), the leader issues, each CTA reads its 128 rows.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) umma_pair_selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ Bm,
+                                                                                          int K, float* __restrict__ D) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  unsigned char* sB = smem;                               // K/64 chunks of [128 x 128 B]
+  unsigned char* sA = smem + (size_t)128 * K * 2;         // K/64 chunks of [128 x 128 B]
+  if (warp == 0) tmem_alloc_pair(&tmem_base_slot, 256);
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  for (int i = tid; i < 128 * (K / 8); i += 128) {
+    const int m = i / (K / 8), u = i - m * (K / 8), c = u >> 3, uu = u & 7;
+    const size_t off = (size_t)c * 128 * 128 + (size_t)(m >> 3) * 1024 + (m & 7) * 128 + ((uu ^ (m & 7)) * 16);
+    *reinterpret_cast<uint4*>(sA + off) = *reinterpret_cast<const uint4*>(A + (size_t)(128 * rank + m) * K + 8 * u);
+    *reinterpret_cast<uint4*>(sB + off) = *reinterpret_cast<const uint4*>(Bm + (size_t)(128 * rank + m) * K + 8 * u);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // both CTAs' operands and barriers are in place
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_slot;
+  if (rank == 0 && tid == 0) {
+    const uint32_t idesc = make_idesc_f16(256, 256);
+    for (int k16 = 0; k16 < K / 16; ++k16) {
+      const int c = k16 >> 2, kk = k16 & 3;
+      mma_ss_pair(tbase, make_smem_desc_sw128(smem_u32(sA + (size_t)c * 128 * 128) + kk * 32),
+                  make_smem_desc_sw128(smem_u32(sB + (size_t)c * 128 * 128) + kk * 32), idesc, k16 > 0);
+    }
+    mma_commit_pair(&bar, 3);
+  }
+  mbar_wait_bounded(&bar, 0);
+  tc_fence_after();
+  for (int n0 = 0; n0 < 256; n0 += 32) {
+    float v[32];
+    tmem_ld32(tmem_addr(tbase, (uint32_t)(warp * 32), n0), v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) D[(size_t)(128 * rank + tid) * 256 + n0 + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 0) tmem_dealloc_pair(tbase, 256);
+}
+
 #ifdef DXI_ENABLE_DEBUG
 // TMEM port micro-benchmark: `warps` warps (multiple of 4) each run `rounds` x (tcgen05.ld|st .32x32b.x32) on their
 // lane quarter; out[0] = cycles for the whole CTA (max over warps).  mode 0 = loads, 1 = stores, 2 = load + store.
@@ -258,6 +308,17 @@ extern "C" DXI_API int dxi_debug_tmem_bw(int mode, int warps, int rounds, long l
   return DXI_OK;
 }
 #endif
+
+extern "C" DXI_API int dxi_selftest_umma_pair(const void* a_f16, const void* b_f16, int K, float* d_out, void* stream) {
+  if (int rc = check_device()) return rc;
+  DXI_REQUIRE(a_f16 && b_f16 && d_out, "dxi_selftest_umma_pair: null argument");
+  DXI_REQUIRE(K >= 64 && K <= 256 && K % 64 == 0, "dxi_selftest_umma_pair: K must be a multiple of 64 in [64,256]");
+  const size_t smem = (size_t)2 * 128 * K * 2 + 2048;
+  DXI_CUDA(cudaFuncSetAttribute(umma_pair_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  umma_pair_selftest_kernel<<<2, 128, smem, as_stream(stream)>>>(reinterpret_cast<const __half*>(a_f16), reinterpret_cast<const __half*>(b_f16), K, d_out);
+  DXI_LAUNCHED("umma_pair_selftest_kernel");
+  return DXI_OK;
+}
 
 extern "C" DXI_API int dxi_selftest_umma(const void* a_f16, const void* b_f16, int N, int K, int variant, float* d_out,
                                  void* stream) {

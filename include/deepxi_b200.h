@@ -229,6 +229,9 @@ DXI_API int dxi_profile_read(const char* key, double* total_ms, int64_t* launche
  * under test (0 = the encoding the production kernels use). */
 DXI_API int dxi_selftest_umma(const void* a_f16, const void* b_f16, int N, int K, int variant, float* d_out,
                       void* stream);
+/* The same for the CTA pair (tcgen05.mma.cta_group::2, a cluster of two CTAs on the SMs of one TPC): D[256,256] = A[256,K] * B[256,K]^T;
+ * CTA r holds rows 128 r .. of A and of B, the leader issues, each CTA reads its 128 rows of D. */
+DXI_API int dxi_selftest_umma_pair(const void* a_f16, const void* b_f16, int K, float* d_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -309,6 +309,36 @@ def test_mhanetv3_more_work_items_than_ctas(xi_stats, mask_mode):
     assert np.array_equal(xbar, np.asarray(net(inp)))
 
 
+@pytest.mark.parametrize('K', [64, 256])
+def test_umma_cta_pair_selftest(K):
+    """tcgen05.mma.cta_group::2: a cluster of two CTAs computes D[256, 256] = A[256, K] B[256, K]^T with ONE sequence of M = 256 MMAs issued by
+    the leader; CTA r supplies rows 128 r .. of A and of B (its half of the N dimension) and reads its 128 rows of D."""
+    rng = np.random.default_rng(K)
+    A = rng.standard_normal((256, K)).astype(np.float16)
+    B = rng.standard_normal((256, K)).astype(np.float16)
+    a, b = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+    d = torch.zeros((256, 256), dtype=torch.float32, device='cuda')
+    _lib.check(_lib.load().dxi_selftest_umma_pair(_lib.ptr(a), _lib.ptr(b), K, _lib.ptr(d), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    assert np.abs(d.cpu().numpy() - ref).max() < 1e-3 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize('lens', [[150000, 90000, 33333], [300], [66000] * 5])
+def test_mhanetv3_linear_layers_cta_pairs_agree(lens, monkeypatch):
+    """DXI_LIN_PAIR=1: the linear layers run as CTA pairs (M = 256 per weight fetch, each CTA loads half of every weight chunk, the peer's
+    MMA warp only forwards its readiness).  Same products in the same order: bit-identical to the default, also when the last pair holds a
+    row tile beyond the matrix."""
+    w = weights.synthetic_mhanetv3(7)
+    x = synth.noisy_speech(len(lens), max(lens), seed=68)
+    inp, _, _ = osig.observation_batch(x, lens)
+    net = network_selector('MHANetV3', None, 257, mask_mode='none', precision='f16x3', **MHA_KW).load_weights(w)
+    ref = np.asarray(net(inp))
+    monkeypatch.setenv('DXI_LIN_PAIR', '1')
+    got = np.asarray(net(inp))
+    assert np.isfinite(got).all() and np.array_equal(ref, got)
+
+
 def test_mhanetv3_infer_and_limits(xi_stats):
     w = weights.synthetic_mhanetv3(1)
     dx = DeepXi(512, 256, 512, 16000, 'MagXi', 'MHANetV3', ver='mhanet-1.1c', map_type='DBNormalCDF', map_params=None,
