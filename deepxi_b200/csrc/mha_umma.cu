@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(L_THREADS, 1) lin_umma_kernel(const LinArgs g)
       for (int j = 0; j < 16; ++j) {
         const int r = r0 + 8 * j;
         uint32_t h0, l0, h1, l1;
-        split_h2(v[j].x, v[j].y, h0, l0);
-        split_h2(v[j].z, v[j].w, h1, l1);
+        split_h2x(make_float2(v[j].x, v[j].y), h0, l0);      // hi by truncation (a mask), lo = the exact remainder: 5 instructions per pair, not 7 -
+        split_h2x(make_float2(v[j].z, v[j].w), h1, l1);      // this conversion, repeated for every column tile, is what bounds the kernel
         const uint32_t off = (uint32_t)(r >> 3) * 1024 + (r & 7) * 128 + ((((uint32_t)c4 >> 1) ^ (r & 7)) << 4) + (c4 & 1) * 8;
         *reinterpret_cast<uint2*>(sA + off) = make_uint2(h0, h1);
         *reinterpret_cast<uint2*>(sA + LA_PART + off) = make_uint2(l0, l1);
